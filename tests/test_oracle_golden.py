@@ -1,0 +1,111 @@
+"""Oracle vs the frozen outputs of the reference's own in-tree Python (tests/golden/make_golden.py)."""
+import math
+
+import pytest
+import torch
+
+from oracle import cednerf_ref as cr
+from oracle import nerfacc_ref as nf
+
+FIELD_KW = dict(n_levels=8, log2_hashmap_size=12, dst_resolution=256, moving_step=1.0 / 256)
+FLAG_SETS = {
+    "plain": dict(),
+    "te_ta_df": dict(use_time_embedding=True, use_time_attenuation=True, use_div_offsets=True),
+    "te_after": dict(use_time_embedding=True, time_inject_before_sigma=False),
+}
+
+
+def scene(golden):
+    est = nf.OccGridEstimator([-1.0, -1.0, -1.0, 1.0, 1.0, 1.0], resolution=16, levels=2)
+    est.binaries, est.occs = golden["scene.binaries"], golden["scene.occs"]
+    assert torch.equal(est.aabbs, golden["scene.aabbs"])
+    return est, cr.Rays(golden["scene.origins"], golden["scene.dirs"]), golden["scene.timestamps"]
+
+
+def load_field(golden, name):
+    est, _, _ = scene(golden)
+    field = cr.DNGPradianceField(est.aabbs[-1], **FIELD_KW, **FLAG_SETS[name])
+    sd = {k[len(name) + 7:]: v for k, v in golden.items() if k.startswith(f"{name}.state.")}
+    field.load_state_dict({k: v for k, v in sd.items() if not k.startswith("time_encoder")})
+    return field
+
+
+def test_time_encoders(golden):
+    assert torch.equal(cr.time_embed(golden["enc.t"]), golden["enc.sin"])
+    torch.testing.assert_close(cr.time_embed_attenuated(golden["enc.t"], golden["enc.move"]), golden["enc.sinexp"],
+                               rtol=0, atol=1e-7)
+
+
+def test_trunc_exp(golden):
+    x = golden["texp.x"].clone().requires_grad_(True)
+    y = cr.trunc_exp(x)
+    y.backward(golden["texp.gy"])
+    assert torch.equal(y.detach(), golden["texp.y"]) and torch.equal(x.grad, golden["texp.gx"])
+
+
+def test_rendering_closed_form(golden):
+    sig = golden["rend.sigma"].clone().requires_grad_(True)
+    col = golden["rend.rgb"].clone().requires_grad_(True)
+    c, o, d, ex = cr.rendering(golden["rend.t0"], golden["rend.t1"], golden["rend.ridx"], 6,
+                               lambda a, b, r: (col, {"density": sig[:, None]}), torch.ones(3))
+    ((c * golden["rend.gc"]).sum() + (o * golden["rend.go"]).sum() + (d * golden["rend.gd"]).sum()).backward()
+    for a, b in ((c, "colors"), (o, "opac"), (d, "depth"), (ex["weights"], "weights"), (ex["trans"], "trans"),
+                 (sig.grad, "gsigma"), (col.grad, "grgb")):
+        torch.testing.assert_close(a.detach(), golden[f"rend.{b}"], rtol=1e-6, atol=1e-7)
+    # independent closed form for ray 0
+    s, dt = golden["rend.sigma"][:3].double(), 0.1
+    T = torch.exp(-torch.cumsum(torch.cat([torch.zeros(1, dtype=torch.float64), s[:-1] * dt]), 0))
+    w = T * (1 - torch.exp(-s * dt))
+    torch.testing.assert_close(ex["weights"][:3].double().detach(), w, rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", list(FLAG_SETS))
+def test_field_forward_backward(golden, name):
+    field = load_field(golden, name).train()
+    rgb, res = field(golden[f"{name}.field.pts"], golden[f"{name}.field.t"], golden[f"{name}.field.dirs"])
+    assert torch.equal(rgb.detach(), golden[f"{name}.field.rgb"])
+    assert torch.equal(res["density"].detach(), golden[f"{name}.field.density"])
+    assert torch.equal(res["base_mlp_out"].detach(), golden[f"{name}.field.base_mlp_out"])
+    assert torch.equal(res["interal_output"]["move"].detach(), golden[f"{name}.field.move"])
+    ((rgb * golden[f"{name}.field.grgb"]).sum() + (res["density"] * golden[f"{name}.field.gsig"]).sum()).backward()
+    for k, p in field.named_parameters():
+        key = f"{name}.field.grad.{k}"
+        if key in golden:
+            torch.testing.assert_close(p.grad, golden[key], rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", list(FLAG_SETS))
+def test_render_paths(golden, name):
+    est, rays, ts = scene(golden)
+    field = load_field(golden, name)
+    opts = dict(near_plane=0.2, render_step_size=2e-2, cone_angle=0.004, alpha_thre=1e-2)
+    bkgd = torch.tensor([0.2, 0.5, 0.8])
+    field.train(), est.train()
+    torch.manual_seed(123)
+    rgb, acc, depth, n_s, extra = cr.render_image(field, est, rays, render_bkgd=bkgd, timestamps=ts, **opts)
+    assert n_s == int(golden[f"{name}.train.n_samples"]) and n_s > 200
+    for k in ("ray_indices", "t_starts", "t_ends"):
+        assert torch.equal(extra[0][k], golden[f"{name}.train.{k}"])
+    for a, k in ((rgb, "rgb"), (acc, "acc"), (depth, "depth"), (extra[0]["weights"], "weights"),
+                 (extra[0]["sigmas"], "sigmas")):
+        torch.testing.assert_close(a.detach(), golden[f"{name}.train.{k}"], rtol=1e-6, atol=1e-7)
+    loss = torch.nn.functional.mse_loss(rgb, golden[f"{name}.train.pixels"])
+    (loss * 1024.0).backward()
+    torch.testing.assert_close(loss.detach(), golden[f"{name}.train.loss"], rtol=1e-6, atol=0)
+    for k, p in field.named_parameters():
+        key = f"{name}.train.grad.{k}"
+        if key in golden:
+            torch.testing.assert_close(p.grad, golden[key], rtol=1e-4, atol=1e-9)
+    field.eval(), est.eval()
+    t_frame = torch.tensor([[0.5]])
+    with torch.no_grad():
+        rgb, acc, depth, n_s, _ = cr.render_image(field, est, rays, render_bkgd=bkgd, timestamps=t_frame,
+                                                  test_chunk_size=40, **opts)
+    assert n_s == int(golden[f"{name}.eval.n_samples"])
+    for a, k in ((rgb, "rgb"), (acc, "acc"), (depth, "depth")):
+        torch.testing.assert_close(a, golden[f"{name}.eval.{k}"], rtol=1e-6, atol=1e-7)
+    rgb, acc, depth, n_s = cr.render_image_test(64, field, est, rays, render_bkgd=bkgd, timestamps=t_frame, **opts)
+    assert n_s == int(golden[f"{name}.test.n_samples"]) and n_s > 100
+    for a, k in ((rgb, "rgb"), (acc, "acc"), (depth, "depth")):
+        torch.testing.assert_close(a, golden[f"{name}.test.{k}"], rtol=1e-6, atol=1e-7)
+    assert float(acc.max()) > 0.5  # the synthetic density really occludes
