@@ -1,0 +1,125 @@
+"""ctypes binding of libcednerf_b200.so (include/cednerf_b200.h).
+
+The library is the product: there is no CPU or PyTorch fallback.  If the shared object is missing the
+import fails loudly with the build command; every op additionally refuses non-CUDA tensors.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcednerf_b200.so")
+
+MAX_LEVELS = 32
+MLP_MAX_LAYERS = 5
+
+
+class GridLevels(ctypes.Structure):
+    _fields_ = [("n_levels", ctypes.c_int), ("scale", ctypes.c_float * MAX_LEVELS),
+                ("res", ctypes.c_uint32 * MAX_LEVELS), ("size", ctypes.c_uint32 * MAX_LEVELS),
+                ("offset", ctypes.c_uint32 * MAX_LEVELS), ("hashed", ctypes.c_uint32 * MAX_LEVELS)]
+
+
+class MlpDesc(ctypes.Structure):
+    _fields_ = [("n_layers", ctypes.c_int), ("dim_in", ctypes.c_int * MLP_MAX_LAYERS),
+                ("dim_out", ctypes.c_int * MLP_MAX_LAYERS), ("param_off", ctypes.c_int * MLP_MAX_LAYERS),
+                ("image_off", ctypes.c_int * MLP_MAX_LAYERS), ("image_bytes", ctypes.c_int)]
+
+
+# p = pointer, i = int, l = int64, f = float, G = GridLevels*, M = MlpDesc*
+_SIGNATURES = {
+    "cednerf_ray_aabb_intersect": "pplpifffpppp",
+    "cednerf_sort_boundaries": "pplippp",
+    "cednerf_occ_pack_bits": "plpp",
+    "cednerf_occ_threshold_pack": "plpppp",
+    "cednerf_march": "ipplppiippffffipppppppppppppppppppp",
+    "cednerf_exclusive_scan": "plppppp",
+    "cednerf_hashgrid_fwd": "pilpGpip",
+    "cednerf_hashgrid_bwd": "pilpGpiippp",
+    "cednerf_hashgrid4d_fwd": "pilpGpiip",
+    "cednerf_hashgrid4d_bwd": "pilGpiipip",
+    "cednerf_cast_f32_to_f16": "pplp",
+    "cednerf_frequency_fwd": "pilipiifp",
+    "cednerf_frequency_bwd": "pilipiipp",
+    "cednerf_sh2_fwd": "plpip",
+    "cednerf_time_embed": "pplpp",
+    "cednerf_mlp_pack_weights": "pMpp",
+    "cednerf_mlp_fwd": "ppMlppp",
+    "cednerf_mlp_bwd": "ppppMlpipp",
+    "cednerf_ray_offsets": "pllpp",
+    "cednerf_composite_fwd": "pppppppillpppppppifp",
+    "cednerf_composite_bwd": "pppppppillppppppppppfp",
+    "cednerf_visibility_mask": "ppppllffpp",
+    "cednerf_accumulate_fwd": "ppipllpip",
+    "cednerf_accumulate_bwd": "ppiplpppp",
+}
+_CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_int64, "f": ctypes.c_float,
+       "G": ctypes.POINTER(GridLevels), "M": ctypes.POINTER(MlpDesc)}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `make -C cednerf_b200/csrc` (or `python -c 'import "
+            "__graft_entry__ as g; g.build()'`).  cednerf_b200 has no CPU / PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.cednerf_last_error.restype = ctypes.c_char_p
+    lib.cednerf_scan_workspace_bytes.restype = ctypes.c_int64
+    lib.cednerf_scan_workspace_bytes.argtypes = [ctypes.c_int64]
+    for name, sig in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = ctypes.c_int
+        fn.argtypes = [_CT[c] for c in sig]
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return sorted(list(_SIGNATURES) + ["cednerf_last_error", "cednerf_abi_version", "cednerf_check_device",
+                                       "cednerf_scan_workspace_bytes"])
+
+
+def ptr(t: Optional[torch.Tensor]):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("cednerf_b200 ops need CUDA tensors (no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("cednerf_b200 ops need contiguous tensors")
+    return t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name: str, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {lib.cednerf_last_error().decode()}")
+
+
+_device_checked = False
+
+
+def check_device():
+    global _device_checked
+    if not _device_checked:
+        lib = load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("cednerf_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        rc = lib.cednerf_check_device()
+        if rc != 0:
+            raise RuntimeError(f"cednerf_check_device failed ({rc}): {lib.cednerf_last_error().decode()}")
+        _device_checked = True

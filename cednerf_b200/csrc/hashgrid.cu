@@ -1,0 +1,313 @@
+// K2 — multi-resolution hash-grid encode (3-D, and 4-D xyz+t key-frame variant) and backward.
+//
+// Same algorithm as the spatial encoder the reference executes through tcnn.Encoding(HashGrid)
+// (cednerf/model.py:242-252, :384) and spells out in-tree in
+//   cednerf/taichi_kernel/hash_encoder_half.py:66-103 (index / scale), :112-161 (fwd), :164-226 (bwd)
+//   cednerf/taichi_kernel/hash_encoder_inter.py:121-199 (4-D fwd), :202-275 (4-D bwd)
+// One thread per (sample, level), level fastest, so a sample's 2*L features are written as one
+// contiguous run and its xyz is a warp broadcast.  All 8 corner gathers are issued before use.
+// Numerics shared with oracle/tcnn_ref.py: pos = x*scale (+) 0.5 as two rounded fp32 ops, fp32
+// trilinear weights in corner-bit order, fp16 table, fp32 accumulate, one rounding to fp16 on output.
+#include "common.cuh"
+
+#define CEDNERF_MAX_LEVELS 32
+
+struct CednerfGridLevels {
+  int n_levels;
+  float scale[CEDNERF_MAX_LEVELS];
+  uint32_t res[CEDNERF_MAX_LEVELS];
+  uint32_t size[CEDNERF_MAX_LEVELS];
+  uint32_t offset[CEDNERF_MAX_LEVELS];
+  uint32_t hashed[CEDNERF_MAX_LEVELS];
+};
+
+namespace {
+
+__device__ __forceinline__ uint32_t corner_index(uint32_t gx, uint32_t gy, uint32_t gz, uint32_t res, uint32_t size,
+                                                 bool hashed) {
+  uint32_t h = hashed ? (gx ^ (gy * 2654435761u) ^ (gz * 805459861u)) : (gx + gy * res + gz * res * res);
+  return h % size;
+}
+
+struct Cell {
+  uint32_t g[3];
+  float f[3];
+};
+
+__device__ __forceinline__ Cell locate(const float* __restrict__ x, float scale) {
+  Cell c;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const float pos = __fadd_rn(__fmul_rn(x[d], scale), 0.5f);
+    const float fl = floorf(pos);
+    c.f[d] = __fsub_rn(pos, fl);
+    c.g[d] = (uint32_t)(int)fl;
+  }
+  return c;
+}
+
+__device__ __forceinline__ float corner_weight(const Cell& c, int corner) {
+  float w = 1.f;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) w = __fmul_rn(w, (corner >> d) & 1 ? c.f[d] : __fsub_rn(1.f, c.f[d]));
+  return w;
+}
+
+// key-frame selection of the 4-D variant: ts = 3t, k = min(floor(ts), 2), tau = ts - k
+// (taichi_compat: tau taken before the clamp, hash_encoder_inter.py:151-160)
+__device__ __forceinline__ void keyframe(float t, int taichi_compat, int& k, float& tau) {
+  const float ts = __fmul_rn(t, 3.f);
+  float kf = floorf(ts);
+  if (taichi_compat) {
+    tau = __fsub_rn(ts, kf);
+    kf = fminf(kf, 2.f);
+  } else {
+    kf = fminf(kf, 2.f);
+    tau = __fsub_rn(ts, kf);
+  }
+  k = (int)kf;
+}
+
+template <bool FOUR_D>
+__global__ void __launch_bounds__(256)
+hashgrid_fwd_kernel(const float* __restrict__ x, int x_stride, int64_t n, const __half* __restrict__ table,
+                    CednerfGridLevels lv, __half* __restrict__ out, int out_stride, int taichi_compat) {
+  const int L = lv.n_levels;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t s = tid / L;
+  const int l = (int)(tid - s * L);
+  if (s >= n) return;
+  const float* xs = x + s * x_stride;
+  const Cell c = locate(xs, lv.scale[l]);
+  const uint32_t res = lv.res[l], size = lv.size[l], off = lv.offset[l];
+  const bool hashed = lv.hashed[l] != 0;
+  uint32_t idx[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    idx[k] = off + corner_index(c.g[0] + (k & 1), c.g[1] + ((k >> 1) & 1), c.g[2] + ((k >> 2) & 1), res, size, hashed);
+  float a0 = 0.f, a1 = 0.f;
+  if (!FOUR_D) {
+    __half2 v[8];
+    const __half2* t2 = reinterpret_cast<const __half2*>(table);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __ldg(t2 + idx[k]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float w = corner_weight(c, k);
+      const float2 f = __half22float2(v[k]);
+      a0 = __fadd_rn(a0, __fmul_rn(w, f.x));
+      a1 = __fadd_rn(a1, __fmul_rn(w, f.y));
+    }
+  } else {
+    int kf;
+    float tau;
+    keyframe(xs[3], taichi_compat, kf, tau);
+    const float om = __fsub_rn(1.f, tau);
+    uint4 v[8];
+    const uint4* t8 = reinterpret_cast<const uint4*>(table);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __ldg(t8 + idx[k]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t words[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+      const uint32_t lo_w = words[kf], hi_w = words[kf + 1];
+      const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&lo_w));
+      const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&hi_w));
+      const float w = corner_weight(c, k);
+      a0 = __fadd_rn(a0, __fmul_rn(w, __fadd_rn(__fmul_rn(lo.x, om), __fmul_rn(hi.x, tau))));
+      a1 = __fadd_rn(a1, __fmul_rn(w, __fadd_rn(__fmul_rn(lo.y, om), __fmul_rn(hi.y, tau))));
+    }
+  }
+  *reinterpret_cast<__half2*>(out + s * out_stride + 2 * l) = __floats2half2_rn(a0, a1);
+}
+
+// Backward: table gradient (fp32 vector reductions, red.global.add.v2.f32) and, for the 3-D encoder,
+// the input gradient dL/dx_d = scale_l * sum_corners (+-) prod_{e != d} w_e * <table[idx], dy_l>
+// (tcnn's kernel_grid_backward_input form; the in-tree Taichi form w/(+-f) is 0/0 on cell faces).
+template <bool FOUR_D, typename GradT>
+__global__ void __launch_bounds__(256)
+hashgrid_bwd_kernel(const float* __restrict__ x, int x_stride, int64_t n, const __half* __restrict__ table,
+                    CednerfGridLevels lv, const GradT* __restrict__ dy, int dy_stride, float* __restrict__ g_table,
+                    float* __restrict__ g_x, int taichi_compat) {
+  const int L = lv.n_levels;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t s = tid / L;
+  const int l = (int)(tid - s * L);
+  const bool active = s < n;
+  if (!active) s = n - 1;  // keep the lane alive for the shuffles below
+  const float* xs = x + s * x_stride;
+  const Cell c = locate(xs, lv.scale[l]);
+  const uint32_t res = lv.res[l], size = lv.size[l], off = lv.offset[l];
+  const bool hashed = lv.hashed[l] != 0;
+  float d0 = 0.f, d1 = 0.f;
+  if (active) {
+    d0 = (float)dy[s * dy_stride + 2 * l];
+    d1 = (float)dy[s * dy_stride + 2 * l + 1];
+  }
+  uint32_t idx[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    idx[k] = off + corner_index(c.g[0] + (k & 1), c.g[1] + ((k >> 1) & 1), c.g[2] + ((k >> 2) & 1), res, size, hashed);
+
+  if (FOUR_D) {
+    if (!active || (d0 == 0.f && d1 == 0.f)) return;
+    int kf;
+    float tau;
+    keyframe(xs[3], taichi_compat, kf, tau);
+    const float om = 1.f - tau;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float w = corner_weight(c, k);
+      float2* dst = reinterpret_cast<float2*>(g_table + (size_t)idx[k] * 8 + 2 * kf);
+      atomicAdd(dst, make_float2(w * d0 * om, w * d1 * om));
+      atomicAdd(dst + 1, make_float2(w * d0 * tau, w * d1 * tau));
+    }
+    return;
+  }
+
+  float gx[3] = {0.f, 0.f, 0.f};
+  if (g_x) {
+    __half2 v[8];
+    const __half2* t2 = reinterpret_cast<const __half2*>(table);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __ldg(t2 + idx[k]);
+    float dot[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float2 f = __half22float2(v[k]);
+      dot[k] = f.x * d0 + f.y * d1;
+    }
+    const float fx = c.f[0], fy = c.f[1], fz = c.f[2];
+    const float wx[2] = {1.f - fx, fx}, wy[2] = {1.f - fy, fy}, wz[2] = {1.f - fz, fz};
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        gx[0] += wy[a] * wz[b] * (dot[1 + 2 * a + 4 * b] - dot[0 + 2 * a + 4 * b]);
+        gx[1] += wx[a] * wz[b] * (dot[a + 2 + 4 * b] - dot[a + 0 + 4 * b]);
+        gx[2] += wx[a] * wy[b] * (dot[a + 2 * b + 4] - dot[a + 2 * b]);
+      }
+    const float sc = lv.scale[l];
+    gx[0] *= sc;
+    gx[1] *= sc;
+    gx[2] *= sc;
+    if (!active) gx[0] = gx[1] = gx[2] = 0.f;
+  }
+  if (g_table && active && (d0 != 0.f || d1 != 0.f)) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float w = corner_weight(c, k);
+      atomicAdd(reinterpret_cast<float2*>(g_table) + idx[k], make_float2(w * d0, w * d1));
+    }
+  }
+  if (g_x) {
+    if (L == 8 || L == 16 || L == 32) {  // the L lanes of a sample are contiguous in the warp
+      for (int o = L / 2; o > 0; o >>= 1) {
+        gx[0] += __shfl_xor_sync(0xffffffffu, gx[0], o);
+        gx[1] += __shfl_xor_sync(0xffffffffu, gx[1], o);
+        gx[2] += __shfl_xor_sync(0xffffffffu, gx[2], o);
+      }
+      if (active && l == 0) {
+        g_x[3 * s] = gx[0];
+        g_x[3 * s + 1] = gx[1];
+        g_x[3 * s + 2] = gx[2];
+      }
+    } else if (active) {  // caller zero-fills g_x
+      atomicAdd(g_x + 3 * s, gx[0]);
+      atomicAdd(g_x + 3 * s + 1, gx[1]);
+      atomicAdd(g_x + 3 * s + 2, gx[2]);
+    }
+  }
+}
+
+__global__ void cast_f32_to_f16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, int64_t n4,
+                                       const float* __restrict__ src_tail, __half* __restrict__ dst_tail, int tail) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n4) {
+    const float4 v = src[i];
+    __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&a);
+    o.y = *reinterpret_cast<uint32_t*>(&b);
+    dst[i] = o;
+  }
+  if (i < tail) dst_tail[i] = __float2half_rn(src_tail[i]);
+}
+
+int check_levels(const CednerfGridLevels* lv) {
+  if (!lv || lv->n_levels < 1 || lv->n_levels > CEDNERF_MAX_LEVELS) return 0;
+  for (int l = 0; l < lv->n_levels; ++l)
+    if (lv->size[l] == 0) return 0;
+  return 1;
+}
+
+}  // namespace
+
+CEDNERF_EXPORT int cednerf_hashgrid_fwd(const float* x, int x_stride, int64_t n, const void* table_f16,
+                                        const CednerfGridLevels* levels, void* out_f16, int out_stride,
+                                        void* stream) {
+  CEDNERF_REQUIRE(check_levels(levels), "bad level table");
+  CEDNERF_REQUIRE(n >= 0 && x_stride >= 3 && out_stride >= 2 * levels->n_levels && (out_stride % 2) == 0, "bad sizes");
+  if (n == 0) return 0;
+  hashgrid_fwd_kernel<false><<<cednerf_blocks(n * levels->n_levels, 256), 256, 0, (cudaStream_t)stream>>>(
+      x, x_stride, n, (const __half*)table_f16, *levels, (__half*)out_f16, out_stride, 0);
+  return cednerf_check_launch("cednerf_hashgrid_fwd");
+}
+
+CEDNERF_EXPORT int cednerf_hashgrid_bwd(const float* x, int x_stride, int64_t n, const void* table_f16,
+                                        const CednerfGridLevels* levels, const void* dy, int dy_stride,
+                                        int dy_is_f16, float* g_table, float* g_x, void* stream) {
+  CEDNERF_REQUIRE(check_levels(levels), "bad level table");
+  CEDNERF_REQUIRE(n >= 0 && x_stride >= 3 && dy_stride >= 2 * levels->n_levels, "bad sizes");
+  CEDNERF_REQUIRE(g_table || g_x, "nothing to compute");
+  if (n == 0) return 0;
+  dim3 grid(cednerf_blocks(n * levels->n_levels, 256));
+  if (dy_is_f16)
+    hashgrid_bwd_kernel<false, __half><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        x, x_stride, n, (const __half*)table_f16, *levels, (const __half*)dy, dy_stride, g_table, g_x, 0);
+  else
+    hashgrid_bwd_kernel<false, float><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        x, x_stride, n, (const __half*)table_f16, *levels, (const float*)dy, dy_stride, g_table, g_x, 0);
+  return cednerf_check_launch("cednerf_hashgrid_bwd");
+}
+
+CEDNERF_EXPORT int cednerf_hashgrid4d_fwd(const float* xyzt, int x_stride, int64_t n, const void* table_f16,
+                                          const CednerfGridLevels* levels, void* out_f16, int out_stride,
+                                          int taichi_compat, void* stream) {
+  CEDNERF_REQUIRE(check_levels(levels), "bad level table");
+  CEDNERF_REQUIRE(n >= 0 && x_stride >= 4 && out_stride >= 2 * levels->n_levels && (out_stride % 2) == 0, "bad sizes");
+  CEDNERF_REQUIRE(((uintptr_t)table_f16 & 15) == 0, "4-D table must be 16-byte aligned");
+  if (n == 0) return 0;
+  hashgrid_fwd_kernel<true><<<cednerf_blocks(n * levels->n_levels, 256), 256, 0, (cudaStream_t)stream>>>(
+      xyzt, x_stride, n, (const __half*)table_f16, *levels, (__half*)out_f16, out_stride, taichi_compat);
+  return cednerf_check_launch("cednerf_hashgrid4d_fwd");
+}
+
+CEDNERF_EXPORT int cednerf_hashgrid4d_bwd(const float* xyzt, int x_stride, int64_t n, const CednerfGridLevels* levels,
+                                          const void* dy, int dy_stride, int dy_is_f16, float* g_table,
+                                          int taichi_compat, void* stream) {
+  CEDNERF_REQUIRE(check_levels(levels), "bad level table");
+  CEDNERF_REQUIRE(n >= 0 && x_stride >= 4 && dy_stride >= 2 * levels->n_levels && g_table, "bad sizes");
+  if (n == 0) return 0;
+  dim3 grid(cednerf_blocks(n * levels->n_levels, 256));
+  if (dy_is_f16)
+    hashgrid_bwd_kernel<true, __half><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        xyzt, x_stride, n, nullptr, *levels, (const __half*)dy, dy_stride, g_table, nullptr, taichi_compat);
+  else
+    hashgrid_bwd_kernel<true, float><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        xyzt, x_stride, n, nullptr, *levels, (const float*)dy, dy_stride, g_table, nullptr, taichi_compat);
+  return cednerf_check_launch("cednerf_hashgrid4d_bwd");
+}
+
+// fp32 master parameters -> fp16 working copy (the reference does this cast on every forward,
+// hash_encoder_half.py:381-385; here it runs once per parameter version)
+CEDNERF_EXPORT int cednerf_cast_f32_to_f16(const float* src, void* dst_f16, int64_t n, void* stream) {
+  CEDNERF_REQUIRE(n >= 0, "bad size");
+  if (n == 0) return 0;
+  const int64_t n4 = n / 4;
+  const int tail = (int)(n - n4 * 4);
+  CEDNERF_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst_f16 & 7) == 0, "unaligned buffers");
+  cast_f32_to_f16_kernel<<<cednerf_blocks(n4 > tail ? n4 : tail, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const float4*)src, (uint2*)dst_f16, n4, src + n4 * 4, (__half*)dst_f16 + n4 * 4, tail);
+  return cednerf_check_launch("cednerf_cast_f32_to_f16");
+}

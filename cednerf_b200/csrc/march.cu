@@ -1,0 +1,499 @@
+// K1 — occupancy-grid ray marching (count -> device scan -> fill), ray/aabb slab test and boundary sort.
+//
+// Same per-ray algorithm as the nerfacc calls the reference makes:
+//   ray_aabb_intersect   cednerf/utils.py:215
+//   sort of boundaries   cednerf/utils.py:219-225
+//   traverse_grids       cednerf/utils.py:241-264 (eval: steps limit + over-allocate + ray mask),
+//                        and inside OccGridEstimator.sampling, cednerf/utils.py:115-125 (train: two pass)
+// restated in SURVEY.md Appendix A.4-A.6.  This translation unit is compiled with -fmad=false: every
+// fp32 operation is individually rounded in the order oracle/march_oracle.c fixes, which is what makes
+// per-ray sample counts, ray_indices and the packed t values bit-comparable with the oracle.
+// Occupancy is read from a bit-packed copy of `binaries` (1 bit/cell, same x*R*R+y*R+z order): 1 MB for
+// 4x128^3, L1/L2 resident.  One thread per ray; per-ray counts are turned into packed offsets by a
+// three-kernel device scan so that no host round trip sits between count and fill.
+#include "common.cuh"
+
+#define MARCH_MAX_LEVELS 8
+
+namespace {
+
+struct MarchArgs {
+  const float* rays_o;
+  const float* rays_d;
+  int64_t n_rays;
+  const uint32_t* occ_bits;
+  const float* aabbs;  // [L,6]
+  int n_levels;
+  int res;
+  const float* near;  // [n] or null -> near_const
+  const float* far;   // [n] or null -> far_const
+  float near_const, far_const;
+  float step_size, cone_angle;
+  int limit;
+  const uint8_t* mask;       // [n] or null
+  const float* t_sorted;     // [n,2L] or null (computed in-kernel)
+  const int64_t* t_indices;  // [n,2L] or null
+  const uint8_t* hits;       // [n,L] or null
+  // fill-pass inputs
+  const int64_t* iv_starts;
+  const int64_t* sm_starts;
+  // nerfacc-shaped outputs (nullable)
+  float* iv_vals;
+  uint8_t* iv_left;
+  uint8_t* iv_right;
+  int64_t* iv_ray;
+  float* sm_vals;
+  int64_t* sm_ray;
+  uint8_t* sm_valid;
+  // packed outputs (nullable)
+  float* t_starts;
+  float* t_ends;
+  int64_t* ray_indices;
+  // per-ray outputs (nullable)
+  int32_t* n_intervals;
+  int32_t* n_samples;
+  float* termination;
+};
+
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+__device__ __forceinline__ float step_dt(float t, float cone, float step) { return clampf(t * cone, step, 1e10f); }
+
+__device__ __forceinline__ void slab(const float* o, const float* inv, const float* bx, float near, float far,
+                                     float miss, float& t_min, float& t_max, bool& hit) {
+  float tmin = -INFINITY, tmax = INFINITY;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float t1 = (bx[a] - o[a]) * inv[a];
+    const float t2 = (bx[3 + a] - o[a]) * inv[a];
+    tmin = fmaxf(tmin, fminf(t1, t2));
+    tmax = fminf(tmax, fmaxf(t1, t2));
+  }
+  hit = (tmax > tmin) && (tmax > 0.0f);
+  t_min = hit ? clampf(tmin, near, far) : miss;
+  t_max = hit ? clampf(tmax, near, far) : miss;
+}
+
+__global__ void ray_aabb_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, int64_t n,
+                                const float* __restrict__ aabbs, int L, float near, float far, float miss,
+                                float* __restrict__ t_mins, float* __restrict__ t_maxs, uint8_t* __restrict__ hits) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const float o[3] = {rays_o[3 * r], rays_o[3 * r + 1], rays_o[3 * r + 2]};
+  const float inv[3] = {1.0f / rays_d[3 * r], 1.0f / rays_d[3 * r + 1], 1.0f / rays_d[3 * r + 2]};
+  for (int l = 0; l < L; ++l) {
+    float a, b;
+    bool h;
+    slab(o, inv, aabbs + 6 * l, near, far, miss, a, b, h);
+    t_mins[r * L + l] = a;
+    t_maxs[r * L + l] = b;
+    hits[r * L + l] = (uint8_t)h;
+  }
+}
+
+// stable insertion sort of the 2L boundary values (ties keep the lower original slot)
+__device__ __forceinline__ void sort_bounds(float* v, int* id, int m) {
+  for (int i = 1; i < m; ++i) {
+    const float kv = v[i];
+    const int ki = id[i];
+    int j = i - 1;
+    while (j >= 0 && v[j] > kv) {
+      v[j + 1] = v[j];
+      id[j + 1] = id[j];
+      --j;
+    }
+    v[j + 1] = kv;
+    id[j + 1] = ki;
+  }
+}
+
+__global__ void sort_boundaries_kernel(const float* __restrict__ t_mins, const float* __restrict__ t_maxs, int64_t n,
+                                       int L, float* __restrict__ t_sorted, int64_t* __restrict__ t_indices) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  float v[2 * MARCH_MAX_LEVELS];
+  int id[2 * MARCH_MAX_LEVELS];
+  const int m = 2 * L;
+  for (int l = 0; l < L; ++l) {
+    v[l] = t_mins[r * L + l];
+    v[L + l] = t_maxs[r * L + l];
+  }
+  for (int i = 0; i < m; ++i) id[i] = i;
+  sort_bounds(v, id, m);
+  for (int i = 0; i < m; ++i) {
+    t_sorted[r * m + i] = v[i];
+    t_indices[r * m + i] = id[i];
+  }
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(128) march_kernel(MarchArgs a) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.n_rays) return;
+  const float near = a.near ? a.near[r] : a.near_const;
+  const float far = a.far ? a.far[r] : a.far_const;
+  if (a.mask && !a.mask[r]) {
+    if (a.n_intervals) a.n_intervals[r] = 0;
+    if (a.n_samples) a.n_samples[r] = 0;
+    if (a.termination) a.termination[r] = near;
+    return;
+  }
+  const int L = a.n_levels, m = 2 * L, res = a.res;
+  const float eps = 1e-6f;
+  const float o[3] = {a.rays_o[3 * r], a.rays_o[3 * r + 1], a.rays_o[3 * r + 2]};
+  const float d[3] = {a.rays_d[3 * r], a.rays_d[3 * r + 1], a.rays_d[3 * r + 2]};
+  const float inv[3] = {1.0f / d[0], 1.0f / d[1], 1.0f / d[2]};
+  const float fres = (float)res;
+  const int64_t cells_per_level = (int64_t)res * res * res;
+
+  float ts[2 * MARCH_MAX_LEVELS];
+  int ti[2 * MARCH_MAX_LEVELS];
+  bool hit[MARCH_MAX_LEVELS];
+  if (a.t_sorted) {
+    for (int i = 0; i < m; ++i) {
+      ts[i] = a.t_sorted[r * m + i];
+      ti[i] = (int)a.t_indices[r * m + i];
+    }
+    for (int l = 0; l < L; ++l) hit[l] = a.hits[r * L + l] != 0;
+  } else {
+    for (int l = 0; l < L; ++l) slab(o, inv, a.aabbs + 6 * l, -INFINITY, INFINITY, INFINITY, ts[l], ts[L + l], hit[l]);
+    for (int i = 0; i < m; ++i) ti[i] = i;
+    sort_bounds(ts, ti, m);
+  }
+
+  const int64_t iv_base = FILL && a.iv_starts ? a.iv_starts[r] : 0;
+  const int64_t sm_base = FILL && a.sm_starts ? a.sm_starts[r] : 0;
+  int n_iv = 0, n_sm = 0;
+  float t_last = near;
+  bool continuous = false;
+  const int limit = a.limit;
+  const float step_size = a.step_size, cone = a.cone_angle;
+
+  for (int i = 0; i < m - 1; ++i) {
+    const int bi = ti[i];
+    const bool entering = bi < L;
+    int level = bi % L;
+    if (!hit[level]) continue;
+    if (!entering) {
+      const int bn = ti[i + 1];
+      if (bn < L) continue;  // gap between boxes
+      level = bn % L;
+      if (!hit[level]) continue;
+    }
+    const float this_tmin = fmaxf(ts[i], near);
+    const float this_tmax = fminf(ts[i + 1], far);
+    if (this_tmin >= this_tmax) continue;
+
+    if (!continuous) {
+      if (step_size <= 0.0f) {
+        t_last = this_tmin;
+      } else {
+        for (;;) {
+          const float dt = step_dt(t_last, cone, step_size);
+          if (t_last + dt * 0.5f >= this_tmin) break;
+          t_last += dt;
+        }
+      }
+    }
+
+    const float* bx = a.aabbs + 6 * level;
+    float tdist[3], delta[3];
+    int cur[3], overflow[3], stepi[3];
+    const float tstart = this_tmin + eps, tend = this_tmax - eps;
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+      const float extent = bx[3 + ax] - bx[ax];
+      const float voxel = extent / fres;
+      const float start = o[ax] + d[ax] * tstart;
+      const float end = o[ax] + d[ax] * tend;
+      int c = (int)(((start - bx[ax]) / extent) * fres);
+      int f = (int)(((end - bx[ax]) / extent) * fres);
+      c = clampi(c, 0, res - 1);
+      f = clampi(f, 0, res - 1);
+      const int start_idx = c + (d[ax] > 0.0f ? 1 : 0);
+      const float tmax_a = ((bx[ax] + (((float)start_idx * voxel) - start)) * inv[ax]) + this_tmin;
+      const float stepf = (d[ax] == 0.0f) ? 0.0f : (d[ax] > 0.0f ? 1.0f : -1.0f);
+      tdist[ax] = (d[ax] == 0.0f) ? this_tmax : tmax_a;
+      delta[ax] = (d[ax] == 0.0f) ? this_tmax : (voxel * inv[ax]) * stepf;
+      stepi[ax] = (int)stepf;
+      cur[ax] = c;
+      overflow[ax] = f + stepi[ax];
+    }
+
+    while (limit <= 0 || n_sm < limit) {
+      const float t_trav = fminf(fminf(tdist[0], fminf(tdist[1], tdist[2])), this_tmax);
+      const int64_t cell = (int64_t)cur[0] * res * res + (int64_t)cur[1] * res + cur[2] + level * cells_per_level;
+      const bool occupied = (__ldg(a.occ_bits + (cell >> 5)) >> (cell & 31)) & 1u;
+      if (!occupied) {
+        if (step_size <= 0.0f) {
+          t_last = t_trav;
+        } else {
+          for (;;) {
+            const float dt = step_dt(t_last, cone, step_size);
+            if (t_last + dt * 0.5f >= t_trav) break;
+            t_last += dt;
+          }
+        }
+        continuous = false;
+      } else {
+        while (limit <= 0 || n_sm < limit) {
+          float t_next;
+          if (step_size <= 0.0f) {
+            t_next = t_trav;
+          } else {
+            const float dt = step_dt(t_last, cone, step_size);
+            if (t_last + dt * 0.5f >= t_trav) break;
+            t_next = t_last + dt;
+          }
+          if (FILL) {
+            if (a.iv_vals) {
+              const int64_t k = iv_base + n_iv;
+              if (!continuous) {
+                a.iv_vals[k] = t_last;
+                a.iv_ray[k] = r;
+                a.iv_left[k] = 1;
+                a.iv_vals[k + 1] = t_next;
+                a.iv_ray[k + 1] = r;
+                a.iv_right[k + 1] = 1;
+              } else {
+                a.iv_vals[k] = t_next;
+                a.iv_ray[k] = r;
+                a.iv_left[k - 1] = 1;
+                a.iv_right[k] = 1;
+              }
+            }
+            const int64_t k = sm_base + n_sm;
+            if (a.sm_vals) {
+              a.sm_vals[k] = (t_next + t_last) * 0.5f;
+              a.sm_ray[k] = r;
+              a.sm_valid[k] = 1;
+            }
+            if (a.t_starts) {
+              a.t_starts[k] = t_last;
+              a.t_ends[k] = t_next;
+              a.ray_indices[k] = r;
+            }
+          }
+          n_iv += continuous ? 1 : 2;
+          n_sm += 1;
+          continuous = true;
+          t_last = t_next;
+          if (t_next >= t_trav) break;
+        }
+      }
+      const int ax = (tdist[0] < tdist[1] && tdist[0] < tdist[2]) ? 0 : (tdist[1] < tdist[2] ? 1 : 2);
+      // register-friendly equivalent of cur[ax] += step[ax]; tdist[ax] += delta[ax]
+      bool done;
+      if (ax == 0) {
+        cur[0] += stepi[0];
+        tdist[0] += delta[0];
+        done = cur[0] == overflow[0];
+      } else if (ax == 1) {
+        cur[1] += stepi[1];
+        tdist[1] += delta[1];
+        done = cur[1] == overflow[1];
+      } else {
+        cur[2] += stepi[2];
+        tdist[2] += delta[2];
+        done = cur[2] == overflow[2];
+      }
+      if (done) break;
+    }
+  }
+  if (a.n_intervals) a.n_intervals[r] = n_iv;
+  if (a.n_samples) a.n_samples[r] = n_sm;
+  if (a.termination) a.termination[r] = t_last;
+}
+
+// ---- bit packing of the occupancy grid ------------------------------------------------------------
+__global__ void pack_bits_kernel(const uint8_t* __restrict__ bin, int64_t n_cells, uint32_t* __restrict__ bits) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one cell per thread, one word per warp
+  const bool b = i < n_cells && bin[i] != 0;
+  const unsigned w = __ballot_sync(0xffffffffu, b);
+  if ((threadIdx.x & 31) == 0 && i < n_cells) bits[i >> 5] = w;
+}
+
+// occs -> binaries (bool bytes) + bit field:  binaries = occs > thre   (SURVEY A.2 last line)
+__global__ void occ_threshold_kernel(const float* __restrict__ occs, int64_t n_cells, const float* __restrict__ thre,
+                                     uint8_t* __restrict__ bin, uint32_t* __restrict__ bits) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool b = i < n_cells && occs[i] > *thre;
+  const unsigned w = __ballot_sync(0xffffffffu, b);
+  if (i < n_cells) {
+    bin[i] = (uint8_t)b;
+    if ((threadIdx.x & 31) == 0) bits[i >> 5] = w;
+  }
+}
+
+// ---- int32 counts -> int64 exclusive offsets (+ total) -----------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ int64_t block_excl_scan(int64_t v, int64_t* total, int64_t* smem) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int64_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int64_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) smem[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    int64_t w = lane < SCAN_THREADS / 32 ? smem[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int64_t y = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += y;
+    }
+    if (lane < SCAN_THREADS / 32) smem[lane] = w;
+  }
+  __syncthreads();
+  const int64_t warp_off = wid ? smem[wid - 1] : 0;
+  *total = smem[SCAN_THREADS / 32 - 1];
+  __syncthreads();
+  return warp_off + x - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_tile_sums_kernel(const int32_t* __restrict__ counts, int64_t n, int64_t* __restrict__ tile_sums) {
+  __shared__ int64_t smem[SCAN_THREADS / 32];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  int64_t s = 0;
+  for (int k = 0; k < SCAN_ITEMS; ++k)
+    if (base + k < n) s += counts[base + k];
+  int64_t total;
+  block_excl_scan(s, &total, smem);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_tile_offsets_kernel(int64_t* __restrict__ tile_sums, int64_t n_tiles, int64_t* __restrict__ total_out) {
+  __shared__ int64_t smem[SCAN_THREADS / 32];
+  int64_t carry = 0;
+  for (int64_t base = 0; base < n_tiles; base += SCAN_THREADS) {
+    const int64_t i = base + threadIdx.x;
+    const int64_t v = i < n_tiles ? tile_sums[i] : 0;
+    int64_t total;
+    const int64_t ex = block_excl_scan(v, &total, smem);
+    if (i < n_tiles) tile_sums[i] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_apply_kernel(const int32_t* __restrict__ counts, int64_t n, const int64_t* __restrict__ tile_offsets,
+                  int64_t* __restrict__ starts, int64_t* __restrict__ packed_info) {
+  __shared__ int64_t smem[SCAN_THREADS / 32];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  int32_t c[SCAN_ITEMS];
+  int64_t s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    c[k] = base + k < n ? counts[base + k] : 0;
+    s += c[k];
+  }
+  int64_t total;
+  int64_t off = tile_offsets[blockIdx.x] + block_excl_scan(s, &total, smem);
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    if (base + k < n) {
+      if (starts) starts[base + k] = off;
+      if (packed_info) {
+        packed_info[2 * (base + k)] = off;
+        packed_info[2 * (base + k) + 1] = c[k];
+      }
+    }
+    off += c[k];
+  }
+}
+
+}  // namespace
+
+CEDNERF_EXPORT int cednerf_ray_aabb_intersect(const float* rays_o, const float* rays_d, int64_t n_rays,
+                                              const float* aabbs, int n_levels, float near_plane, float far_plane,
+                                              float miss_value, float* t_mins, float* t_maxs, uint8_t* hits,
+                                              void* stream) {
+  CEDNERF_REQUIRE(n_rays >= 0 && n_levels >= 1, "bad sizes");
+  if (n_rays == 0) return 0;
+  ray_aabb_kernel<<<cednerf_blocks(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(
+      rays_o, rays_d, n_rays, aabbs, n_levels, near_plane, far_plane, miss_value, t_mins, t_maxs, hits);
+  return cednerf_check_launch("cednerf_ray_aabb_intersect");
+}
+
+CEDNERF_EXPORT int cednerf_sort_boundaries(const float* t_mins, const float* t_maxs, int64_t n_rays, int n_levels,
+                                           float* t_sorted, int64_t* t_indices, void* stream) {
+  CEDNERF_REQUIRE(n_rays >= 0 && n_levels >= 1 && n_levels <= MARCH_MAX_LEVELS, "bad sizes (levels <= 8)");
+  if (n_rays == 0) return 0;
+  sort_boundaries_kernel<<<cednerf_blocks(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(t_mins, t_maxs, n_rays,
+                                                                                       n_levels, t_sorted, t_indices);
+  return cednerf_check_launch("cednerf_sort_boundaries");
+}
+
+CEDNERF_EXPORT int cednerf_occ_pack_bits(const uint8_t* binaries, int64_t n_cells, uint32_t* bits, void* stream) {
+  CEDNERF_REQUIRE(n_cells > 0 && (n_cells % 32) == 0, "cell count must be a multiple of 32");
+  pack_bits_kernel<<<cednerf_blocks(n_cells, 256), 256, 0, (cudaStream_t)stream>>>(binaries, n_cells, bits);
+  return cednerf_check_launch("cednerf_occ_pack_bits");
+}
+
+CEDNERF_EXPORT int cednerf_occ_threshold_pack(const float* occs, int64_t n_cells, const float* threshold_dev,
+                                              uint8_t* binaries, uint32_t* bits, void* stream) {
+  CEDNERF_REQUIRE(n_cells > 0 && (n_cells % 32) == 0, "cell count must be a multiple of 32");
+  occ_threshold_kernel<<<cednerf_blocks(n_cells, 256), 256, 0, (cudaStream_t)stream>>>(occs, n_cells, threshold_dev,
+                                                                                      binaries, bits);
+  return cednerf_check_launch("cednerf_occ_threshold_pack");
+}
+
+// March one pass.  fill == 0: count only (n_intervals / n_samples / termination).  fill == 1: write the
+// outputs at the offsets given by iv_starts / sm_starts.  near/far: per-ray arrays or null (constants).
+CEDNERF_EXPORT int cednerf_march(int fill, const float* rays_o, const float* rays_d, int64_t n_rays,
+                                 const uint32_t* occ_bits, const float* aabbs, int n_levels, int resolution,
+                                 const float* near_planes, const float* far_planes, float near_const, float far_const,
+                                 float step_size, float cone_angle, int steps_limit, const uint8_t* rays_mask,
+                                 const float* t_sorted, const int64_t* t_indices, const uint8_t* hits,
+                                 const int64_t* iv_starts, const int64_t* sm_starts, float* iv_vals, uint8_t* iv_left,
+                                 uint8_t* iv_right, int64_t* iv_ray, float* sm_vals, int64_t* sm_ray,
+                                 uint8_t* sm_valid, float* t_starts, float* t_ends, int64_t* ray_indices,
+                                 int32_t* n_intervals, int32_t* n_samples, float* termination, void* stream) {
+  CEDNERF_REQUIRE(n_rays >= 0 && n_levels >= 1 && n_levels <= MARCH_MAX_LEVELS && resolution >= 1,
+                  "bad sizes (levels <= 8)");
+  CEDNERF_REQUIRE((t_sorted == nullptr) == (t_indices == nullptr) && (t_sorted == nullptr) == (hits == nullptr),
+                  "t_sorted, t_indices and hits go together");
+  CEDNERF_REQUIRE(!fill || ((!t_starts && !sm_vals) || sm_starts) , "fill pass needs sm_starts");
+  CEDNERF_REQUIRE(!fill || !iv_vals || iv_starts, "fill pass needs iv_starts");
+  CEDNERF_REQUIRE(!t_starts || (t_ends && ray_indices), "packed outputs go together");
+  if (n_rays == 0) return 0;
+  MarchArgs a{rays_o, rays_d, n_rays, occ_bits, aabbs, n_levels, resolution, near_planes, far_planes, near_const,
+              far_const, step_size, cone_angle, steps_limit, rays_mask, t_sorted, t_indices, hits, iv_starts,
+              sm_starts, iv_vals, iv_left, iv_right, iv_ray, sm_vals, sm_ray, sm_valid, t_starts, t_ends, ray_indices,
+              n_intervals, n_samples, termination};
+  const unsigned grid = cednerf_blocks(n_rays, 128);
+  if (fill) march_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  else march_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  return cednerf_check_launch("cednerf_march");
+}
+
+CEDNERF_EXPORT int64_t cednerf_scan_workspace_bytes(int64_t n) {
+  const int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  return 8 * (tiles + 1);
+}
+
+// counts int32[n] -> starts int64[n] (exclusive), optional packed_info int64[n,2] = (start, count),
+// optional total int64[1]; workspace from cednerf_scan_workspace_bytes.
+CEDNERF_EXPORT int cednerf_exclusive_scan(const int32_t* counts, int64_t n, int64_t* starts, int64_t* packed_info,
+                                          int64_t* total, void* workspace, void* stream) {
+  CEDNERF_REQUIRE(n >= 0 && workspace, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) {
+    if (total) cudaMemsetAsync(total, 0, 8, st);
+    return 0;
+  }
+  const int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  int64_t* tile_sums = (int64_t*)workspace;
+  scan_tile_sums_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(counts, n, tile_sums);
+  scan_tile_offsets_kernel<<<1, SCAN_THREADS, 0, st>>>(tile_sums, tiles, total);
+  scan_apply_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(counts, n, tile_sums, starts, packed_info);
+  return cednerf_check_launch("cednerf_exclusive_scan");
+}

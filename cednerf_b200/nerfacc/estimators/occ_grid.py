@@ -1,0 +1,122 @@
+"""nerfacc.estimators.occ_grid.OccGridEstimator surface (reference: ctor train_real.py:185-187, .sampling
+cednerf/utils.py:115-125, .update_every_n_steps train_real.py:332-336, state_dict train_real.py:438)."""
+from __future__ import annotations
+
+import math
+from typing import Callable, Optional
+
+import torch
+
+from ... import ops
+from ..grid import occupancy_bits, set_occupancy_bits
+
+
+class OccGridEstimator(torch.nn.Module):
+    def __init__(self, roi_aabb, resolution: int = 128, levels: int = 1):
+        super().__init__()
+        roi = torch.as_tensor(roi_aabb, dtype=torch.float32).flatten()
+        centre, half = (roi[:3] + roi[3:]) / 2, (roi[3:] - roi[:3]) / 2
+        aabbs = torch.stack([torch.cat([centre - half * 2 ** l, centre + half * 2 ** l]) for l in range(levels)])
+        self.levels, self.cells_per_lvl = int(levels), int(resolution) ** 3
+        if self.cells_per_lvl % 32:
+            raise ValueError("resolution^3 must be a multiple of 32")
+        self.register_buffer("resolution", torch.tensor([resolution] * 3, dtype=torch.int32))
+        self.register_buffer("aabbs", aabbs)
+        self.register_buffer("occs", torch.zeros(self.levels * self.cells_per_lvl))
+        self.register_buffer("binaries", torch.zeros(levels, resolution, resolution, resolution, dtype=torch.bool))
+        g = torch.arange(resolution)
+        coords = torch.stack(torch.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+        self.register_buffer("grid_coords", coords, persistent=False)
+        self.register_buffer("grid_indices", torch.arange(self.cells_per_lvl), persistent=False)
+        self._occ_mean_key, self._occ_mean = None, 0.0
+
+    @property
+    def device(self):
+        return self.aabbs.device
+
+    def _occs_mean(self) -> float:
+        """occs.mean() as nerfacc reads it in .sampling; one host read per occupancy version."""
+        key = (self.occs.data_ptr(), self.occs._version)
+        if key != self._occ_mean_key:
+            self._occ_mean, self._occ_mean_key = float(self.occs.mean().item()), key
+        return self._occ_mean
+
+    @torch.no_grad()
+    def march(self, rays_o, rays_d, near_plane=0.0, far_plane=1e10, render_step_size=1e-3, cone_angle=0.0,
+              stratified=False, jitter: Optional[torch.Tensor] = None, t_min=None, t_max=None):
+        """Two-pass marching -> (ray_indices, t_starts, t_ends, packed_info).  One host read (the total)."""
+        n = rays_o.shape[0]
+        near = far = None
+        if stratified or t_min is not None or t_max is not None:
+            near = torch.full((n,), float(near_plane), device=rays_o.device)
+            far = torch.full((n,), float(far_plane), device=rays_o.device)
+            if t_min is not None:
+                near = torch.clamp(near, min=t_min)
+            if t_max is not None:
+                far = torch.clamp(far, max=t_max)
+            if stratified:
+                u = torch.rand(n, device=rays_o.device) if jitter is None else jitter.to(rays_o.device).float()
+                near = near + u * render_step_size
+        mi = ops.MarchInputs(rays_o, rays_d, occupancy_bits(self.binaries), self.aabbs, int(self.resolution[0]),
+                             near, far, float(near_plane), float(far_plane), render_step_size, cone_angle)
+        _, n_sm, _ = mi.count()
+        starts, packed, total = ops.exclusive_scan(n_sm)
+        ridx, t0, t1, _ = mi.fill_packed(starts, int(total.item()))
+        return ridx, t0, t1, packed
+
+    @torch.no_grad()
+    def sampling(self, rays_o, rays_d, sigma_fn: Optional[Callable] = None, alpha_fn: Optional[Callable] = None,
+                 near_plane: float = 0.0, far_plane: float = 1e10, t_min=None, t_max=None,
+                 render_step_size: float = 1e-3, early_stop_eps: float = 1e-4, alpha_thre: float = 0.0,
+                 stratified: bool = False, cone_angle: float = 0.0, jitter: Optional[torch.Tensor] = None):
+        if alpha_fn is not None:
+            raise NotImplementedError("alpha_fn is not used by the reference")
+        ridx, t0, t1, packed = self.march(rays_o, rays_d, near_plane, far_plane, render_step_size, cone_angle,
+                                          stratified, jitter, t_min, t_max)
+        if (alpha_thre > 0 or early_stop_eps > 0) and sigma_fn is not None:
+            alpha_thre = min(alpha_thre, self._occs_mean())
+            if t0.numel():
+                sigmas = sigma_fn(t0, t1, ridx)
+                assert sigmas.shape == t0.shape, f"sigmas must have shape {tuple(t0.shape)}"
+                keep = ops.visibility_mask(t0, t1, sigmas, ops.offsets_from_packed(packed), rays_o.shape[0],
+                                           early_stop_eps, alpha_thre)
+                ridx, t0, t1 = ridx[keep], t0[keep], t1[keep]
+        return ridx, t0, t1
+
+    @torch.no_grad()
+    def update_every_n_steps(self, step: int, occ_eval_fn: Callable, occ_thre: float = 1e-2, ema_decay: float = 0.95,
+                             warmup_steps: int = 256, n: int = 16, rng=None):
+        if not self.training:
+            raise RuntimeError("update_every_n_steps() is a training-time call (estimator.train())")
+        if step % n == 0:
+            self._update(step, occ_eval_fn, occ_thre, ema_decay, warmup_steps, rng)
+
+    @torch.no_grad()
+    def _update(self, step, occ_eval_fn, occ_thre=1e-2, ema_decay=0.95, warmup_steps=256, rng=None):
+        """SURVEY.md Appendix A.2.  `rng` (randint(high, n), rand(*shape)) lets parity tests share draws."""
+        dev, cpl = self.device, self.cells_per_lvl
+        randint = (lambda hi, k: torch.randint(hi, (k,), device=dev)) if rng is None else rng.randint
+        rand = (lambda *s: torch.rand(*s, device=dev)) if rng is None else rng.rand
+        lvl_indices = []
+        if step < warmup_steps:
+            for l in range(self.levels):
+                lvl_indices.append(self.grid_indices[self.occs[l * cpl + self.grid_indices] >= 0])
+        else:
+            k = cpl // 4
+            for l in range(self.levels):
+                uni = randint(cpl, k).to(dev)
+                uni = uni[self.occs[l * cpl + uni] >= 0]
+                occ_idx = torch.nonzero(self.binaries[l].flatten())[:, 0]
+                if k < len(occ_idx):
+                    occ_idx = occ_idx[randint(len(occ_idx), k).to(dev)]
+                lvl_indices.append(torch.cat([uni, occ_idx]))
+        for l, idx in enumerate(lvl_indices):
+            x = (self.grid_coords[idx].float() + rand(len(idx), 3).to(dev)) / self.resolution.float()
+            x = self.aabbs[l, :3] + x * (self.aabbs[l, 3:] - self.aabbs[l, :3])
+            occ = occ_eval_fn(x).squeeze(-1).float()
+            cell = l * cpl + idx
+            self.occs[cell] = torch.maximum(self.occs[cell] * ema_decay, occ)
+        thre = torch.clamp(self.occs[self.occs >= 0].mean(), max=occ_thre).reshape(1).contiguous()
+        bits = torch.empty(self.occs.numel() // 32, dtype=torch.int32, device=dev)
+        ops.occ_threshold_pack(self.occs, thre, self.binaries, bits)
+        set_occupancy_bits(self.binaries, bits)

@@ -1,0 +1,115 @@
+"""cednerf/utils.py surface: render_image (:46-150), render_image_test (:153-318), trunc_exp, set_random_seed."""
+from __future__ import annotations
+
+import collections
+import random
+
+import numpy as np
+import torch
+
+from . import nerfacc, ops
+from .model import trunc_exp  # noqa: F401  (re-exported like cednerf/utils.py:43)
+from .render import rendering
+
+Rays = collections.namedtuple("Rays", ("origins", "viewdirs"))
+
+
+def namedtuple_map(fn, tup):
+    """datasets/utils.py:8-15."""
+    return type(tup)(*(None if x is None else fn(x) for x in tup))
+
+
+def set_random_seed(seed):
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+
+
+def _field_fns(field, rays, timestamps):
+    def positions_of(t0, t1, ridx):
+        o, d = rays.origins[ridx], rays.viewdirs[ridx]
+        x = o + d * (t0 + t1)[:, None] / 2.0
+        t = timestamps[ridx] if field.training else timestamps.expand_as(x[:, :1])
+        return x, t, d
+
+    def sigma_fn(t0, t1, ridx):
+        x, t, _ = positions_of(t0, t1, ridx)
+        return field.query_density(x, t)["density"].squeeze(-1)
+
+    def rgb_sigma_fn(t0, t1, ridx):
+        x, t, d = positions_of(t0, t1, ridx)
+        return field(x, t, d)
+
+    return sigma_fn, rgb_sigma_fn
+
+
+def render_image(radiance_field, estimator, rays, near_plane=0.0, far_plane=1e10, render_step_size=1e-3,
+                 render_bkgd=None, cone_angle=0.0, alpha_thre=0.0, test_chunk_size=8192, timestamps=None,
+                 jitter=None):
+    """-> (rgb, acc, depth, n_rendering_samples, extras list).  `jitter` (optional, [n_rays] in [0,1)) replaces the
+    stratified random draw so that parity tests do not depend on the RNG stream."""
+    shape = rays.origins.shape
+    rays = Rays(rays.origins.reshape(-1, 3), rays.viewdirs.reshape(-1, 3))
+    n = rays.origins.shape[0]
+    chunk = n if radiance_field.training else test_chunk_size
+    outs, infos = [], []
+    for i in range(0, n, chunk):
+        cr = Rays(rays.origins[i:i + chunk], rays.viewdirs[i:i + chunk])
+        ts = timestamps[i:i + chunk] if (radiance_field.training and timestamps is not None) else timestamps
+        sigma_fn, rgb_sigma_fn = _field_fns(radiance_field, cr, ts)
+        ridx, t0, t1 = estimator.sampling(cr.origins, cr.viewdirs, sigma_fn=sigma_fn, near_plane=near_plane,
+                                          far_plane=far_plane, render_step_size=render_step_size,
+                                          stratified=radiance_field.training, cone_angle=cone_angle,
+                                          alpha_thre=alpha_thre, jitter=None if jitter is None else jitter[i:i + chunk])
+        rgb, opac, depth, extras = rendering(t0, t1, ridx, cr.origins.shape[0], rgb_sigma_fn=rgb_sigma_fn,
+                                             render_bkgd=render_bkgd)
+        extras.update(ray_indices=ridx, t_starts=t0, t_ends=t1)
+        outs.append((rgb, opac, depth, len(t0)))
+        infos.append(extras)
+    rgb, opac, depth = (torch.cat([o[k] for o in outs], 0) for k in range(3))
+    return (rgb.view(*shape[:-1], -1), opac.view(*shape[:-1], -1), depth.view(*shape[:-1], -1),
+            sum(o[3] for o in outs), infos)
+
+
+@torch.no_grad()
+def render_image_test(max_samples, radiance_field, estimator, rays, near_plane=0.0, far_plane=1e10,
+                      render_step_size=1e-3, render_bkgd=None, cone_angle=0.0, alpha_thre=0.0, early_stop_eps=1e-4,
+                      timestamps=None):
+    """Iterative early-terminating marcher of cednerf/utils.py:153-318 -> (rgb, acc, depth, n_samples)."""
+    shape = rays.origins.shape
+    rays = Rays(rays.origins.reshape(-1, 3), rays.viewdirs.reshape(-1, 3))
+    n, dev = rays.origins.shape[0], rays.origins.device
+    _, rgb_sigma_fn = _field_fns(radiance_field, rays, timestamps)
+    opacity, depth, rgb = torch.zeros(n, 1, device=dev), torch.zeros(n, 1, device=dev), torch.zeros(n, 3, device=dev)
+    alive = torch.ones(n, dtype=torch.bool, device=dev)
+    min_samples = 1 if cone_angle == 0 else 4
+    near = torch.full((n,), float(near_plane), device=dev)
+    far = torch.full((n,), float(far_plane), device=dev)
+    t_mins, t_maxs, hits = nerfacc.ray_aabb_intersect(rays.origins, rays.viewdirs, estimator.aabbs)
+    t_sorted, t_indices = ops.sort_boundaries(t_mins, t_maxs)
+    done = total = 0
+    while done < max_samples:
+        n_alive = int(alive.sum())
+        if n_alive == 0:
+            break
+        k = max(min(n // n_alive, 64), min_samples)
+        done += k
+        iv, sm, term = nerfacc.traverse_grids(rays.origins, rays.viewdirs, estimator.binaries, estimator.aabbs, near,
+                                              far, render_step_size, cone_angle, k, True, alive, t_sorted, t_indices,
+                                              hits)
+        t0, t1 = iv.vals[iv.is_left], iv.vals[iv.is_right]
+        ridx = sm.ray_indices[sm.is_valid]
+        if ridx.numel():
+            rgbs, sres = rgb_sigma_fn(t0, t1, ridx)
+            offsets = ops.ray_offsets(ridx, n)
+            w, _, _ = ops.RenderWeightFunction.apply(t0, t1, sres["density"].squeeze(-1), offsets, n,
+                                                     1 - opacity[ridx].squeeze(-1))
+            ops.accumulate_inplace(w, rgbs, offsets, rgb)
+            ops.accumulate_inplace(w, None, offsets, opacity)
+            ops.accumulate_inplace(w, (t0 + t1)[:, None] / 2.0, offsets, depth)
+        near = term
+        alive = (opacity.view(-1) <= 1 - early_stop_eps) & (sm.packed_info[:, 1] == k)
+        total += ridx.shape[0]
+    rgb = rgb + render_bkgd * (1.0 - opacity)
+    depth = depth / opacity.clamp_min(torch.finfo(torch.float32).eps)
+    return rgb.view(*shape[:-1], -1), opacity.view(*shape[:-1], -1), depth.view(*shape[:-1], -1), total

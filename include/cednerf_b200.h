@@ -1,0 +1,160 @@
+/*
+ * cednerf_b200 — C ABI of libcednerf_b200.so (sm_100a).
+ *
+ * The reference (Linyou/Ced-NeRF) has no FFI of its own: its per-ray rendering hot path calls three
+ * third-party CUDA/JIT packages from Python (nerfacc, tiny-cuda-nn, Taichi).  The entry points below are
+ * what a Python binding for that path binds instead; each one names the reference call it stands behind.
+ * INTEGRATION.md shows the ctypes stubs.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host or its type is a descriptor struct
+ *     (descriptors are small host structs passed by pointer and copied at launch);
+ *   - the caller owns all memory, including workspaces; the library never allocates or frees device memory
+ *     and keeps no pointer after returning;
+ *   - functions only enqueue work on `stream` (a cudaStream_t) and return; no device synchronisation;
+ *   - return value 0 = ok, > 0 = cudaError_t, < 0 = library error (CEDNERF_ERR_*);
+ *     cednerf_last_error() returns a thread-local message;
+ *   - nullable arguments are marked (nullable).
+ */
+#ifndef CEDNERF_B200_H
+#define CEDNERF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CEDNERF_ERR_BAD_ARG (-1)
+#define CEDNERF_ERR_UNSUPPORTED (-2)
+
+#define CEDNERF_MAX_LEVELS 32
+#define CEDNERF_MLP_MAX_LAYERS 5
+
+/* ---- library ------------------------------------------------------------------------------------ */
+const char* cednerf_last_error(void);
+int cednerf_abi_version(void);
+int cednerf_check_device(void); /* 0 iff the current device is compute capability 10.x */
+
+/* ---- K1: marching --------------------------------------------------------------------------------
+ * nerfacc.ray_aabb_intersect — reference call site cednerf/utils.py:215 */
+int cednerf_ray_aabb_intersect(const float* rays_o, const float* rays_d, int64_t n_rays, const float* aabbs,
+                               int n_levels, float near_plane, float far_plane, float miss_value, float* t_mins,
+                               float* t_maxs, uint8_t* hits, void* stream);
+/* torch.sort of cat([t_mins, t_maxs]) — cednerf/utils.py:219-225 (stable; ties keep the lower slot) */
+int cednerf_sort_boundaries(const float* t_mins, const float* t_maxs, int64_t n_rays, int n_levels, float* t_sorted,
+                            int64_t* t_indices, void* stream);
+/* OccGridEstimator.binaries (bool bytes [L,R,R,R]) -> 1 bit per cell, same cell order */
+int cednerf_occ_pack_bits(const uint8_t* binaries, int64_t n_cells, uint32_t* bits, void* stream);
+/* binaries = occs > *threshold_dev, plus the bit field (last line of OccGridEstimator._update; train_real.py:332-336) */
+int cednerf_occ_threshold_pack(const float* occs, int64_t n_cells, const float* threshold_dev, uint8_t* binaries,
+                               uint32_t* bits, void* stream);
+/* nerfacc.traverse_grids — cednerf/utils.py:245-264 (eval) and inside OccGridEstimator.sampling,
+ * cednerf/utils.py:115-125 (train).  fill == 0 counts (n_intervals / n_samples / termination);
+ * fill == 1 writes at iv_starts / sm_starts.  near/far: per-ray arrays or (nullable) -> the constants.
+ * t_sorted / t_indices / hits (nullable, all or none): computed in-kernel when absent.
+ * Output groups (each nullable): nerfacc intervals (iv_*), nerfacc samples (sm_*), packed
+ * (t_starts, t_ends, ray_indices). */
+int cednerf_march(int fill, const float* rays_o, const float* rays_d, int64_t n_rays, const uint32_t* occ_bits,
+                  const float* aabbs, int n_levels, int resolution, const float* near_planes, const float* far_planes,
+                  float near_const, float far_const, float step_size, float cone_angle, int steps_limit,
+                  const uint8_t* rays_mask, const float* t_sorted, const int64_t* t_indices, const uint8_t* hits,
+                  const int64_t* iv_starts, const int64_t* sm_starts, float* iv_vals, uint8_t* iv_left,
+                  uint8_t* iv_right, int64_t* iv_ray, float* sm_vals, int64_t* sm_ray, uint8_t* sm_valid,
+                  float* t_starts, float* t_ends, int64_t* ray_indices, int32_t* n_intervals, int32_t* n_samples,
+                  float* termination, void* stream);
+/* cumsum between the two traversal passes (nerfacc: torch.cumsum + .item()); stays on the device */
+int64_t cednerf_scan_workspace_bytes(int64_t n);
+int cednerf_exclusive_scan(const int32_t* counts, int64_t n, int64_t* starts /*nullable*/,
+                           int64_t* packed_info /*nullable, [n,2]*/, int64_t* total /*nullable*/, void* workspace,
+                           void* stream);
+
+/* ---- K2: hash-grid encoders ------------------------------------------------------------------------ */
+typedef struct CednerfGridLevels {
+  int n_levels;
+  float scale[CEDNERF_MAX_LEVELS];     /* base * exp(l * log_b) - 1   (hash_encoder_half.py:96-103) */
+  uint32_t res[CEDNERF_MAX_LEVELS];    /* ceil(scale) + 1 */
+  uint32_t size[CEDNERF_MAX_LEVELS];   /* min(max_params, align8(res^3)) */
+  uint32_t offset[CEDNERF_MAX_LEVELS]; /* prefix sum of size */
+  uint32_t hashed[CEDNERF_MAX_LEVELS]; /* res^3 > size */
+} CednerfGridLevels;
+/* tcnn.Encoding(HashGrid) forward — cednerf/model.py:384; Taichi twin hash_encoder_half.py:112-161.
+ * table: fp16 [sum size, 2]; out: fp16, row stride out_stride (>= 2*n_levels) */
+int cednerf_hashgrid_fwd(const float* x, int x_stride, int64_t n, const void* table_f16,
+                         const CednerfGridLevels* levels, void* out_f16, int out_stride, void* stream);
+/* backward: g_table fp32 [sum size, 2] is accumulated into (caller zeroes); g_x fp32 [n,3] (nullable) */
+int cednerf_hashgrid_bwd(const float* x, int x_stride, int64_t n, const void* table_f16,
+                         const CednerfGridLevels* levels, const void* dy, int dy_stride, int dy_is_f16,
+                         float* g_table /*nullable*/, float* g_x /*nullable*/, void* stream);
+/* 4-D (xyz+t, 4 key-frames x 2 features per entry) — hash_encoder_inter.py:121-199 / :202-275 */
+int cednerf_hashgrid4d_fwd(const float* xyzt, int x_stride, int64_t n, const void* table_f16,
+                           const CednerfGridLevels* levels, void* out_f16, int out_stride, int taichi_compat,
+                           void* stream);
+int cednerf_hashgrid4d_bwd(const float* xyzt, int x_stride, int64_t n, const CednerfGridLevels* levels, const void* dy,
+                           int dy_stride, int dy_is_f16, float* g_table, int taichi_compat, void* stream);
+/* fp32 master -> fp16 working copy (hash_encoder_half.py:381-385 does this on every call) */
+int cednerf_cast_f32_to_f16(const float* src, void* dst_f16, int64_t n, void* stream);
+
+/* ---- parameter-free encodings ----------------------------------------------------------------------- */
+/* tcnn Frequency(n): out[j] = sin(2^k pi x_dim + phase), dim = j/(2n), k = (j/2)%n, phase = (j%2) pi/2 —
+ * cednerf/model.py:205-213, :316-319, :333-336.  Columns [width, pad_to) are filled with pad_value
+ * (tcnn pads MLP inputs to a multiple of 16 with 1.0). */
+int cednerf_frequency_fwd(const float* x, int n_dims, int64_t n, int n_frequencies, void* out_f16, int out_stride,
+                          int pad_to, float pad_value, void* stream);
+int cednerf_frequency_bwd(const float* x, int n_dims, int64_t n, int n_frequencies, const void* dy, int dy_stride,
+                          int dy_is_f16, float* dx, void* stream);
+/* tcnn SphericalHarmonics(degree 2), input in [0,1]^3 — cednerf/model.py:226-239, :450-455 */
+int cednerf_sh2_fwd(const float* d01, int64_t n, void* out_f16, int out_stride, void* stream);
+/* SinusoidalEncoder(1,0,4,True) (move_norm == NULL) / SinusoidalEncoderWithExp(1,0,4,True) —
+ * cednerf/encoder.py:28-44, :69-90; out fp32 [n,9] */
+int cednerf_time_embed(const float* t, const float* move_norm /*nullable*/, int64_t n, float* out, void* stream);
+
+/* ---- K3: fully fused 64-wide MLPs (tcgen05) -------------------------------------------------------- */
+typedef struct CednerfMlpDesc {
+  int n_layers;                          /* hidden layers + 1 */
+  int dim_in[CEDNERF_MLP_MAX_LAYERS];    /* padded to 16; 64 for every layer but the first */
+  int dim_out[CEDNERF_MLP_MAX_LAYERS];   /* 64 for hidden layers; padded n_out for the last */
+  int param_off[CEDNERF_MLP_MAX_LAYERS]; /* element offset of W_l [dim_out, dim_in] in the flat fp32 params */
+  int image_off[CEDNERF_MLP_MAX_LAYERS]; /* byte offset of W_l's image: dim_out rows x 128 B, 128-byte swizzle */
+  int image_bytes;
+} CednerfMlpDesc;
+/* tcnn.Network — cednerf/model.py:200-222, :280-290, :292-309, :312-344 */
+int cednerf_mlp_pack_weights(const float* params, const CednerfMlpDesc* desc, void* image, void* stream);
+int cednerf_mlp_fwd(const void* x_f16, const void* weight_image, const CednerfMlpDesc* desc, int64_t n, void* out_f16,
+                    void* hidden_f16 /*nullable: [n_layers-1][n][64]*/, void* stream);
+int cednerf_mlp_bwd(const void* x_f16, const void* hidden_f16, const void* d_out_f16, const void* weight_image,
+                    const CednerfMlpDesc* desc, int64_t n, void* d_x /*nullable*/, int dx_is_f32,
+                    float* d_params /*nullable, accumulated into*/, void* stream);
+
+/* ---- K4: compositing ------------------------------------------------------------------------------- */
+/* offsets[r] = first sample of ray r (ray_indices sorted); offsets[n_rays] = n_samples */
+int cednerf_ray_offsets(const int64_t* ray_indices, int64_t n_samples, int64_t n_rays, int64_t* offsets, void* stream);
+/* nerfacc.render_weight_from_density (+ accumulate_along_rays x3, depth normalise, background) —
+ * cednerf/render.py:81-87, :158-174; prefix_trans / in-place form cednerf/utils.py:274-299 */
+int cednerf_composite_fwd(const float* t_starts, const float* t_ends, const float* sigmas, const float* rgbs,
+                          const float* prefix_trans, const int64_t* offsets, const float* bkgd, int bkgd_stride,
+                          int64_t n_samples, int64_t n_rays, float* weights, float* trans, float* alphas,
+                          float* colors, float* opacity, float* depth, float* depth_raw, int accumulate_inplace,
+                          float depth_eps, void* stream);
+int cednerf_composite_bwd(const float* t_starts, const float* t_ends, const float* rgbs, const float* trans,
+                          const float* alphas, const int64_t* offsets, const float* bkgd, int bkgd_stride,
+                          int64_t n_samples, int64_t n_rays, const float* opacity, const float* depth_raw,
+                          const float* g_colors, const float* g_opacity, const float* g_depth, const float* g_weights,
+                          const float* g_trans, const float* g_alphas, float* g_sigmas, float* g_rgbs, float depth_eps,
+                          void* stream);
+/* nerfacc.render_visibility_from_density — inside OccGridEstimator.sampling (cednerf/utils.py:115-125) */
+int cednerf_visibility_mask(const float* t_starts, const float* t_ends, const float* sigmas, const int64_t* offsets,
+                            int64_t n_samples, int64_t n_rays, float early_stop_eps, float alpha_thre, uint8_t* keep,
+                            void* stream);
+/* nerfacc.accumulate_along_rays / accumulate_along_rays_ — cednerf/render.py:158-169, cednerf/utils.py:282-299 */
+int cednerf_accumulate_fwd(const float* weights, const float* values /*nullable*/, int n_channels,
+                           const int64_t* offsets, int64_t n_samples, int64_t n_rays, float* outputs, int inplace,
+                           void* stream);
+int cednerf_accumulate_bwd(const float* weights, const float* values /*nullable*/, int n_channels,
+                           const int64_t* ray_indices, int64_t n_samples, const float* g_outputs,
+                           float* g_weights /*nullable*/, float* g_values /*nullable*/, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CEDNERF_B200_H */

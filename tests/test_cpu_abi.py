@@ -1,0 +1,137 @@
+"""CPU-side checks (no GPU): the C-ABI library loads, exports every symbol include/cednerf_b200.h declares,
+the ctypes signatures agree with the header, host-side descriptors match the oracle's geometry, and the product
+refuses to run without CUDA (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_decls():
+    h = open(os.path.join(ROOT, "include", "cednerf_b200.h")).read()
+    h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
+    return re.findall(r"\b(int|int64_t|const char\*)\s+(cednerf_\w+)\s*\(([^;]*?)\)\s*;", h, flags=re.S)
+
+
+def test_library_exports_every_declared_symbol():
+    from cednerf_b200 import _lib
+
+    lib = _lib.load()
+    names = [n for _, n, _ in header_decls()]
+    assert len(names) >= 28
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    assert sorted(names) == _lib.exported_symbols()
+    assert lib.cednerf_abi_version() == 1
+
+
+def test_ctypes_signatures_match_header():
+    from cednerf_b200 import _lib
+
+    for _, name, args in header_decls():
+        if name not in _lib._SIGNATURES:
+            continue
+        sig = ""
+        for a in [x.strip() for x in args.split(",")]:
+            if "CednerfGridLevels" in a:
+                sig += "G"
+            elif "CednerfMlpDesc" in a:
+                sig += "M"
+            elif "*" in a:
+                sig += "p"
+            elif a.startswith("int64_t"):
+                sig += "l"
+            elif a.startswith("int "):
+                sig += "i"
+            elif a.startswith("float "):
+                sig += "f"
+            else:
+                raise AssertionError(f"unparsed argument {a!r} in {name}")
+        assert sig == _lib._SIGNATURES[name], name
+
+
+def test_descriptor_structs_match_header_layout():
+    from cednerf_b200 import _lib
+
+    assert ctypes.sizeof(_lib.GridLevels) == 4 + 5 * 4 * 32
+    assert ctypes.sizeof(_lib.MlpDesc) == 4 + 4 * 4 * 5 + 4
+
+
+def test_level_geometry_matches_oracle_and_survey():
+    import math
+
+    from cednerf_b200 import ops
+    from oracle import tcnn_ref as tc
+
+    for dst, log2_t in ((8192, 21), (4096, 21), (1024, 21), (256, 12)):
+        log_b = math.log(dst / 16) / 15
+        g, total, info = ops.grid_levels(16, 16, log_b, 2 ** log2_t)
+        scales, ress, sizes, offsets, hashed, tot = tc.grid_levels(16, 16, log_b, 2 ** log2_t)
+        assert total == tot and [i[1] for i in info] == ress and [i[2] for i in info] == sizes
+        assert [i[3] for i in info] == offsets and [i[4] for i in info] == hashed
+        assert [g.scale[l] for l in range(16)] == [float(s) for s in scales]
+    _, total, info = ops.grid_levels(16, 16, math.log(8192 / 16) / 15, 2 ** 21)
+    assert total == 23928800 and [i[1] for i in info][:6] == [16, 25, 37, 56, 85, 128]
+
+
+def test_mlp_descriptor_matches_oracle_shapes():
+    from cednerf_b200 import ops
+    from oracle import tcnn_ref as tc
+
+    for n_in, n_out, h in ((32, 6, 3), (41, 16, 1), (19, 3, 2), (32, 32, 1), (32, 1, 1)):
+        d, n_params = ops.mlp_desc(n_in, n_out, 64, h)
+        shapes = tc.mlp_layer_shapes(n_in, n_out, 64, h)
+        assert d.n_layers == len(shapes) and n_params == sum(o * i for o, i in shapes)
+        assert [(d.dim_out[l], d.dim_in[l]) for l in range(d.n_layers)] == shapes
+        assert d.image_bytes == sum(o for o, _ in shapes) * 128
+    with pytest.raises(NotImplementedError):
+        ops.mlp_desc(32, 3, 128, 2)
+
+
+def test_no_cpu_fallback():
+    import cednerf_b200 as cb
+
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    with pytest.raises(RuntimeError):
+        cb.nerfacc.ray_aabb_intersect(torch.zeros(4, 3), torch.ones(4, 3), torch.zeros(1, 6))
+    with pytest.raises(RuntimeError):
+        cb.tcnn.Network(32, 16, {"otype": "FullyFusedMLP", "n_neurons": 64, "n_hidden_layers": 1})(torch.zeros(8, 32))
+    with pytest.raises(RuntimeError):
+        cb.ops.time_embed(torch.zeros(3, 1))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "cednerf_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, os.path.join(dirpath, f)
+
+
+def test_module_surface_mirrors_reference_names():
+    import cednerf_b200 as cb
+
+    for name in ("traverse_grids", "ray_aabb_intersect", "render_weight_from_density", "accumulate_along_rays",
+                 "render_transmittance_from_density", "render_visibility_from_density", "OccGridEstimator"):
+        assert hasattr(cb.nerfacc, name)
+    assert hasattr(cb.nerfacc.volrend, "accumulate_along_rays_")
+    from cednerf_b200.nerfacc.estimators.occ_grid import OccGridEstimator  # noqa: F401  (train_real.py:27)
+
+    for name in ("Encoding", "Network", "NetworkWithInputEncoding"):
+        assert hasattr(cb.tcnn, name)
+    for name in ("render_image", "render_image_test", "trunc_exp", "set_random_seed", "Rays", "namedtuple_map"):
+        assert hasattr(cb.utils, name)
+    est = cb.OccGridEstimator([-1, -1, -1, 1, 1, 1], resolution=128, levels=4)
+    assert est.binaries.shape == (4, 128, 128, 128) and est.occs.numel() == 4 * 128 ** 3
+    assert torch.equal(est.aabbs[-1], torch.tensor([-8.0, -8, -8, 8, 8, 8]))
+    field = cb.DNGPradianceField(est.aabbs[-1], dst_resolution=8192, log2_hashmap_size=21, use_feat_predict=True,
+                                 use_time_embedding=True, use_time_attenuation=True, use_div_offsets=True)
+    assert field.hash_encoder.params.numel() == 2 * 23928800
+    assert field.mlp_base.n_input_dims == 41 and field.mlp_head.n_input_dims == 19
+    assert field.xyz_wrap.n_output_dims == 6 and field.mlp_feat_prediction.n_output_dims == 32

@@ -1,0 +1,176 @@
+"""GPU parity of the assembled path (field, rendering, render_image, render_image_test) against the golden
+vectors frozen from the reference's own Python (tests/golden/make_golden.py) and against the oracle.
+
+Tolerances (BASELINE.json north_star): marcher outputs bit-exact; fp16 MLP path <= 2e-3; loss and gradient
+relative error <= 1e-3 (measured as ||g - g_ref|| / ||g_ref|| per parameter tensor).
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import cednerf_ref as cr  # noqa: E402
+from oracle import nerfacc_ref as nf  # noqa: E402
+
+DEV = "cuda:0"
+FIELD_KW = dict(n_levels=8, log2_hashmap_size=12, dst_resolution=256, moving_step=1.0 / 256)
+FLAG_SETS = {
+    "plain": dict(),
+    "te_ta_df": dict(use_time_embedding=True, use_time_attenuation=True, use_div_offsets=True),
+    "te_after": dict(use_time_embedding=True, time_inject_before_sigma=False),
+}
+OPTS = dict(near_plane=0.2, render_step_size=2e-2, cone_angle=0.004, alpha_thre=1e-2)
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import cednerf_b200
+
+    return cednerf_b200
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+def gpu_scene(cb, golden):
+    est = cb.OccGridEstimator([-1.0, -1.0, -1.0, 1.0, 1.0, 1.0], resolution=16, levels=2).to(DEV)
+    est.binaries = golden["scene.binaries"].to(DEV)
+    est.occs = golden["scene.occs"].to(DEV)
+    assert torch.equal(est.aabbs.cpu(), golden["scene.aabbs"])
+    rays = cb.Rays(golden["scene.origins"].to(DEV), golden["scene.dirs"].to(DEV))
+    return est, rays, golden["scene.timestamps"].to(DEV)
+
+
+def gpu_field(cb, golden, name, extra=None):
+    field = cb.DNGPradianceField(golden["scene.aabbs"][-1], **FIELD_KW, **FLAG_SETS[name], **(extra or {}))
+    sd = {k[len(name) + 7:]: v for k, v in golden.items() if k.startswith(f"{name}.state.")}
+    missing = field.load_state_dict({k: v for k, v in sd.items() if not k.startswith("time_encoder")}, strict=False)
+    assert not missing.unexpected_keys and all("prediction" in k for k in missing.missing_keys)
+    return field.to(DEV)
+
+
+@pytest.mark.parametrize("name", list(FLAG_SETS))
+def test_field_against_golden(cb, golden, name):
+    field = gpu_field(cb, golden, name).train()
+    to = lambda k: golden[f"{name}.field.{k}"].to(DEV)
+    rgb, res = field(to("pts"), to("t"), to("dirs"))
+    assert rgb.dtype == torch.float32 and res["density"].dtype == torch.float32
+    torch.testing.assert_close(rgb.cpu(), golden[f"{name}.field.rgb"], rtol=0, atol=2e-3)
+    torch.testing.assert_close(res["density"].cpu(), golden[f"{name}.field.density"], rtol=2e-3, atol=2e-3)
+    bo = golden[f"{name}.field.base_mlp_out"]
+    torch.testing.assert_close(res["base_mlp_out"].float().cpu(), bo, rtol=2e-3, atol=2e-3 * float(bo.abs().max()))
+    mv = golden[f"{name}.field.move"]
+    torch.testing.assert_close(res["interal_output"]["move"].cpu(), mv, rtol=2e-3, atol=2e-3 * float(mv.abs().max()))
+    ((rgb * to("grgb")).sum() + (res["density"] * to("gsig")).sum()).backward()
+    for k, p in field.named_parameters():
+        key = f"{name}.field.grad.{k}"
+        if key in golden:
+            assert rel(p.grad.cpu(), golden[key]) < 1e-3, (k, rel(p.grad.cpu(), golden[key]))
+
+
+@pytest.mark.parametrize("name", list(FLAG_SETS))
+def test_render_paths_against_golden(cb, golden, name):
+    est, rays, ts = gpu_scene(cb, golden)
+    field = gpu_field(cb, golden, name)
+    bkgd = torch.tensor([0.2, 0.5, 0.8], device=DEV)
+    field.train(), est.train()
+    torch.manual_seed(123)
+    jitter = torch.rand(rays.origins.shape[0])  # the draw the reference's sampling() made under the same seed
+    # marcher alone, before visibility filtering: bit-exact against the oracle
+    near = torch.full((96,), 0.2) + jitter * 2e-2
+    r_ref, a_ref, b_ref, _, _ = nf.traverse_grids(golden["scene.origins"], golden["scene.dirs"], golden["scene.binaries"],
+                                                  golden["scene.aabbs"], near, torch.full((96,), 1e10), 2e-2, 0.004,
+                                                  packed_only=True)
+    r_g, a_g, b_g, _ = est.march(rays.origins, rays.viewdirs, 0.2, 1e10, 2e-2, 0.004, True, jitter)
+    assert torch.equal(r_g.cpu(), r_ref) and torch.equal(a_g.cpu(), a_ref) and torch.equal(b_g.cpu(), b_ref)
+
+    rgb, acc, depth, n_s, extra = cb.render_image(field, est, rays, render_bkgd=bkgd, timestamps=ts, jitter=jitter,
+                                                  **OPTS)
+    assert n_s == int(golden[f"{name}.train.n_samples"])
+    for k in ("ray_indices", "t_starts", "t_ends"):
+        assert torch.equal(extra[0][k].cpu(), golden[f"{name}.train.{k}"])
+    for a, k in ((rgb, "rgb"), (acc, "acc"), (depth, "depth"), (extra[0]["weights"], "weights"),
+                 (extra[0]["trans"], "trans"), (extra[0]["alphas"], "alphas")):
+        torch.testing.assert_close(a.detach().cpu(), golden[f"{name}.train.{k}"], rtol=0, atol=2e-3)
+    torch.testing.assert_close(extra[0]["sigmas"].detach().cpu(), golden[f"{name}.train.sigmas"], rtol=2e-3, atol=2e-3)
+    loss = torch.nn.functional.mse_loss(rgb, golden[f"{name}.train.pixels"].to(DEV))
+    (loss * 1024.0).backward()
+    assert abs(float(loss) - float(golden[f"{name}.train.loss"])) <= 1e-3 * float(golden[f"{name}.train.loss"])
+    for k, p in field.named_parameters():
+        key = f"{name}.train.grad.{k}"
+        if key in golden:
+            assert rel(p.grad.cpu(), golden[key]) < 1e-3, (k, rel(p.grad.cpu(), golden[key]))
+
+    field.eval(), est.eval()
+    t_frame = torch.tensor([[0.5]], device=DEV)
+    with torch.no_grad():
+        rgb, acc, depth, n_s, _ = cb.render_image(field, est, rays, render_bkgd=bkgd, timestamps=t_frame,
+                                                  test_chunk_size=40, **OPTS)
+    assert n_s == int(golden[f"{name}.eval.n_samples"])
+    for a, k in ((rgb, "rgb"), (acc, "acc"), (depth, "depth")):
+        torch.testing.assert_close(a.cpu(), golden[f"{name}.eval.{k}"], rtol=0, atol=2e-3)
+    rgb, acc, depth, n_s = cb.render_image_test(64, field, est, rays, render_bkgd=bkgd, timestamps=t_frame, **OPTS)
+    assert n_s == int(golden[f"{name}.test.n_samples"])
+    for a, k in ((rgb, "rgb"), (acc, "acc"), (depth, "depth")):
+        torch.testing.assert_close(a.cpu(), golden[f"{name}.test.{k}"], rtol=0, atol=2e-3)
+
+
+def test_predictor_flags_against_oracle(cb, golden):
+    """-f / -w heads (cednerf/model.py:312-344, cednerf/render.py:101-124): no golden, compare with the oracle."""
+    flags = dict(use_time_embedding=True, use_time_attenuation=True, use_div_offsets=True, use_feat_predict=True,
+                 use_weight_predict=True)
+    ref = cr.DNGPradianceField(golden["scene.aabbs"][-1], **FIELD_KW, **flags).train()
+    with torch.no_grad():
+        ref.hash_encoder.params.mul_(5000.0)
+        ref.mlp_base.params.mul_(3.0)
+    field = cb.DNGPradianceField(golden["scene.aabbs"][-1], **FIELD_KW, **flags)
+    field.load_state_dict(ref.state_dict())
+    field = field.to(DEV).train()
+    est, rays, ts = gpu_scene(cb, golden)
+    est.train()
+    est_ref = nf.OccGridEstimator([-1.0, -1.0, -1.0, 1.0, 1.0, 1.0], resolution=16, levels=2).train()
+    est_ref.binaries, est_ref.occs = golden["scene.binaries"], golden["scene.occs"]
+    jitter = torch.rand(96, generator=torch.Generator().manual_seed(3))
+    bk = torch.tensor([0.1, 0.2, 0.3])
+    rays_ref = cr.Rays(golden["scene.origins"], golden["scene.dirs"])
+    out_ref = cr.render_image(ref, est_ref, rays_ref, render_bkgd=bk, timestamps=golden["scene.timestamps"],
+                              jitter=jitter, **OPTS)
+    out = cb.render_image(field, est, rays, render_bkgd=bk.to(DEV), timestamps=ts, jitter=jitter, **OPTS)
+    assert out[3] == out_ref[3]
+
+    def total(o):
+        ex = o[4][0]
+        return (o[0] ** 2).mean() + ex["latent_losses"].mean() + ex["weight_losses"].mean()
+
+    for k in ("latent_losses", "weight_losses"):
+        a, b = out[4][0][k].detach().cpu(), out_ref[4][0][k].detach()
+        torch.testing.assert_close(a, b, rtol=5e-3, atol=2e-3 * float(b.abs().max()))
+    (total(out_ref) * 1024).backward()
+    (total(out) * 1024).backward()
+    for (k, p), (_, q) in zip(field.named_parameters(), ref.named_parameters()):
+        if q.grad is not None and q.numel():
+            assert rel(p.grad.cpu(), q.grad) < 2e-3, (k, rel(p.grad.cpu(), q.grad))
+
+
+def test_estimator_update_matches_oracle(cb, golden):
+    """OccGridEstimator._update with shared random draws: occs close, binaries equal."""
+    est_ref = nf.OccGridEstimator([-1.0, -1.0, -1.0, 1.0, 1.0, 1.0], resolution=16, levels=2).train()
+    est = cb.OccGridEstimator([-1.0, -1.0, -1.0, 1.0, 1.0, 1.0], resolution=16, levels=2).to(DEV).train()
+
+    def occ_fn(x):  # smooth analytic density, identical on both sides
+        return torch.exp(-4.0 * (x ** 2).sum(-1, keepdim=True)) * 0.05
+
+    for step in (0, 16, 256, 272):
+        est_ref.update_every_n_steps(step, occ_fn, occ_thre=1e-2, rng=nf.HostRng(step))
+        est.update_every_n_steps(step, occ_fn, occ_thre=1e-2, rng=nf.HostRng(step, device=DEV))
+        torch.testing.assert_close(est.occs.cpu(), est_ref.occs, rtol=1e-5, atol=1e-8)
+        diff = est.binaries.cpu() != est_ref.binaries
+        assert int(diff.sum()) <= 2  # threshold ties only
+    assert int(est.binaries.sum()) > 0
+    # the bit field used by the marcher follows the update
+    from cednerf_b200.nerfacc.grid import occupancy_bits
+
+    assert torch.equal(occupancy_bits(est.binaries), cb.ops.pack_occupancy(est.binaries))
+    sd = est.state_dict()
+    assert set(sd) == {"resolution", "aabbs", "occs", "binaries"}
