@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""Benchmark of the per-ray rendering hot path: DyNeRF flame_salmon_1-shaped train step (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W             # this repo's CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...   # the CPU restatement of the reference path (oracle/)
+
+One step = the body of the reference's training loop for this path (train_real.py:330-420 without the data loader
+and without the every-16-steps occupancy update): stratified occupancy-grid sampling with the
+no-grad density pre-pass and visibility filtering, the field forward on the surviving samples, compositing, the
+MSE + auxiliary losses of the canonical DyNeRF flags (-te -ta -df -f -wr -ae), backward, GradScaler (2^10) and Adam.
+Rank 0 prints ONE JSON line (see the keys below).  Synthetic data: seeded rays / pixels / occupancy, random-init
+weights with a density boost (cednerf_b200/workload.py)."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rays", type=int, default=2 ** 18, help="rays per rank per step")
+    ap.add_argument("--cpu-rays", type=int, default=2048, help="rays per step of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-steps", type=int, default=3, help="instrumented steps for the per-kernel breakdown")
+    ap.add_argument("--torch-profile", default="", help="write a torch.profiler kernel table of one step to this file")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------------------------
+# the step (shared by both arms: `impl` is cednerf_b200 or the oracle namespace below)
+# --------------------------------------------------------------------------------------------------------------
+def aux_losses(rgb, acc, pixels, extra, flags):
+    """train_real.py:369-409 for the canonical DyNeRF flags (-ae, -wr, -f)."""
+    loss = 0.0
+    t_last = (1 - acc).clamp(1e-6, 1 - 1e-6)
+    loss = loss + (-(t_last * torch.log(t_last) + (1 - t_last) * torch.log(1 - t_last)).mean()) * 1e-3
+    for ex in extra:
+        rgbper = (ex["rgbs"] - pixels[ex["ray_indices"]]).pow(2).sum(dim=-1)
+        loss = loss + (rgbper * ex["weights"].detach()).sum() / pixels.shape[0] * 1e-3
+        if flags.get("use_feat_predict"):
+            loss = loss + ex["latent_losses"].mean()
+    return loss
+
+
+def train_step(impl, field, est, opt, scaler, batch, cfg, rk, reducer=None):
+    rays = impl.Rays(batch["origins"], batch["viewdirs"])
+    rgb, acc, depth, n_samples, extra = impl.render_image(field, est, rays, render_bkgd=batch["color_bkgd"],
+                                                          timestamps=batch["timestamps"], jitter=batch["jitter"], **rk)
+    if n_samples == 0:
+        return None, 0
+    loss = torch.nn.functional.mse_loss(rgb, batch["pixels"]) + aux_losses(rgb, acc, batch["pixels"], extra, cfg.flags)
+    opt.zero_grad()
+    if scaler is not None:
+        scaler.scale(loss).backward()
+        if reducer is not None:
+            reducer.wait()
+        scaler.step(opt)
+        scaler.update()
+    else:
+        (loss * 1024.0).backward()
+        for p in field.parameters():
+            if p.grad is not None:
+                p.grad.div_(1024.0)
+        opt.step()
+    return loss, n_samples
+
+
+class ClockSampler:
+    """SM clock and throttle reasons sampled through NVML during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index, self.sm, self.reasons, self.max_mhz, self.run, self.th = index, [], set(), None, False, None
+
+    def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001 - NVML missing: report it, do not fail the benchmark
+            return
+        names = {"hw_slowdown": pynvml.nvmlClocksEventReasonHwSlowdown if hasattr(pynvml, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                 "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        self.run = True
+
+        def loop():
+            while self.run:
+                try:
+                    self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                    mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    for k, bit in names.items():
+                        if mask & bit:
+                            self.reasons.add(k)
+                except Exception:  # noqa: BLE001
+                    pass
+                time.sleep(0.02)
+
+        self.th = threading.Thread(target=loop, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        self.run = False
+        if self.th is not None:
+            self.th.join(timeout=1.0)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"], "samples": 0}
+        return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.sm)}
+
+
+# algorithmic bytes per launch of each entry point (SURVEY.md §8d per-unit figures x units of the launch)
+def algorithmic_bytes(name, args):
+    if name == "cednerf_hashgrid_fwd":
+        n, L = args[2], args[4]._obj.n_levels
+        return n * (L * 8 * 4 + 12 + L * 4)                     # 512 B table + 12 B xyz + 64 B features (L = 16)
+    if name == "cednerf_hashgrid_bwd":
+        n, L, is16 = args[2], args[4]._obj.n_levels, args[7]
+        b = n * (2 * L * (2 if is16 else 4) + 12)               # dy + xyz
+        if args[8]:
+            b += n * L * 8 * 8                                  # fp32 table-gradient RMW, counted once (1024 B)
+        if args[9]:
+            b += n * (L * 8 * 4 + 12)                           # table re-read for dL/dx + dx write
+        return b
+    if name == "cednerf_mlp_fwd":
+        d, n = args[2]._obj, args[3]
+        hid = (d.n_layers - 1) * 128 if args[5] else 0
+        return n * (d.dim_in[0] * 2 + d.dim_out[d.n_layers - 1] * 2 + hid)
+    if name == "cednerf_mlp_bwd":
+        d, n = args[4]._obj, args[5]
+        return n * (d.dim_in[0] * 2 + (d.n_layers - 1) * 128 + d.dim_out[d.n_layers - 1] * 2 +
+                    (d.dim_in[0] * (4 if args[7] else 2) if args[6] else 0))
+    if name == "cednerf_march":
+        n = args[3]
+        return n * 52                                           # 32 B/ray in + 20 B/ray out; per-sample writes added below
+    if name == "cednerf_composite_fwd":
+        return args[8] * 44 + args[9] * 20
+    if name == "cednerf_composite_bwd":
+        return args[8] * 60 + args[9] * 20
+    return None
+
+
+def run_ours(args):
+    import torch.distributed as dist
+
+    import cednerf_b200 as cb
+    from cednerf_b200 import _lib, dp, workload
+
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl=ours) needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = workload.DYNERF
+    rk = workload.render_kwargs(cfg)
+    est, field = workload.build_scene(cfg, dev, cb, seed=42)
+    est.train(), field.train()
+    opt = torch.optim.Adam(field.parameters(), lr=1e-2, eps=1e-15, fused=True)  # train_real.py:269-274
+    scaler = torch.amp.GradScaler("cuda", init_scale=2 ** 10)                    # train_real.py:252
+    reducer = dp.GradAllReducer(field.parameters(), world) if world > 1 else None
+
+    gen = torch.Generator().manual_seed(1000 + rank)  # every rank draws its own slice of the global batch
+    n_host = 4
+    host = [workload.draw_batch(cfg, args.rays, gen, pin=True) for _ in range(n_host)]
+    resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
+
+    def step_resident(i):
+        return train_step(cb, field, est, opt, scaler, resident[i % n_host], cfg, rk, reducer)
+
+    def step_e2e(i):
+        b = {k: v.to(dev, non_blocking=True) for k, v in host[i % n_host].items()}
+        loss, n_s = train_step(cb, field, est, opt, scaler, b, cfg, rk, reducer)
+        return (None if loss is None else float(loss.item())), n_s  # device -> host read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n_tot = 0
+        for i in range(k):
+            n_tot += fn(i)[1]
+        e1.record()
+        barrier()
+        ms = dp.max_over_ranks(e0.elapsed_time(e1) / k, dev)
+        return ms, n_tot / k, (_lib.launch_count() - l0) // k
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+        step_e2e(i)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ms, samples, launches = timed(step_resident, args.steps)
+    clk = clocks.stop() if rank == 0 else None
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+    samples_all = dp.sum_over_ranks(samples, dev)
+
+    # ---- per-entry-point breakdown and the roofline of the dominant kernel (CUDA events, same stream) -----------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    roof, breakdown = None, {}
+    if rank == 0 and args.profile_steps > 0:
+        rec = []
+        real_call = _lib.call
+
+        def recording_call(name, *a):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            real_call(name, *a)
+            e.record()
+            rec.append((name, a, s, e))
+
+        for m in (_lib, cb.ops):
+            m.call = recording_call
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(args.profile_steps):
+            step_resident(i)
+        torch.cuda.synchronize()
+        prof_ms = (time.perf_counter() - t0) * 1e3 / args.profile_steps
+        for m in (_lib, cb.ops):
+            m.call = real_call
+        agg = {}
+        for name, a, s, e in rec:
+            t = s.elapsed_time(e)
+            by = algorithmic_bytes(name, a)
+            d = agg.setdefault(name, {"ms": 0.0, "launches": 0, "bytes": 0, "has_bytes": by is not None})
+            d["ms"] += t
+            d["launches"] += 1
+            d["bytes"] += by or 0
+        for name, d in agg.items():
+            breakdown[name] = {"ms_per_step": round(d["ms"] / args.profile_steps, 4),
+                               "launches_per_step": d["launches"] // args.profile_steps}
+        top = max((n for n in agg if agg[n]["has_bytes"]), key=lambda n: agg[n]["ms"])
+        d = agg[top]
+        achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+        roof = {"kernel": top, "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
+                "frac": round(achieved / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": round(d["ms"] / d["launches"], 4), "bytes_per_launch": d["bytes"] // d["launches"],
+                "share_of_step": round(d["ms"] / args.profile_steps / prof_ms, 3)}
+        breakdown["_ours_total_ms"] = round(sum(v["ms"] for v in agg.values()) / args.profile_steps, 3)
+        breakdown["_instrumented_step_ms"] = round(prof_ms, 3)
+
+    if rank == 0 and args.torch_profile:
+        from torch.profiler import ProfilerActivity, profile
+
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            step_resident(0)
+            torch.cuda.synchronize()
+        with open(args.torch_profile, "w") as f:
+            f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=70))
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = run_reference_steps(args.cpu_rays, steps=2, warmup=1)
+
+    if rank == 0:
+        rays_all = args.rays * world
+        h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+        line = {
+            "metric": "train_step_rays_per_s", "value": round(rays_all / (ms * 1e-3), 1), "unit": "rays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16 (MLP, tables) / f32 (marching, compositing, grads)",
+            "data": "synthetic",
+            "config": {"workload": f"{cfg.name} train step, {args.rays} rays/GPU/step, occgrid sampler "
+                                   f"(BASELINE.json configs[1]); flags -te -ta -df -f -wr -ae; GradScaler 2^10 + Adam",
+                       "rays_per_gpu": args.rays, "samples_per_step": round(samples_all, 1),
+                       "samples_per_ray": round(samples_all / rays_all, 3),
+                       "samples_per_s": round(samples_all / (ms * 1e-3), 1),
+                       "l2": "working set (96 MB fp16 table + 191 MB fp32 master + 383 MB Adam state + per-step "
+                             "buffers) far exceeds the 126 MB L2; 4 rotating input batches",
+                       "occ_update": "not in the step (runs every 16 steps in the reference; SURVEY.md §8f N1)",
+                       "parallelism": f"dp{world}" if world > 1 else "single"},
+            "e2e": {"value": round(rays_all / (ms_e2e * 1e-3), 1), "unit": "rays/s", "ms_per_step": round(ms_e2e, 4),
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+            "breakdown": breakdown,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------------------
+# reference arm: the CPU restatement of the reference path (the reference itself cannot run: nerfacc / tiny-cuda-nn /
+# Taichi are CUDA-only third-party packages that are not installed and the reference has no CPU path)
+# --------------------------------------------------------------------------------------------------------------
+class _OracleImpl:
+    def __init__(self):
+        from oracle import cednerf_ref as cr
+        from oracle import nerfacc_ref as nf
+
+        self.OccGridEstimator, self.DNGPradianceField = nf.OccGridEstimator, cr.DNGPradianceField
+        self.Rays, self.render_image = cr.Rays, cr.render_image
+
+
+def run_reference_steps(n_rays, steps, warmup):
+    from cednerf_b200 import workload
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    impl = _OracleImpl()
+    cfg = workload.DYNERF
+    rk = workload.render_kwargs(cfg)
+    est, field = workload.build_scene(cfg, "cpu", impl, seed=42)
+    est.train(), field.train()
+    opt = torch.optim.Adam(field.parameters(), lr=1e-2, eps=1e-15)
+    gen = torch.Generator().manual_seed(1000)
+    batches = [workload.draw_batch(cfg, n_rays, gen) for _ in range(2)]
+    times, samples = [], 0
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, n_s = train_step(impl, field, est, opt, None, batches[i % 2], cfg, rk)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+            samples += n_s
+    sec = sum(times) / len(times)
+    return {"value": round(n_rays / sec, 1), "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n_rays} rays/step of the same workload, {steps} timed steps after {warmup} warm-up "
+                      f"({round(samples / steps / n_rays, 2)} samples/ray), oracle/ PyTorch-CPU + OpenMP C marcher",
+            "ms_per_step": round(sec * 1e3, 1), "samples_per_s": round(samples / steps / sec, 1)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from cednerf_b200 import workload
+
+    cfg = workload.DYNERF
+    cpu = run_reference_steps(args.cpu_rays, steps=max(1, min(args.steps, 3)), warmup=1)
+    line = {"impl": "reference", "metric": "train_step_rays_per_s", "value": cpu["value"], "unit": "rays/s",
+            "n_gpus": args.gpus, "steps": max(1, min(args.steps, 3)), "warmup": 1, "ms_per_step": cpu["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (CPU), fp16-rounded MLP",
+            "data": "synthetic",
+            "config": {"workload": f"{cfg.name} train step, bounded sample of {args.cpu_rays} rays/step on the host CPU "
+                                   f"(BASELINE.json configs[1]); flags -te -ta -df -f -wr -ae; Adam"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

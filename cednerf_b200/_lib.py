@@ -74,6 +74,7 @@ def load() -> ctypes.CDLL:
     lib = ctypes.CDLL(LIB_PATH)
     lib.cednerf_last_error.restype = ctypes.c_char_p
     lib.cednerf_scan_workspace_bytes.restype = ctypes.c_int64
+    lib.cednerf_launch_count.restype = ctypes.c_int64
     lib.cednerf_scan_workspace_bytes.argtypes = [ctypes.c_int64]
     for name, sig in _SIGNATURES.items():
         fn = getattr(lib, name)
@@ -85,7 +86,7 @@ def load() -> ctypes.CDLL:
 
 def exported_symbols():
     return sorted(list(_SIGNATURES) + ["cednerf_last_error", "cednerf_abi_version", "cednerf_check_device",
-                                       "cednerf_scan_workspace_bytes"])
+                                       "cednerf_scan_workspace_bytes", "cednerf_launch_count"])
 
 
 def ptr(t: Optional[torch.Tensor]):
@@ -103,14 +104,28 @@ def stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+_timers = None  # bench.py's per-entry-point CUDA-event instrumentation (None = off)
+
+
 def call(name: str, *args):
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if _timers is not None:
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        rc = getattr(lib, name)(*args)
+        end.record()
+        _timers.append((name, start, end))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {lib.cednerf_last_error().decode()}")
 
 
 _device_checked = False
+
+
+def launch_count() -> int:
+    return int(load().cednerf_launch_count())
 
 
 def check_device():

@@ -4,7 +4,15 @@
 
 #include "common.cuh"
 
+#include <atomic>
+
 static thread_local char g_last_error[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void cednerf_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// number of kernels this library has launched in this process (every entry point counts its own)
+CEDNERF_EXPORT int64_t cednerf_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 
 void cednerf_set_error(const char* fmt, ...) {
   va_list ap;

@@ -12,8 +12,10 @@
 #define CEDNERF_ERR_UNSUPPORTED (-2)
 
 void cednerf_set_error(const char* fmt, ...);
+void cednerf_count_launches(int n);  // bookkeeping for cednerf_launch_count()
 
-static inline int cednerf_check_launch(const char* what) {
+static inline int cednerf_check_launch(const char* what, int n_launches = 1) {
+  cednerf_count_launches(n_launches);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     cednerf_set_error("%s: %s", what, cudaGetErrorString(e));

@@ -495,5 +495,5 @@ CEDNERF_EXPORT int cednerf_exclusive_scan(const int32_t* counts, int64_t n, int6
   scan_tile_sums_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(counts, n, tile_sums);
   scan_tile_offsets_kernel<<<1, SCAN_THREADS, 0, st>>>(tile_sums, tiles, total);
   scan_apply_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(counts, n, tile_sums, starts, packed_info);
-  return cednerf_check_launch("cednerf_exclusive_scan");
+  return cednerf_check_launch("cednerf_exclusive_scan", 3);
 }

@@ -115,7 +115,11 @@ class OccGridEstimator(torch.nn.Module):
             x = self.aabbs[l, :3] + x * (self.aabbs[l, 3:] - self.aabbs[l, :3])
             occ = occ_eval_fn(x).squeeze(-1).float()
             cell = l * cpl + idx
-            self.occs[cell] = torch.maximum(self.occs[cell] * ema_decay, occ)
+            # nerfacc writes occs[cell] = max(occs[cell]*decay, occ) with an index_put whose winner among duplicate
+            # cells (uniform draws that repeat or coincide with occupied cells) is undefined on CUDA; here the
+            # largest candidate wins (scatter-amax), which is one of those outcomes and is deterministic.
+            self.occs.scatter_reduce_(0, cell, torch.maximum(self.occs[cell] * ema_decay, occ), "amax",
+                                      include_self=False)
         thre = torch.clamp(self.occs[self.occs >= 0].mean(), max=occ_thre).reshape(1).contiguous()
         bits = torch.empty(self.occs.numel() // 32, dtype=torch.int32, device=dev)
         ops.occ_threshold_pack(self.occs, thre, self.binaries, bits)

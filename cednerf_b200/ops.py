@@ -263,7 +263,7 @@ class MlpFunction(torch.autograd.Function):
     """x [N, n_in] (any float dtype) -> fp16 [N, n_out].
 
     The operand handed to the kernel is fp16 [N, pad16(n_in)] with the padding columns set to 1.0 (tcnn's
-    input padding); d_x comes back in fp32 and autograd casts it to x's dtype."""
+    input padding); d_x is produced in the network precision (fp16), as tcnn's dL_dinput is."""
 
     @staticmethod
     def forward(ctx, x, params, image, desc: MlpDesc, save: bool, n_out: int):
@@ -293,10 +293,10 @@ class MlpFunction(torch.autograd.Function):
         dy = torch.zeros(n, out_pad, dtype=F16, device=x16.device)
         dy[:, : ctx.n_out] = g
         need_x, need_p = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        d_x = torch.empty(n, desc.dim_in[0], dtype=F32, device=x16.device) if need_x else None
+        d_x = torch.empty(n, desc.dim_in[0], dtype=F16, device=x16.device) if need_x else None
         d_p = torch.zeros(ctx.n_params, dtype=F32, device=x16.device) if need_p else None
         if need_x or need_p:
-            call("cednerf_mlp_bwd", ptr(x16), ptr(hidden), ptr(dy), ptr(image), ctypes.byref(desc), n, ptr(d_x), 1,
+            call("cednerf_mlp_bwd", ptr(x16), ptr(hidden), ptr(dy), ptr(image), ctypes.byref(desc), n, ptr(d_x), 0,
                  ptr(d_p), stream())
         return (None if d_x is None else d_x[:, : ctx.n_in]), d_p, None, None, None, None
 

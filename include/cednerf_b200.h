@@ -35,6 +35,7 @@ extern "C" {
 const char* cednerf_last_error(void);
 int cednerf_abi_version(void);
 int cednerf_check_device(void); /* 0 iff the current device is compute capability 10.x */
+int64_t cednerf_launch_count(void); /* kernels launched by this library so far in this process */
 
 /* ---- K1: marching --------------------------------------------------------------------------------
  * nerfacc.ray_aabb_intersect — reference call site cednerf/utils.py:215 */

@@ -19,7 +19,7 @@ import math
 
 import torch
 
-from .tcnn_ref import _RoundF16Fwd, _corner_index, grid_levels, hashgrid_forward
+from .tcnn_ref import _RoundF16, _RoundF16Fwd, _corner_index, grid_levels, hashgrid_forward
 
 
 def encoder_levels(max_params=2 ** 19, levels=16, base_res=16.0, max_res=2048.0):
@@ -106,7 +106,7 @@ def hashgrid4d_forward(xyzt, table, levels, taichi_compat=False):
             lo, hi = tab[idx, k], tab[idx, k + 1]
             acc = acc + w[:, None] * (lo * (1.0 - tau)[:, None] + hi * tau[:, None])
         outs.append(acc)
-    return _RoundF16Fwd.apply(torch.cat(outs, -1))
+    return _RoundF16.apply(torch.cat(outs, -1))
 
 
 class HashEncoder4D(torch.nn.Module):

@@ -16,7 +16,11 @@ Numerical contract shared with cednerf_b200 (documented in DESIGN.md):
   * Frequency: sin(pi * (2^k x + phase/2)) evaluated in fp64 then rounded to fp16.
   * MLP: fp16 weights/activations, fp32 accumulate, ReLU hidden, no bias, inputs padded to a
     multiple of 16 with the constant 1.0 (tcnn behaviour), outputs padded to 16 and sliced;
-    gradients between layers rounded to fp16, weight gradients and input gradients fp32.
+    gradients between layers rounded to fp16, weight gradients fp32.
+  * dtype flow of gradients, as in tcnn's torch bindings: every encoding / network OUTPUT is an fp16
+    tensor, so the gradient that reaches it is fp16-rounded; the network's INPUT gradient is produced in
+    the network precision (tcnn: dL_dinput is a __half matrix) and is fp16-rounded as well; the hash
+    grid's and the Frequency encoding's input gradients (dL/dx) are fp32.
 """
 from __future__ import annotations
 
@@ -112,7 +116,7 @@ def hashgrid_forward(x: torch.Tensor, table: torch.Tensor, levels, n_features: i
             acc = acc + w[:, None] * tab[idx]
         outs.append(acc)
     out = torch.cat(outs, -1)
-    return _RoundF16Fwd.apply(out) if round_output else out
+    return _RoundF16.apply(out) if round_output else out
 
 
 def frequency_encode(x: torch.Tensor, n_frequencies: int = 4) -> torch.Tensor:
@@ -123,7 +127,7 @@ def frequency_encode(x: torch.Tensor, n_frequencies: int = 4) -> torch.Tensor:
     for j in range(x.shape[-1] * 2 * n):
         dim, k, p = j // (2 * n), (j // 2) % n, j % 2
         cols.append(torch.sin(math.pi * (xd[:, dim] * float(2 ** k) + 0.5 * p)))
-    return _RoundF16Fwd.apply(torch.stack(cols, -1).float())
+    return _RoundF16.apply(torch.stack(cols, -1).float())
 
 
 def sh_encode_deg2(d01: torch.Tensor) -> torch.Tensor:
@@ -132,7 +136,7 @@ def sh_encode_deg2(d01: torch.Tensor) -> torch.Tensor:
     x, y, z = v[:, 0], v[:, 1], v[:, 2]
     out = torch.stack([torch.full_like(x, 0.28209479177387814), -0.48860251190291987 * y,
                        0.48860251190291987 * z, -0.48860251190291987 * x], -1)
-    return _RoundF16Fwd.apply(out)
+    return _RoundF16.apply(out)
 
 
 def pad16(n: int) -> int:
@@ -157,7 +161,7 @@ def mlp_forward(x: torch.Tensor, params: torch.Tensor, n_in, n_out, n_neurons=64
                 output_f16: bool = True) -> torch.Tensor:
     """F-table numerics.  x [N,n_in] (any float) -> [N,n_out] f32 holding fp16-rounded values."""
     shapes = mlp_layer_shapes(n_in, n_out, n_neurons, n_hidden)
-    h = _RoundF16Fwd.apply(x.float())
+    h = _RoundF16.apply(x.float())
     if shapes[0][1] > n_in:
         h = torch.cat([h, torch.ones(h.shape[0], shapes[0][1] - n_in, device=h.device)], -1)
     off = 0
