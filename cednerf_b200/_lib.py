@@ -30,7 +30,13 @@ class MlpDesc(ctypes.Structure):
                 ("image_off", ctypes.c_int * MLP_MAX_LAYERS), ("image_bytes", ctypes.c_int)]
 
 
-# p = pointer, i = int, l = int64, f = float, G = GridLevels*, M = MlpDesc*
+class FieldDesc(ctypes.Structure):
+    _fields_ = [("aabb", ctypes.c_float * 6), ("moving_step", ctypes.c_float), ("use_div_offsets", ctypes.c_int),
+                ("time_mode", ctypes.c_int), ("time_before_sigma", ctypes.c_int), ("f1", MlpDesc), ("f2", MlpDesc),
+                ("f3", MlpDesc), ("levels", GridLevels)]
+
+
+# p = pointer, i = int, l = int64, f = float, G = GridLevels*, M = MlpDesc*, F = FieldDesc*
 _SIGNATURES = {
     "cednerf_ray_aabb_intersect": "pplpifffpppp",
     "cednerf_sort_boundaries": "pplippp",
@@ -50,6 +56,7 @@ _SIGNATURES = {
     "cednerf_mlp_pack_weights": "pMpp",
     "cednerf_mlp_fwd": "ppMlppp",
     "cednerf_mlp_bwd": "ppppMlpipp",
+    "cednerf_field_fwd": "ppppppppilppppFppp",
     "cednerf_ray_offsets": "pllpp",
     "cednerf_composite_fwd": "pppppppillpppppppifp",
     "cednerf_composite_bwd": "pppppppillppppppppppfp",
@@ -58,7 +65,7 @@ _SIGNATURES = {
     "cednerf_accumulate_bwd": "ppiplpppp",
 }
 _CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_int64, "f": ctypes.c_float,
-       "G": ctypes.POINTER(GridLevels), "M": ctypes.POINTER(MlpDesc)}
+       "G": ctypes.POINTER(GridLevels), "M": ctypes.POINTER(MlpDesc), "F": ctypes.POINTER(FieldDesc)}
 
 _lib = None
 

@@ -1,0 +1,395 @@
+// Fused radiance-field query: positions -> deformation MLP -> hash-grid encode -> density MLP (-> colour MLP)
+// in ONE kernel per 128-sample tile (no activation, feature or position tensor ever touches HBM).
+//
+// Replaces the chain DNGPradianceField.query_density / .forward executes as ~40 separate PyTorch / tcnn launches
+// (cednerf/model.py:354-365 query_move, :378-384 normalise + selector + hash, :386-403 time embedding, :406-417
+// density MLP + trunc_exp, :447-466 SH + colour MLP + sigmoid), together with the position closure of
+// cednerf/utils.py:74-104 (x = o + d * (t0 + t1) / 2, t = timestamps[ray]).
+//
+// Per tile: thread r owns sample r end to end (its position, Frequency / SH / time encodings, its 16x8 hash
+// gathers, its activations after each layer); the only cross-thread step is the tensor-core layer itself:
+// operand rows are written to a 128-byte-swizzled shared-memory tile, one thread issues tcgen05.mma against the
+// weight images resident in shared memory, the accumulator comes back from TMEM with tcgen05.ld.
+// Adjacent threads hold adjacent samples of the same ray, so one gather instruction touches one level for 32
+// neighbouring samples: coarse and middle levels coalesce into few sectors, L1/L2 serve the reuse.
+#include "hashgrid.cuh"
+#include "tc05.cuh"
+
+struct CednerfFieldDesc {
+  float aabb[6];
+  float moving_step;
+  int use_div_offsets;    // deformation net emits 6 values: move = o[:3]*MS + tanh(o[3:])*MS   (model.py:358-363)
+  int time_mode;          // 0 none, 1 SinusoidalEncoder, 2 SinusoidalEncoderWithExp (attenuated by |move|)
+  int time_before_sigma;  // 1: density-MLP input = [hash | time9];  0: colour-MLP input = [sh4 | feat15 | time9]
+  CednerfMlpDesc f1, f2, f3;  // deformation, density, colour networks
+  CednerfGridLevels levels;
+};
+
+namespace {
+
+struct FieldFwdArgs {
+  const int64_t* ridx;  // packed samples (with t0, t1, rays_o, rays_d) ...
+  const float* t0;
+  const float* t1;
+  const float* rays_o;
+  const float* rays_d;
+  const float* x;       // ... or explicit points (with dirs)
+  const float* dirs;
+  const float* t;       // timestamps: [n_rays] when ridx != null else [n]; stride 0 = one value for all
+  int t_stride;
+  int64_t n;
+  const uint8_t* img1;
+  const uint8_t* img2;
+  const uint8_t* img3;
+  const __half* table;
+  float* sigma;   // [n]
+  float* rgb;     // [n,3] or null (density only)
+  CednerfFieldDesc d;
+};
+
+// layers of one network on the tile in abuf[cur]; the last layer's accumulator is left in TMEM columns [0, N_last)
+__device__ __forceinline__ void run_chain(const CednerfMlpDesc& d, const uint8_t* wimg, uint8_t* abuf0, uint8_t* abuf1,
+                                          int& cur, uint32_t tmem_base, uint32_t tmem_warp, uint64_t* bar,
+                                          uint32_t& phase, int tid) {
+  const int L = d.n_layers;
+  for (int l = 0; l < L; ++l) {
+    const int K = d.dim_in[l], N = d.dim_out[l];
+    uint8_t* a_cur = cur ? abuf1 : abuf0;
+    uint8_t* a_nxt = cur ? abuf0 : abuf1;
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t ad = make_desc(smem_u32(a_cur), 1, 64);
+      const uint64_t bd = make_desc(smem_u32(wimg + d.image_off[l]), 1, 64);
+      const uint32_t id = make_idesc(128, N, 0, 0);
+      for (int k = 0; k < K / 16; ++k) umma(tmem_base, ad + 2 * k, bd + 2 * k, id, k > 0);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    if (l < L - 1) {
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) {
+        uint32_t r[16];
+        tmem_ld16(tmem_warp + cb * 16, r);
+        tmem_ld_wait();
+        uint32_t p[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          p[j] = pack_h2(fmaxf(__uint_as_float(r[2 * j]), 0.f), fmaxf(__uint_as_float(r[2 * j + 1]), 0.f));
+        *reinterpret_cast<uint4*>(a_nxt + swz(tid, 2 * cb)) = make_uint4(p[0], p[1], p[2], p[3]);
+        *reinterpret_cast<uint4*>(a_nxt + swz(tid, 2 * cb + 1)) = make_uint4(p[4], p[5], p[6], p[7]);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      cur ^= 1;
+    }
+  }
+}
+
+// value the tensor-core chain hands on: fp32 accumulator rounded to fp16 (tcnn network output precision)
+__device__ __forceinline__ float rnd16(uint32_t acc_bits) { return __half2float(__float2half_rn(__uint_as_float(acc_bits))); }
+
+__device__ __forceinline__ void time_embedding(float tv, float mvnorm, int mode, float* e /*[9]*/) {
+  const float half_pi = 1.5707963267948966f;
+  e[0] = tv;
+  if (mode == 1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float tb = tv * (float)(1 << i);
+      e[1 + i] = sinf(tb);
+      e[5 + i] = sinf(tb + half_pi);
+    }
+  } else {
+    const float scm[4] = {0.f, 2.f, 8.f, 24.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float tb = tv * (float)(1 << i);
+      const float att = expf(-1.f * (mvnorm * scm[i]));
+      e[1 + 2 * i] = sinf(tb) * att;
+      e[2 + 2 * i] = sinf(tb + half_pi) * att;
+    }
+  }
+}
+
+// 2*L hash features of one point, packed as L half2 words (numerics of hashgrid_fwd_kernel)
+template <int LG>
+__device__ __forceinline__ void hash_levels(const float* xn, const __half* __restrict__ table, const CednerfGridLevels& lv,
+                                            int l0, uint32_t* feat) {
+  const __half2* t2 = reinterpret_cast<const __half2*>(table);
+  Cell c[LG];
+  __half2 v[LG][8];
+#pragma unroll
+  for (int a = 0; a < LG; ++a) {
+    const int l = l0 + a;
+    c[a] = locate(xn, lv.scale[l]);
+    const uint32_t res = lv.res[l], size = lv.size[l], off = lv.offset[l];
+    const bool hashed = lv.hashed[l] != 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t idx =
+          off + corner_index(c[a].g[0] + (k & 1), c[a].g[1] + ((k >> 1) & 1), c[a].g[2] + ((k >> 2) & 1), res, size, hashed);
+      v[a][k] = __ldg(t2 + idx);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < LG; ++a) {
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float w = corner_weight(c[a], k);
+      const float2 f = __half22float2(v[a][k]);
+      a0 = __fadd_rn(a0, __fmul_rn(w, f.x));
+      a1 = __fadd_rn(a1, __fmul_rn(w, f.y));
+    }
+    feat[l0 + a] = pack_h2(a0, a1);
+  }
+}
+
+__global__ void __launch_bounds__(MLP_TILE) field_fwd_kernel(FieldFwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const CednerfFieldDesc& d = a.d;
+  const bool want_rgb = a.rgb != nullptr;
+  uint8_t* w1 = smem;
+  uint8_t* w2 = w1 + d.f1.image_bytes;
+  uint8_t* w3 = w2 + d.f2.image_bytes;
+  uint8_t* abuf0 = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(w3 + (want_rgb ? d.f3.image_bytes : 0)) + 1023) & ~(uintptr_t)1023);
+  uint8_t* abuf1 = abuf0 + MLP_TILE_BYTES;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int q = tid; q < d.f1.image_bytes / 16; q += blockDim.x)
+    reinterpret_cast<uint4*>(w1)[q] = __ldg(reinterpret_cast<const uint4*>(a.img1) + q);
+  for (int q = tid; q < d.f2.image_bytes / 16; q += blockDim.x)
+    reinterpret_cast<uint4*>(w2)[q] = __ldg(reinterpret_cast<const uint4*>(a.img2) + q);
+  if (want_rgb)
+    for (int q = tid; q < d.f3.image_bytes / 16; q += blockDim.x)
+      reinterpret_cast<uint4*>(w3)[q] = __ldg(reinterpret_cast<const uint4*>(a.img3) + q);
+  if (warp == 0) tmem_alloc(&tmem_base_s, 64);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t tmem_warp = tmem_base + ((uint32_t)(warp * 32) << 16);
+  uint32_t phase = 0;
+  const int64_t n_tiles = (a.n + MLP_TILE - 1) / MLP_TILE;
+  const float ms = d.moving_step;
+  const int L = d.levels.n_levels;
+  const uint32_t one2 = 0x3C003C00u;  // half2(1, 1): tcnn's input padding value
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t s = tile * MLP_TILE + tid;
+    const bool ok = s < a.n;
+    // ---- the sample: position, time, direction (cednerf/utils.py:74-104) -------------------------------------
+    float x[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 1.f}, tv = 0.f;
+    if (ok) {
+      if (a.ridx) {
+        const int64_t r = a.ridx[s];
+        const float tm = __fadd_rn(a.t0[s], a.t1[s]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          dir[k] = a.rays_d[3 * r + k];
+          x[k] = __fadd_rn(a.rays_o[3 * r + k], __fmul_rn(__fmul_rn(dir[k], tm), 0.5f));
+        }
+        tv = a.t[r * a.t_stride];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          x[k] = a.x[3 * s + k];
+          if (a.dirs) dir[k] = a.dirs[3 * s + k];
+        }
+        tv = a.t[s * a.t_stride];
+      }
+    }
+    // ---- deformation net input: Frequency(x, y, z, t), 4 octaves (model.py:205-213) ---------------------------
+    {
+      const float in4[4] = {x[0], x[1], x[2], tv};
+#pragma unroll
+      for (int dim = 0; dim < 4; ++dim) {
+        uint32_t p[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float ph = in4[dim] * (float)(1 << k);
+          p[k] = pack_h2(sinpif(ph), sinpif(ph + 0.5f));
+        }
+        *reinterpret_cast<uint4*>(abuf0 + swz(tid, dim)) = make_uint4(p[0], p[1], p[2], p[3]);
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    int cur = 0;
+    run_chain(d.f1, w1, abuf0, abuf1, cur, tmem_base, tmem_warp, &bar, phase, tid);
+    float xn[3], mvnorm;
+    bool selector = true;
+    {
+      uint32_t r[16];
+      tmem_ld16(tmem_warp, r);
+      tmem_ld_wait();
+      float mv[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        mv[k] = rnd16(r[k]) * ms;
+        if (d.use_div_offsets) mv[k] = mv[k] + tanhf(rnd16(r[3 + k])) * ms;
+        const float xm = x[k] + mv[k];
+        xn[k] = __fdiv_rn(__fsub_rn(xm, d.aabb[k]), __fsub_rn(d.aabb[3 + k], d.aabb[k]));
+        selector = selector && (xn[k] > 0.f) && (xn[k] < 1.f);
+      }
+      mvnorm = sqrtf(mv[0] * mv[0] + mv[1] * mv[1] + mv[2] * mv[2]);
+    }
+    // ---- density net input: [hash 2L | time 9 | 1.0 padding] (model.py:384-403) -------------------------------
+    float temb[9];
+    if (d.time_mode) time_embedding(tv, mvnorm, d.time_mode, temb);
+    {
+      uint32_t feat[16];
+#pragma unroll
+      for (int l = 0; l < 16; ++l) feat[l] = one2;
+      if ((L & 3) == 0) {
+#pragma unroll
+        for (int l0 = 0; l0 < 16; l0 += 4)
+          if (l0 < L) hash_levels<4>(xn, a.table, d.levels, l0, feat);
+      } else {
+#pragma unroll
+        for (int l0 = 0; l0 < 16; ++l0)
+          if (l0 < L) hash_levels<1>(xn, a.table, d.levels, l0, feat);
+      }
+      const int k2 = d.f2.dim_in[0];
+      uint32_t row[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) row[j] = one2;
+#pragma unroll
+      for (int l = 0; l < 16; ++l)
+        if (l < L) row[l] = feat[l];
+      if (d.time_mode && d.time_before_sigma) {
+        // 9 time features start at column 2L (even): pairs (e0,e1) .. (e6,e7), then (e8, 1.0)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) row[L + j] = pack_h2(temb[2 * j], temb[2 * j + 1]);
+        row[L + 4] = pack_h2(temb[8], 1.f);
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c * 8 < k2)
+          *reinterpret_cast<uint4*>(abuf0 + swz(tid, c)) = make_uint4(row[4 * c], row[4 * c + 1], row[4 * c + 2], row[4 * c + 3]);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    cur = 0;
+    run_chain(d.f2, w2, abuf0, abuf1, cur, tmem_base, tmem_warp, &bar, phase, tid);
+    uint32_t o2[16];
+    tmem_ld16(tmem_warp, o2);
+    tmem_ld_wait();
+    if (ok) a.sigma[s] = selector ? expf(rnd16(o2[0]) - 1.f) : 0.f;  // trunc_exp(raw - 1) * selector (model.py:414-417)
+    if (!want_rgb) {
+      tc_fence_before();
+      __syncthreads();
+      continue;
+    }
+    // ---- colour net input: [SH4(dir) | 15 geometry features (| time 9) | 1.0 padding] (model.py:447-466) --------
+    {
+      const float nrm = sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+      float v[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) v[k] = ((dir[k] / nrm + 1.f) / 2.f) * 2.f - 1.f;
+      float in[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) in[j] = 1.f;
+      in[0] = 0.28209479177387814f;
+      in[1] = -0.48860251190291987f * v[1];
+      in[2] = 0.48860251190291987f * v[2];
+      in[3] = -0.48860251190291987f * v[0];
+#pragma unroll
+      for (int j = 0; j < 15; ++j) in[4 + j] = rnd16(o2[1 + j]);
+      if (d.time_mode && !d.time_before_sigma) {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) in[19 + j] = temb[j];
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<uint4*>(abuf0 + swz(tid, c)) =
+            make_uint4(pack_h2(in[8 * c], in[8 * c + 1]), pack_h2(in[8 * c + 2], in[8 * c + 3]),
+                       pack_h2(in[8 * c + 4], in[8 * c + 5]), pack_h2(in[8 * c + 6], in[8 * c + 7]));
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    cur = 0;
+    run_chain(d.f3, w3, abuf0, abuf1, cur, tmem_base, tmem_warp, &bar, phase, tid);
+    {
+      uint32_t r[16];
+      tmem_ld16(tmem_warp, r);
+      tmem_ld_wait();
+      if (ok) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) a.rgb[3 * s + k] = 1.f / (1.f + expf(-rnd16(r[k])));
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 64);
+}
+
+int check_field(const CednerfFieldDesc* d, bool want_rgb) {
+  if (!d) return 0;
+  const int L = d->levels.n_levels;
+  if (L < 1 || L > 16) return 0;
+  if (d->time_mode < 0 || d->time_mode > 2) return 0;
+  const int n1 = d->f1.n_layers, n2 = d->f2.n_layers, n3 = d->f3.n_layers;
+  if (n1 < 1 || n1 > MLP_MAX_LAYERS || n2 < 1 || n2 > MLP_MAX_LAYERS) return 0;
+  if (d->f1.dim_in[0] != 32 || d->f1.dim_out[n1 - 1] != 16) return 0;
+  const int in2 = 2 * L + ((d->time_mode && d->time_before_sigma) ? 9 : 0);
+  if (d->f2.dim_in[0] != (in2 + 15) / 16 * 16 || d->f2.dim_out[n2 - 1] != 16) return 0;
+  if (want_rgb) {
+    if (n3 < 1 || n3 > MLP_MAX_LAYERS) return 0;
+    const int in3 = 19 + ((d->time_mode && !d->time_before_sigma) ? 9 : 0);
+    if (d->f3.dim_in[0] != (in3 + 15) / 16 * 16 || d->f3.dim_out[n3 - 1] != 16) return 0;
+  }
+  return 1;
+}
+
+}  // namespace
+
+// sigma (and rgb) of n samples.  Samples are either packed ray samples (ray_indices, t_starts, t_ends, rays_o,
+// rays_d; timestamps indexed by ray) or explicit points (x, dirs; timestamps indexed by point); t_stride 0 = one
+// timestamp for all (the reference's eval path, cednerf/utils.py:187-191).  rgb == NULL: density only (the sigma_fn
+// pre-pass of OccGridEstimator.sampling and occ_eval_fn).
+CEDNERF_EXPORT int cednerf_field_fwd(const int64_t* ray_indices, const float* t_starts, const float* t_ends,
+                                     const float* rays_o, const float* rays_d, const float* x, const float* dirs,
+                                     const float* timestamps, int t_stride, int64_t n, const void* image_deform,
+                                     const void* image_density, const void* image_colour, const void* table_f16,
+                                     const CednerfFieldDesc* desc, float* sigma, float* rgb, void* stream) {
+  CEDNERF_REQUIRE(check_field(desc, rgb != nullptr), "bad field descriptor");
+  CEDNERF_REQUIRE(n >= 0 && sigma && timestamps, "bad arguments");
+  CEDNERF_REQUIRE((ray_indices && t_starts && t_ends && rays_o && rays_d) || (!ray_indices && x), "need packed samples or points");
+  CEDNERF_REQUIRE(!rgb || ray_indices || dirs, "colour needs directions");
+  if (n == 0) return 0;
+  const int smem = desc->f1.image_bytes + desc->f2.image_bytes + (rgb ? desc->f3.image_bytes : 0) + 2 * MLP_TILE_BYTES + 2048;
+  static int configured = 0;
+  if (configured < smem) {
+    cudaError_t e = cudaFuncSetAttribute(field_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e != cudaSuccess) {
+      cednerf_set_error("cednerf_field_fwd: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured = 160 * 1024;
+  }
+  FieldFwdArgs a{ray_indices, t_starts, t_ends, rays_o, rays_d, x, dirs, timestamps, t_stride, n,
+                 (const uint8_t*)image_deform, (const uint8_t*)image_density, (const uint8_t*)image_colour,
+                 (const __half*)table_f16, sigma, rgb, *desc};
+  const int64_t tiles = (n + MLP_TILE - 1) / MLP_TILE;
+  const int per_sm = smem <= 72 * 1024 ? 3 : (smem <= 110 * 1024 ? 2 : 1);
+  const int64_t max_ctas = (int64_t)cednerf_num_sms() * per_sm;
+  field_fwd_kernel<<<(unsigned)(tiles < max_ctas ? tiles : max_ctas), MLP_TILE, smem, (cudaStream_t)stream>>>(a);
+  return cednerf_check_launch("cednerf_field_fwd");
+}

@@ -1,0 +1,123 @@
+// tcgen05 / TMEM / mbarrier PTX wrappers and the 128-byte-swizzle tile helpers shared by the MLP and field kernels.
+#pragma once
+#include "common.cuh"
+
+#define MLP_MAX_LAYERS 5
+#define MLP_TILE 128
+#define MLP_ROW_BYTES 128
+#define MLP_TILE_BYTES (MLP_TILE * MLP_ROW_BYTES)
+
+struct CednerfMlpDesc {
+  int n_layers;                    // hidden layers + 1
+  int dim_in[MLP_MAX_LAYERS];      // padded (multiple of 16, <= 64)
+  int dim_out[MLP_MAX_LAYERS];     // 64 for hidden layers, padded n_out (16..64) for the last
+  int param_off[MLP_MAX_LAYERS];   // element offset of W_l ([dim_out, dim_in] row-major) in the flat fp32 params
+  int image_off[MLP_MAX_LAYERS];   // byte offset of W_l's swizzled fp16 image (dim_out rows x 128 B)
+  int image_bytes;
+};
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0, spins = 0;
+  while (!done) {
+    if (++spins > (1u << 24)) __trap();  // a lost completion must surface as an error, never as a hang
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// shared-memory matrix descriptor, 128-byte swizzle (layout type 2), descriptor version 1 (Blackwell)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_enc, uint32_t sbo_enc) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)lbo_enc << 16) | ((uint64_t)sbo_enc << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+// instruction descriptor for kind::f16: fp16 A/B, fp32 D
+__device__ __forceinline__ uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// byte offset of 16-byte chunk `c` of row `r` inside a swizzled [rows][128 B] tile (tile base 1024-aligned)
+__device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * MLP_ROW_BYTES + ((c ^ (r & 7)) << 4)); }
+
+// global [rows_valid, width] fp16 row-major  ->  swizzled tile; rows >= rows_valid are zero-filled
+__device__ __forceinline__ void load_tile(uint8_t* tile, const __half* __restrict__ g, int width, int rows_valid) {
+  const int cpr = width >> 3;  // 16-byte chunks per row
+  const int total = MLP_TILE * cpr;
+  const uint4* src = reinterpret_cast<const uint4*>(g);
+  for (int q = threadIdx.x; q < total; q += blockDim.x) {
+    const int r = q / cpr, c = q - r * cpr;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r < rows_valid) v = __ldg(src + q);
+    *reinterpret_cast<uint4*>(tile + swz(r, c)) = v;
+  }
+}
+// swizzled tile -> global [rows_valid, width] fp16 row-major (coalesced 16-byte chunks)
+__device__ __forceinline__ void store_tile(const uint8_t* tile, __half* __restrict__ g, int width, int rows_valid) {
+  const int cpr = width >> 3;
+  const int total = rows_valid * cpr;
+  uint4* dst = reinterpret_cast<uint4*>(g);
+  for (int q = threadIdx.x; q < total; q += blockDim.x) {
+    const int r = q / cpr, c = q - r * cpr;
+    dst[q] = *reinterpret_cast<const uint4*>(tile + swz(r, c));
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+
+}  // namespace

@@ -53,6 +53,7 @@ class DNGPradianceField(torch.nn.Module):
         self.use_time_embedding, self.use_time_attenuation = use_time_embedding, use_time_attenuation
         self.time_inject_before_sigma, self.use_div_offsets = time_inject_before_sigma, use_div_offsets
         self.MOVING_STEP, self.loose_move = moving_step, False
+        self._default_density = density_activation is None
         self.density_activation = density_activation or (lambda x: trunc_exp(x - 1))
         freq = {"otype": "Frequency", "n_frequencies": 4}
         self.xyz_wrap = tcnn.NetworkWithInputEncoding(4, 6 if use_div_offsets else 3, freq, _mlp_cfg(3), seed + 1)
@@ -78,6 +79,35 @@ class DNGPradianceField(torch.nn.Module):
         if use_weight_predict:
             self.mlp_weight_prediction = tcnn.NetworkWithInputEncoding(4, 1, freq, _mlp_cfg(1), seed + 6)
 
+    # ---- fused no-grad path (cednerf_field_fwd): sampler pre-pass, occupancy updates, eval rendering ------------
+    def fused_supported(self) -> bool:
+        return (self.use_viewdirs and self.geo_feat_dim == 15 and not self.loose_move and self._default_density
+                and self.hash_encoder.n_levels <= 16 and self.aabb.is_cuda)
+
+    def _field_desc(self):
+        key = (self.aabb.data_ptr(), self.aabb._version, self.MOVING_STEP)
+        if getattr(self, "_fdesc_key", None) != key:
+            from ._lib import FieldDesc
+
+            d = FieldDesc()
+            for i, v in enumerate(self.aabb.tolist()):
+                d.aabb[i] = v
+            d.moving_step = float(self.MOVING_STEP)
+            d.use_div_offsets = int(self.use_div_offsets)
+            d.time_mode = 0 if not self.use_time_embedding else (2 if self.use_time_attenuation else 1)
+            d.time_before_sigma = int(self.time_inject_before_sigma)
+            d.f1, d.f2, d.f3 = self.xyz_wrap.network.desc, self.mlp_base.desc, self.mlp_head.desc
+            d.levels = self.hash_encoder.levels
+            self._fdesc, self._fdesc_key = d, key
+        return self._fdesc
+
+    @torch.no_grad()
+    def fused_query(self, n, packed=None, points=None, timestamps=None, t_stride=1, sigma_only=True):
+        """-> (sigma [n], rgb [n,3] | None) in one kernel; see ops.field_fwd."""
+        images = (self.xyz_wrap.network.weight_image(), self.mlp_base.weight_image(), self.mlp_head.weight_image())
+        return ops.field_fwd(self._field_desc(), images, self.hash_encoder.table_f16(), n, sigma_only, packed, points,
+                             timestamps, t_stride)
+
     def query_move(self, x, t):
         off = self.xyz_wrap(torch.cat([x, t], -1)).float()
         move = off[:, :3] * self.MOVING_STEP
@@ -86,6 +116,13 @@ class DNGPradianceField(torch.nn.Module):
         return x + move, move
 
     def query_density(self, x, t, return_feat: bool = False, return_interal: bool = False):
+        if (not torch.is_grad_enabled()) and not return_feat and not return_interal and x.shape[0] > 0 \
+                and self.fused_supported():
+            xs = x.reshape(-1, 3)
+            ts = t.reshape(-1)
+            sigma, _ = self.fused_query(xs.shape[0], points=(xs, None), timestamps=ts,
+                                        t_stride=1 if ts.numel() == xs.shape[0] else 0)
+            return {"density": sigma[:, None]}
         if (not self.loose_move) and x.shape[0] > 0:
             x_move, move = self.query_move(x.view(-1, 3), t.view(-1, 1))
         else:

@@ -12,7 +12,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import GridLevels, MlpDesc, call, ptr, stream
+from ._lib import FieldDesc, GridLevels, MlpDesc, call, ptr, stream
 
 F32, F16, I64, I32, U8 = torch.float32, torch.float16, torch.int64, torch.int32, torch.uint8
 
@@ -467,3 +467,30 @@ def time_embed(t: torch.Tensor, move_norm: Optional[torch.Tensor] = None) -> tor
     out = torch.empty(tt.numel(), 9, device=tt.device)
     call("cednerf_time_embed", ptr(tt), ptr(mv), tt.numel(), ptr(out), stream())
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# fused field query (inference: density pre-pass of the sampler, occupancy updates, eval rendering)
+# ------------------------------------------------------------------------------------------------
+def field_fwd(desc: FieldDesc, images, table_f16, n: int, sigma_only: bool, packed=None, points=None,
+              timestamps=None, t_stride: int = 1):
+    """packed = (ray_indices, t_starts, t_ends, rays_o, rays_d) or points = (x, dirs-or-None).
+    -> (sigma [n], rgb [n,3] or None)."""
+    _lib.check_device()
+    dev = table_f16.device
+    sigma = torch.empty(n, device=dev)
+    rgb = None if sigma_only else torch.empty(n, 3, device=dev)
+    ts = _f32c(timestamps).view(-1)
+    if packed is not None:
+        ridx, t0, t1, o, d = packed
+        args = (ptr(ridx.detach().to(I64).contiguous()), ptr(_f32c(t0)), ptr(_f32c(t1)), ptr(_f32c(o)), ptr(_f32c(d)),
+                None, None)
+        keep = args  # the temporaries must outlive the launch (stream-ordered, same stream: safe to drop after)
+    else:
+        x, dirs = points
+        xs = _f32c(x)
+        ds = None if dirs is None else _f32c(dirs)
+        args = (None, None, None, None, None, ptr(xs), ptr(ds))
+    call("cednerf_field_fwd", *args, ptr(ts), int(t_stride), n, ptr(images[0]), ptr(images[1]), ptr(images[2]),
+         ptr(table_f16), ctypes.byref(desc), ptr(sigma), ptr(rgb), stream())
+    return sigma, rgb

@@ -32,11 +32,26 @@ def _field_fns(field, rays, timestamps):
         t = timestamps[ridx] if field.training else timestamps.expand_as(x[:, :1])
         return x, t, d
 
+    def fused(t0, t1, ridx, sigma_only):
+        """One launch from packed samples: positions, encodings and networks never leave the SM."""
+        per_ray = field.training and timestamps.numel() == rays.origins.shape[0]
+        return field.fused_query(t0.numel(), packed=(ridx, t0, t1, rays.origins, rays.viewdirs), timestamps=timestamps,
+                                 t_stride=1 if per_ray else 0, sigma_only=sigma_only)
+
+    def can_fuse(t0):
+        ok = (not torch.is_grad_enabled()) and t0.numel() > 0 and getattr(field, "fused_supported", lambda: False)()
+        return ok and (timestamps.numel() == 1 or (field.training and timestamps.numel() == rays.origins.shape[0]))
+
     def sigma_fn(t0, t1, ridx):
+        if can_fuse(t0):
+            return fused(t0, t1, ridx, True)[0]
         x, t, _ = positions_of(t0, t1, ridx)
         return field.query_density(x, t)["density"].squeeze(-1)
 
     def rgb_sigma_fn(t0, t1, ridx):
+        if can_fuse(t0) and not field.training:
+            sigma, rgb = fused(t0, t1, ridx, False)
+            return rgb, {"density": sigma[:, None]}
         x, t, d = positions_of(t0, t1, ridx)
         return field(x, t, d)
 

@@ -127,6 +127,25 @@ int cednerf_mlp_bwd(const void* x_f16, const void* hidden_f16, const void* d_out
                     const CednerfMlpDesc* desc, int64_t n, void* d_x /*nullable*/, int dx_is_f32,
                     float* d_params /*nullable, accumulated into*/, void* stream);
 
+/* ---- fused field query (K2 + K3 in one kernel) -------------------------------------------------------- */
+typedef struct CednerfFieldDesc {
+  float aabb[6];
+  float moving_step;
+  int use_div_offsets;   /* deformation net emits 6 values: move = o[:3]*MS + tanh(o[3:])*MS (model.py:358-363) */
+  int time_mode;         /* 0 none, 1 SinusoidalEncoder, 2 SinusoidalEncoderWithExp */
+  int time_before_sigma; /* 1: density input = [hash | time9]; 0: colour input = [sh4 | feat15 | time9] */
+  CednerfMlpDesc f1, f2, f3; /* deformation (xyz_wrap), density (mlp_base), colour (mlp_head) */
+  CednerfGridLevels levels;
+} CednerfFieldDesc;
+/* DNGPradianceField.query_density / .forward without autograd (cednerf/model.py:367-488) fused with the position
+ * closure of cednerf/utils.py:74-104.  Samples: packed ray samples (ray_indices, t_starts, t_ends, rays_o, rays_d;
+ * timestamps indexed by ray) or explicit points (x, dirs; timestamps indexed by point); t_stride 0 = one timestamp
+ * for all.  rgb == NULL: density only. */
+int cednerf_field_fwd(const int64_t* ray_indices, const float* t_starts, const float* t_ends, const float* rays_o,
+                      const float* rays_d, const float* x, const float* dirs, const float* timestamps, int t_stride,
+                      int64_t n, const void* image_deform, const void* image_density, const void* image_colour,
+                      const void* table_f16, const CednerfFieldDesc* desc, float* sigma, float* rgb, void* stream);
+
 /* ---- K4: compositing ------------------------------------------------------------------------------- */
 /* offsets[r] = first sample of ray r (ray_indices sorted); offsets[n_rays] = n_samples */
 int cednerf_ray_offsets(const int64_t* ray_indices, int64_t n_samples, int64_t n_rays, int64_t* offsets, void* stream);

@@ -37,7 +37,9 @@ def test_ctypes_signatures_match_header():
             continue
         sig = ""
         for a in [x.strip() for x in args.split(",")]:
-            if "CednerfGridLevels" in a:
+            if "CednerfFieldDesc" in a:
+                sig += "F"
+            elif "CednerfGridLevels" in a:
                 sig += "G"
             elif "CednerfMlpDesc" in a:
                 sig += "M"
@@ -59,6 +61,7 @@ def test_descriptor_structs_match_header_layout():
 
     assert ctypes.sizeof(_lib.GridLevels) == 4 + 5 * 4 * 32
     assert ctypes.sizeof(_lib.MlpDesc) == 4 + 4 * 4 * 5 + 4
+    assert ctypes.sizeof(_lib.FieldDesc) == 6 * 4 + 4 + 3 * 4 + 3 * ctypes.sizeof(_lib.MlpDesc) + ctypes.sizeof(_lib.GridLevels)
 
 
 def test_level_geometry_matches_oracle_and_survey():
