@@ -47,21 +47,22 @@ struct FieldFwdArgs {
   CednerfFieldDesc d;
 };
 
-// layers of one network on the tile in abuf[cur]; the last layer's accumulator is left in TMEM columns [0, N_last)
-__device__ __forceinline__ void run_chain(const CednerfMlpDesc& d, const uint8_t* wimg, uint8_t* abuf0, uint8_t* abuf1,
-                                          int& cur, uint32_t tmem_base, uint32_t tmem_warp, uint64_t* bar,
-                                          uint32_t& phase, int tid) {
+__device__ __forceinline__ void group_sync(int group) { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); }
+
+// Layers of one network on the 128-row tile in `abuf` (one warp-group of 4 warps = one tile).  Hidden activations are
+// written back IN PLACE: the MMA that read the tile has completed (commit -> mbarrier) before any row is overwritten.
+// The last layer's accumulator is left in TMEM columns [0, N_last) of this group's TMEM slice.
+__device__ __forceinline__ void run_chain(const CednerfMlpDesc& d, const uint8_t* wimg, uint8_t* abuf, uint32_t tmem_grp,
+                                          uint32_t tmem_warp, uint64_t* bar, uint32_t& phase, int gtid, int group) {
   const int L = d.n_layers;
   for (int l = 0; l < L; ++l) {
     const int K = d.dim_in[l], N = d.dim_out[l];
-    uint8_t* a_cur = cur ? abuf1 : abuf0;
-    uint8_t* a_nxt = cur ? abuf0 : abuf1;
-    if (tid == 0) {
+    if (gtid == 0) {
       tc_fence_after();
-      const uint64_t ad = make_desc(smem_u32(a_cur), 1, 64);
+      const uint64_t ad = make_desc(smem_u32(abuf), 1, 64);
       const uint64_t bd = make_desc(smem_u32(wimg + d.image_off[l]), 1, 64);
       const uint32_t id = make_idesc(128, N, 0, 0);
-      for (int k = 0; k < K / 16; ++k) umma(tmem_base, ad + 2 * k, bd + 2 * k, id, k > 0);
+      for (int k = 0; k < K / 16; ++k) umma(tmem_grp, ad + 2 * k, bd + 2 * k, id, k > 0);
       umma_commit(bar);
     }
     mbar_wait(bar, phase);
@@ -77,13 +78,12 @@ __device__ __forceinline__ void run_chain(const CednerfMlpDesc& d, const uint8_t
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           p[j] = pack_h2(fmaxf(__uint_as_float(r[2 * j]), 0.f), fmaxf(__uint_as_float(r[2 * j + 1]), 0.f));
-        *reinterpret_cast<uint4*>(a_nxt + swz(tid, 2 * cb)) = make_uint4(p[0], p[1], p[2], p[3]);
-        *reinterpret_cast<uint4*>(a_nxt + swz(tid, 2 * cb + 1)) = make_uint4(p[4], p[5], p[6], p[7]);
+        *reinterpret_cast<uint4*>(abuf + swz(gtid, 2 * cb)) = make_uint4(p[0], p[1], p[2], p[3]);
+        *reinterpret_cast<uint4*>(abuf + swz(gtid, 2 * cb + 1)) = make_uint4(p[4], p[5], p[6], p[7]);
       }
       fence_proxy_async();
       tc_fence_before();
-      __syncthreads();
-      cur ^= 1;
+      group_sync(group);
     }
   }
 }
@@ -118,50 +118,52 @@ template <int LG>
 __device__ __forceinline__ void hash_levels(const float* xn, const __half* __restrict__ table, const CednerfGridLevels& lv,
                                             int l0, uint32_t* feat) {
   const __half2* t2 = reinterpret_cast<const __half2*>(table);
-  Cell c[LG];
+  float frac[LG][3];
   __half2 v[LG][8];
 #pragma unroll
-  for (int a = 0; a < LG; ++a) {
+  for (int a = 0; a < LG; ++a) {  // issue all 8*LG gathers first ...
     const int l = l0 + a;
-    c[a] = locate(xn, lv.scale[l]);
-    const uint32_t res = lv.res[l], size = lv.size[l], off = lv.offset[l];
-    const bool hashed = lv.hashed[l] != 0;
+    const Cell c = locate(xn, lv.scale[l]);
+    frac[a][0] = c.f[0], frac[a][1] = c.f[1], frac[a][2] = c.f[2];
+    uint32_t idx[8];
+    cell_indices(c.g, lv.res[l], lv.size[l], lv.offset[l], lv.hashed[l] != 0, idx);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const uint32_t idx =
-          off + corner_index(c[a].g[0] + (k & 1), c[a].g[1] + ((k >> 1) & 1), c[a].g[2] + ((k >> 2) & 1), res, size, hashed);
-      v[a][k] = __ldg(t2 + idx);
-    }
+    for (int k = 0; k < 8; ++k) v[a][k] = __ldg(t2 + idx[k]);
   }
 #pragma unroll
-  for (int a = 0; a < LG; ++a) {
+  for (int a = 0; a < LG; ++a) {  // ... then the weights (recomputed from 3 fractions) and the blend
+    float w[8];
+    cell_weights(frac[a], w);
     float a0 = 0.f, a1 = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float w = corner_weight(c[a], k);
       const float2 f = __half22float2(v[a][k]);
-      a0 = __fadd_rn(a0, __fmul_rn(w, f.x));
-      a1 = __fadd_rn(a1, __fmul_rn(w, f.y));
+      a0 = __fadd_rn(a0, __fmul_rn(w[k], f.x));
+      a1 = __fadd_rn(a1, __fmul_rn(w[k], f.y));
     }
     feat[l0 + a] = pack_h2(a0, a1);
   }
 }
 
-__global__ void __launch_bounds__(MLP_TILE) field_fwd_kernel(FieldFwdArgs a) {
+#define FIELD_MAX_GROUPS 4
+
+__global__ void __launch_bounds__(384, 2) field_fwd_kernel(FieldFwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const CednerfFieldDesc& d = a.d;
   const bool want_rgb = a.rgb != nullptr;
+  const int n_groups = blockDim.x / MLP_TILE;           // one warp-group (128 threads) per 128-sample tile
+  const int tid = threadIdx.x, warp = tid >> 5, group = tid / MLP_TILE, gtid = tid % MLP_TILE;
   uint8_t* w1 = smem;
   uint8_t* w2 = w1 + d.f1.image_bytes;
   uint8_t* w3 = w2 + d.f2.image_bytes;
   uint8_t* abuf0 = reinterpret_cast<uint8_t*>(
-      (reinterpret_cast<uintptr_t>(w3 + (want_rgb ? d.f3.image_bytes : 0)) + 1023) & ~(uintptr_t)1023);
-  uint8_t* abuf1 = abuf0 + MLP_TILE_BYTES;
-  __shared__ uint64_t bar;
+                       (reinterpret_cast<uintptr_t>(w3 + (want_rgb ? d.f3.image_bytes : 0)) + 1023) & ~(uintptr_t)1023) +
+                   (size_t)group * MLP_TILE_BYTES;
+  __shared__ uint64_t bars[FIELD_MAX_GROUPS];
   __shared__ uint32_t tmem_base_s;
+  uint64_t* bar = &bars[group];
 
-  const int tid = threadIdx.x, warp = tid >> 5;
   for (int q = tid; q < d.f1.image_bytes / 16; q += blockDim.x)
     reinterpret_cast<uint4*>(w1)[q] = __ldg(reinterpret_cast<const uint4*>(a.img1) + q);
   for (int q = tid; q < d.f2.image_bytes / 16; q += blockDim.x)
@@ -169,44 +171,39 @@ __global__ void __launch_bounds__(MLP_TILE) field_fwd_kernel(FieldFwdArgs a) {
   if (want_rgb)
     for (int q = tid; q < d.f3.image_bytes / 16; q += blockDim.x)
       reinterpret_cast<uint4*>(w3)[q] = __ldg(reinterpret_cast<const uint4*>(a.img3) + q);
-  if (warp == 0) tmem_alloc(&tmem_base_s, 64);
-  if (tid == 0) {
-    mbar_init(&bar, 1);
-    fence_barrier_init();
-  }
+  const uint32_t tmem_cols = n_groups <= 1 ? 64 : (n_groups == 2 ? 128 : 256);
+  if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
+  if (gtid == 0) mbar_init(bar, 1);
+  if (tid == 0) fence_barrier_init();
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
+  if (gtid == 0) fence_barrier_init();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_base_s;
-  const uint32_t tmem_warp = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const uint32_t tmem_base = tmem_base_s + 64u * (uint32_t)group;
+  const uint32_t tmem_warp = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   uint32_t phase = 0;
   const int64_t n_tiles = (a.n + MLP_TILE - 1) / MLP_TILE;
   const float ms = d.moving_step;
   const int L = d.levels.n_levels;
   const uint32_t one2 = 0x3C003C00u;  // half2(1, 1): tcnn's input padding value
 
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t s = tile * MLP_TILE + tid;
+  for (int64_t tile = (int64_t)blockIdx.x * n_groups + group; tile < n_tiles; tile += (int64_t)gridDim.x * n_groups) {
+    const int64_t s = tile * MLP_TILE + gtid;
     const bool ok = s < a.n;
     // ---- the sample: position, time, direction (cednerf/utils.py:74-104) -------------------------------------
-    float x[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 1.f}, tv = 0.f;
+    float x[3] = {0.f, 0.f, 0.f}, tv = 0.f;
     if (ok) {
       if (a.ridx) {
         const int64_t r = a.ridx[s];
         const float tm = __fadd_rn(a.t0[s], a.t1[s]);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          dir[k] = a.rays_d[3 * r + k];
-          x[k] = __fadd_rn(a.rays_o[3 * r + k], __fmul_rn(__fmul_rn(dir[k], tm), 0.5f));
-        }
+        for (int k = 0; k < 3; ++k)
+          x[k] = __fadd_rn(a.rays_o[3 * r + k], __fmul_rn(__fmul_rn(a.rays_d[3 * r + k], tm), 0.5f));
         tv = a.t[r * a.t_stride];
       } else {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          x[k] = a.x[3 * s + k];
-          if (a.dirs) dir[k] = a.dirs[3 * s + k];
-        }
+        for (int k = 0; k < 3; ++k) x[k] = a.x[3 * s + k];
         tv = a.t[s * a.t_stride];
       }
     }
@@ -221,14 +218,13 @@ __global__ void __launch_bounds__(MLP_TILE) field_fwd_kernel(FieldFwdArgs a) {
           const float ph = in4[dim] * (float)(1 << k);
           p[k] = pack_h2(sinpif(ph), sinpif(ph + 0.5f));
         }
-        *reinterpret_cast<uint4*>(abuf0 + swz(tid, dim)) = make_uint4(p[0], p[1], p[2], p[3]);
+        *reinterpret_cast<uint4*>(abuf0 + swz(gtid, dim)) = make_uint4(p[0], p[1], p[2], p[3]);
       }
     }
     fence_proxy_async();
     tc_fence_before();
-    __syncthreads();
-    int cur = 0;
-    run_chain(d.f1, w1, abuf0, abuf1, cur, tmem_base, tmem_warp, &bar, phase, tid);
+    group_sync(group);
+    run_chain(d.f1, w1, abuf0, tmem_base, tmem_warp, bar, phase, gtid, group);
     float xn[3], mvnorm;
     bool selector = true;
     {
@@ -248,20 +244,20 @@ __global__ void __launch_bounds__(MLP_TILE) field_fwd_kernel(FieldFwdArgs a) {
     }
     // ---- density net input: [hash 2L | time 9 | 1.0 padding] (model.py:384-403) -------------------------------
     float temb[9];
-    if (d.time_mode) time_embedding(tv, mvnorm, d.time_mode, temb);
     {
       uint32_t feat[16];
 #pragma unroll
       for (int l = 0; l < 16; ++l) feat[l] = one2;
-      if ((L & 3) == 0) {
+      if ((L & 1) == 0) {
 #pragma unroll
-        for (int l0 = 0; l0 < 16; l0 += 4)
-          if (l0 < L) hash_levels<4>(xn, a.table, d.levels, l0, feat);
+        for (int l0 = 0; l0 < 16; l0 += 2)
+          if (l0 < L) hash_levels<2>(xn, a.table, d.levels, l0, feat);
       } else {
 #pragma unroll
         for (int l0 = 0; l0 < 16; ++l0)
           if (l0 < L) hash_levels<1>(xn, a.table, d.levels, l0, feat);
       }
+      if (d.time_mode) time_embedding(tv, mvnorm, d.time_mode, temb);  // after the gathers: keeps registers free
       const int k2 = d.f2.dim_in[0];
       uint32_t row[32];
 #pragma unroll
@@ -278,24 +274,28 @@ __global__ void __launch_bounds__(MLP_TILE) field_fwd_kernel(FieldFwdArgs a) {
 #pragma unroll
       for (int c = 0; c < 8; ++c)
         if (c * 8 < k2)
-          *reinterpret_cast<uint4*>(abuf0 + swz(tid, c)) = make_uint4(row[4 * c], row[4 * c + 1], row[4 * c + 2], row[4 * c + 3]);
+          *reinterpret_cast<uint4*>(abuf0 + swz(gtid, c)) = make_uint4(row[4 * c], row[4 * c + 1], row[4 * c + 2], row[4 * c + 3]);
     }
     fence_proxy_async();
     tc_fence_before();
-    __syncthreads();
-    cur = 0;
-    run_chain(d.f2, w2, abuf0, abuf1, cur, tmem_base, tmem_warp, &bar, phase, tid);
+    group_sync(group);
+    run_chain(d.f2, w2, abuf0, tmem_base, tmem_warp, bar, phase, gtid, group);
     uint32_t o2[16];
     tmem_ld16(tmem_warp, o2);
     tmem_ld_wait();
     if (ok) a.sigma[s] = selector ? expf(rnd16(o2[0]) - 1.f) : 0.f;  // trunc_exp(raw - 1) * selector (model.py:414-417)
     if (!want_rgb) {
       tc_fence_before();
-      __syncthreads();
+      group_sync(group);
       continue;
     }
     // ---- colour net input: [SH4(dir) | 15 geometry features (| time 9) | 1.0 padding] (model.py:447-466) --------
     {
+      float dir[3] = {0.f, 0.f, 1.f};
+      if (ok) {
+        const float* dp = a.ridx ? a.rays_d + 3 * a.ridx[s] : a.dirs + 3 * s;
+        dir[0] = dp[0], dir[1] = dp[1], dir[2] = dp[2];
+      }
       const float nrm = sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
       float v[3];
 #pragma unroll
@@ -315,15 +315,14 @@ __global__ void __launch_bounds__(MLP_TILE) field_fwd_kernel(FieldFwdArgs a) {
       }
 #pragma unroll
       for (int c = 0; c < 4; ++c)
-        *reinterpret_cast<uint4*>(abuf0 + swz(tid, c)) =
+        *reinterpret_cast<uint4*>(abuf0 + swz(gtid, c)) =
             make_uint4(pack_h2(in[8 * c], in[8 * c + 1]), pack_h2(in[8 * c + 2], in[8 * c + 3]),
                        pack_h2(in[8 * c + 4], in[8 * c + 5]), pack_h2(in[8 * c + 6], in[8 * c + 7]));
     }
     fence_proxy_async();
     tc_fence_before();
-    __syncthreads();
-    cur = 0;
-    run_chain(d.f3, w3, abuf0, abuf1, cur, tmem_base, tmem_warp, &bar, phase, tid);
+    group_sync(group);
+    run_chain(d.f3, w3, abuf0, tmem_base, tmem_warp, bar, phase, gtid, group);
     {
       uint32_t r[16];
       tmem_ld16(tmem_warp, r);
@@ -334,10 +333,11 @@ __global__ void __launch_bounds__(MLP_TILE) field_fwd_kernel(FieldFwdArgs a) {
       }
     }
     tc_fence_before();
-    __syncthreads();
+    group_sync(group);
   }
+  tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 64);
+  if (warp == 0) tmem_dealloc(tmem_base_s, tmem_cols);
 }
 
 int check_field(const CednerfFieldDesc* d, bool want_rgb) {
@@ -374,22 +374,25 @@ CEDNERF_EXPORT int cednerf_field_fwd(const int64_t* ray_indices, const float* t_
   CEDNERF_REQUIRE((ray_indices && t_starts && t_ends && rays_o && rays_d) || (!ray_indices && x), "need packed samples or points");
   CEDNERF_REQUIRE(!rgb || ray_indices || dirs, "colour needs directions");
   if (n == 0) return 0;
-  const int smem = desc->f1.image_bytes + desc->f2.image_bytes + (rgb ? desc->f3.image_bytes : 0) + 2 * MLP_TILE_BYTES + 2048;
-  static int configured = 0;
-  if (configured < smem) {
-    cudaError_t e = cudaFuncSetAttribute(field_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  const int n_groups = 3;  // 3 tiles (12 warps) per CTA, 2 CTAs per SM: 24 warps/SM at <= 85 registers/thread
+  const int smem = desc->f1.image_bytes + desc->f2.image_bytes + (rgb ? desc->f3.image_bytes : 0) +
+                   n_groups * MLP_TILE_BYTES + 2048;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(field_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
     if (e != cudaSuccess) {
       cednerf_set_error("cednerf_field_fwd: %s", cudaGetErrorString(e));
       return (int)e;
     }
-    configured = 160 * 1024;
+    configured = true;
   }
+  CEDNERF_REQUIRE(smem <= 112 * 1024, "networks too large for the fused kernel");
   FieldFwdArgs a{ray_indices, t_starts, t_ends, rays_o, rays_d, x, dirs, timestamps, t_stride, n,
                  (const uint8_t*)image_deform, (const uint8_t*)image_density, (const uint8_t*)image_colour,
                  (const __half*)table_f16, sigma, rgb, *desc};
   const int64_t tiles = (n + MLP_TILE - 1) / MLP_TILE;
-  const int per_sm = smem <= 72 * 1024 ? 3 : (smem <= 110 * 1024 ? 2 : 1);
-  const int64_t max_ctas = (int64_t)cednerf_num_sms() * per_sm;
-  field_fwd_kernel<<<(unsigned)(tiles < max_ctas ? tiles : max_ctas), MLP_TILE, smem, (cudaStream_t)stream>>>(a);
+  const int64_t ctas = (tiles + n_groups - 1) / n_groups;
+  const int64_t max_ctas = (int64_t)cednerf_num_sms() * 2;
+  field_fwd_kernel<<<(unsigned)(ctas < max_ctas ? ctas : max_ctas), n_groups * MLP_TILE, smem, (cudaStream_t)stream>>>(a);
   return cednerf_check_launch("cednerf_field_fwd");
 }

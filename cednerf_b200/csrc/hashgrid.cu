@@ -26,9 +26,8 @@ hashgrid_fwd_kernel(const float* __restrict__ x, int x_stride, int64_t n, const 
   const uint32_t res = lv.res[l], size = lv.size[l], off = lv.offset[l];
   const bool hashed = lv.hashed[l] != 0;
   uint32_t idx[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k)
-    idx[k] = off + corner_index(c.g[0] + (k & 1), c.g[1] + ((k >> 1) & 1), c.g[2] + ((k >> 2) & 1), res, size, hashed);
+  float wgt[8];
+  cell_corners(c, res, size, off, hashed, idx, wgt);
   float a0 = 0.f, a1 = 0.f;
   if (!FOUR_D) {
     __half2 v[8];
@@ -37,10 +36,9 @@ hashgrid_fwd_kernel(const float* __restrict__ x, int x_stride, int64_t n, const 
     for (int k = 0; k < 8; ++k) v[k] = __ldg(t2 + idx[k]);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float w = corner_weight(c, k);
       const float2 f = __half22float2(v[k]);
-      a0 = __fadd_rn(a0, __fmul_rn(w, f.x));
-      a1 = __fadd_rn(a1, __fmul_rn(w, f.y));
+      a0 = __fadd_rn(a0, __fmul_rn(wgt[k], f.x));
+      a1 = __fadd_rn(a1, __fmul_rn(wgt[k], f.y));
     }
   } else {
     int kf;
@@ -57,7 +55,7 @@ hashgrid_fwd_kernel(const float* __restrict__ x, int x_stride, int64_t n, const 
       const uint32_t lo_w = words[kf], hi_w = words[kf + 1];
       const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&lo_w));
       const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&hi_w));
-      const float w = corner_weight(c, k);
+      const float w = wgt[k];
       a0 = __fadd_rn(a0, __fmul_rn(w, __fadd_rn(__fmul_rn(lo.x, om), __fmul_rn(hi.x, tau))));
       a1 = __fadd_rn(a1, __fmul_rn(w, __fadd_rn(__fmul_rn(lo.y, om), __fmul_rn(hi.y, tau))));
     }
@@ -164,6 +162,57 @@ hashgrid_bwd_kernel(const float* __restrict__ x, int x_stride, int64_t n, const 
   }
 }
 
+// Table gradient, level-major: blockIdx.y = level, lanes = 32 CONSECUTIVE samples.  Samples are packed along rays, so
+// at coarse and middle levels neighbouring lanes sit in the same cell and would hammer the same 8 addresses (on the
+// DyNeRF scene the content occupies [-1,1]^3 of a [-8,8]^3 grid: the 16^3 level sees ~64 distinct entries in total).
+// Lanes are grouped into runs of equal cell; each run is summed with a segmented shuffle scan and only its last lane
+// issues the vector reduction.  Fine levels degenerate to runs of one lane (one reduction per corner, as before).
+template <typename GradT>
+__global__ void __launch_bounds__(256)
+hashgrid_bwd_table_kernel(const float* __restrict__ x, int x_stride, int64_t n, CednerfGridLevels lv,
+                          const GradT* __restrict__ dy, int dy_stride, float* __restrict__ g_table) {
+  const int l = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = s < n;
+  if (!active) s = n - 1;
+  const Cell c = locate(x + s * x_stride, lv.scale[l]);
+  const uint32_t res = lv.res[l], size = lv.size[l], off = lv.offset[l];
+  const bool hashed = lv.hashed[l] != 0;
+  float d0 = 0.f, d1 = 0.f;
+  if (active) {
+    d0 = (float)dy[s * dy_stride + 2 * l];
+    d1 = (float)dy[s * dy_stride + 2 * l + 1];
+  }
+  // run structure: a lane starts a run when its cell differs from the previous lane's
+  const uint32_t px = __shfl_up_sync(0xffffffffu, c.g[0], 1), py = __shfl_up_sync(0xffffffffu, c.g[1], 1),
+                 pz = __shfl_up_sync(0xffffffffu, c.g[2], 1);
+  const bool head = lane == 0 || px != c.g[0] || py != c.g[1] || pz != c.g[2];
+  int run_start = head ? lane : 0;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) run_start = max(run_start, __shfl_up_sync(0xffffffffu, run_start, o));
+  const unsigned heads = __ballot_sync(0xffffffffu, head);
+  const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float w = corner_weight(c, k);
+    float v0 = w * d0, v1 = w * d1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float u0 = __shfl_up_sync(0xffffffffu, v0, o), u1 = __shfl_up_sync(0xffffffffu, v1, o);
+      if (lane - o >= run_start) {
+        v0 += u0;
+        v1 += u1;
+      }
+    }
+    if (tail && (v0 != 0.f || v1 != 0.f)) {
+      const uint32_t idx =
+          off + corner_index(c.g[0] + (k & 1), c.g[1] + ((k >> 1) & 1), c.g[2] + ((k >> 2) & 1), res, size, hashed);
+      atomicAdd(reinterpret_cast<float2*>(g_table) + idx, make_float2(v0, v1));
+    }
+  }
+}
+
 __global__ void cast_f32_to_f16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, int64_t n4,
                                        const float* __restrict__ src_tail, __half* __restrict__ dst_tail, int tail) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -205,14 +254,27 @@ CEDNERF_EXPORT int cednerf_hashgrid_bwd(const float* x, int x_stride, int64_t n,
   CEDNERF_REQUIRE(n >= 0 && x_stride >= 3 && dy_stride >= 2 * levels->n_levels, "bad sizes");
   CEDNERF_REQUIRE(g_table || g_x, "nothing to compute");
   if (n == 0) return 0;
-  dim3 grid(cednerf_blocks(n * levels->n_levels, 256));
-  if (dy_is_f16)
-    hashgrid_bwd_kernel<false, __half><<<grid, 256, 0, (cudaStream_t)stream>>>(
-        x, x_stride, n, (const __half*)table_f16, *levels, (const __half*)dy, dy_stride, g_table, g_x, 0);
-  else
-    hashgrid_bwd_kernel<false, float><<<grid, 256, 0, (cudaStream_t)stream>>>(
-        x, x_stride, n, (const __half*)table_f16, *levels, (const float*)dy, dy_stride, g_table, g_x, 0);
-  return cednerf_check_launch("cednerf_hashgrid_bwd");
+  cudaStream_t st = (cudaStream_t)stream;
+  int launches = 0;
+  if (g_table) {
+    dim3 grid(cednerf_blocks(n, 256), levels->n_levels);
+    if (dy_is_f16)
+      hashgrid_bwd_table_kernel<__half><<<grid, 256, 0, st>>>(x, x_stride, n, *levels, (const __half*)dy, dy_stride, g_table);
+    else
+      hashgrid_bwd_table_kernel<float><<<grid, 256, 0, st>>>(x, x_stride, n, *levels, (const float*)dy, dy_stride, g_table);
+    ++launches;
+  }
+  if (g_x) {
+    dim3 grid(cednerf_blocks(n * levels->n_levels, 256));
+    if (dy_is_f16)
+      hashgrid_bwd_kernel<false, __half><<<grid, 256, 0, st>>>(x, x_stride, n, (const __half*)table_f16, *levels,
+                                                             (const __half*)dy, dy_stride, nullptr, g_x, 0);
+    else
+      hashgrid_bwd_kernel<false, float><<<grid, 256, 0, st>>>(x, x_stride, n, (const __half*)table_f16, *levels,
+                                                            (const float*)dy, dy_stride, nullptr, g_x, 0);
+    ++launches;
+  }
+  return cednerf_check_launch("cednerf_hashgrid_bwd", launches);
 }
 
 CEDNERF_EXPORT int cednerf_hashgrid4d_fwd(const float* xyzt, int x_stride, int64_t n, const void* table_f16,
