@@ -55,7 +55,7 @@ _SIGNATURES = {
     "cednerf_time_embed": "pplpp",
     "cednerf_mlp_pack_weights": "pMpp",
     "cednerf_mlp_fwd": "ppMlppp",
-    "cednerf_mlp_bwd": "ppppMlpipp",
+    "cednerf_mlp_bwd": "ppppMlpippp",
     "cednerf_field_fwd": "ppppppppilppppFppp",
     "cednerf_ray_offsets": "pllpp",
     "cednerf_composite_fwd": "pppppppillpppppppifp",

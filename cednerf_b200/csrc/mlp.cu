@@ -131,6 +131,7 @@ struct MlpBwdArgs {
   void* d_x;              // [n, dim_in[0]] fp32 or fp16, or null
   int dx_is_f32;
   float* d_params;        // flat fp32, same layout as params (atomically accumulated), or null
+  __half* d_hidden;       // [n_layers-1][n][64] gradients w.r.t. the hidden activations after the ReLU mask, or null
   int64_t n;
   uint32_t tmem_cols;
   CednerfMlpDesc d;
@@ -227,6 +228,11 @@ __global__ void __launch_bounds__(MLP_TILE) mlp_bwd_kernel(MlpBwdArgs a) {
           }
           *reinterpret_cast<uint4*>(nxt + swz(tid, 2 * cb)) = make_uint4(p[0], p[1], p[2], p[3]);
           *reinterpret_cast<uint4*>(nxt + swz(tid, 2 * cb + 1)) = make_uint4(p[4], p[5], p[6], p[7]);
+          if (a.d_hidden && tid < rows_valid) {
+            uint4* dst = reinterpret_cast<uint4*>(a.d_hidden + ((int64_t)(l - 1) * a.n + row0 + tid) * 64 + cb * 16);
+            dst[0] = make_uint4(p[0], p[1], p[2], p[3]);
+            dst[1] = make_uint4(p[4], p[5], p[6], p[7]);
+          }
         }
       } else if (a.d_x) {
         for (int cb = 0; cb < K_in / 16; ++cb) {
@@ -351,7 +357,7 @@ CEDNERF_EXPORT int cednerf_mlp_fwd(const void* x_f16, const void* weight_image, 
 
 CEDNERF_EXPORT int cednerf_mlp_bwd(const void* x_f16, const void* hidden_f16, const void* d_out_f16,
                                    const void* weight_image, const CednerfMlpDesc* desc, int64_t n, void* d_x,
-                                   int dx_is_f32, float* d_params, void* stream) {
+                                   int dx_is_f32, float* d_params, void* d_hidden_f16, void* stream) {
   CEDNERF_REQUIRE(check_desc(desc), "bad MLP descriptor");
   CEDNERF_REQUIRE(n >= 0 && (desc->n_layers == 1 || hidden_f16), "bad arguments");
   if (n == 0) return 0;
@@ -367,7 +373,7 @@ CEDNERF_EXPORT int cednerf_mlp_bwd(const void* x_f16, const void* hidden_f16, co
   uint32_t cols = 64u * (uint32_t)(desc->n_layers + 1), alloc = 64;
   while (alloc < cols) alloc <<= 1;
   MlpBwdArgs a{(const __half*)x_f16, (const __half*)hidden_f16, (const __half*)d_out_f16, (const uint8_t*)weight_image,
-               d_x, dx_is_f32, d_params, n, alloc, *desc};
+               d_x, dx_is_f32, d_params, (__half*)d_hidden_f16, n, alloc, *desc};
   const int64_t tiles = (n + MLP_TILE - 1) / MLP_TILE;
   const int64_t max_ctas = (int64_t)cednerf_num_sms() * (alloc <= 256 ? 2 : 1);
   mlp_bwd_kernel<<<(unsigned)(tiles < max_ctas ? tiles : max_ctas), MLP_TILE, BWD_SMEM, (cudaStream_t)stream>>>(a);

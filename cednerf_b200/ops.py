@@ -265,6 +265,16 @@ class MlpFunction(torch.autograd.Function):
     The operand handed to the kernel is fp16 [N, pad16(n_in)] with the padding columns set to 1.0 (tcnn's
     input padding); d_x is produced in the network precision (fp16), as tcnn's dL_dinput is."""
 
+    _debug = None  # tests / diagnostics: set to a dict to capture the masked hidden gradients of the next backward
+
+    @staticmethod
+    def debug_hidden_grads(n, desc, device):
+        if MlpFunction._debug is None or desc.n_layers < 2:
+            return None
+        t = torch.zeros(desc.n_layers - 1, n, 64, dtype=F16, device=device)
+        MlpFunction._debug.setdefault("d_hidden", []).append(t)
+        return t
+
     @staticmethod
     def forward(ctx, x, params, image, desc: MlpDesc, save: bool, n_out: int):
         _lib.check_device()
@@ -297,7 +307,7 @@ class MlpFunction(torch.autograd.Function):
         d_p = torch.zeros(ctx.n_params, dtype=F32, device=x16.device) if need_p else None
         if need_x or need_p:
             call("cednerf_mlp_bwd", ptr(x16), ptr(hidden), ptr(dy), ptr(image), ctypes.byref(desc), n, ptr(d_x), 0,
-                 ptr(d_p), stream())
+                 ptr(d_p), ptr(MlpFunction.debug_hidden_grads(n, desc, x16.device)), stream())
         return (None if d_x is None else d_x[:, : ctx.n_in]), d_p, None, None, None, None
 
 

@@ -125,7 +125,9 @@ int cednerf_mlp_fwd(const void* x_f16, const void* weight_image, const CednerfMl
                     void* hidden_f16 /*nullable: [n_layers-1][n][64]*/, void* stream);
 int cednerf_mlp_bwd(const void* x_f16, const void* hidden_f16, const void* d_out_f16, const void* weight_image,
                     const CednerfMlpDesc* desc, int64_t n, void* d_x /*nullable*/, int dx_is_f32,
-                    float* d_params /*nullable, accumulated into*/, void* stream);
+                    float* d_params /*nullable, accumulated into*/,
+                    void* d_hidden_f16 /*nullable: [n_layers-1][n][64] masked hidden gradients, for inspection*/,
+                    void* stream);
 
 /* ---- fused field query (K2 + K3 in one kernel) -------------------------------------------------------- */
 typedef struct CednerfFieldDesc {
