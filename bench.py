@@ -138,6 +138,9 @@ def algorithmic_bytes(name, args):
         if args[9]:
             b += n * (L * 8 * 4 + 12)                           # table re-read for dL/dx + dx write
         return b
+    if name == "cednerf_field_fwd":
+        n, L = args[9], args[14]._obj.levels.n_levels
+        return n * (L * 8 * 4 + 16 + 4 + (12 if args[16] else 0))  # 512 B table + packed sample 16 B + sigma (+ rgb)
     if name == "cednerf_mlp_fwd":
         d, n = args[2]._obj, args[3]
         hid = (d.n_layers - 1) * 128 if args[5] else 0
@@ -229,7 +232,8 @@ def run_ours(args):
         pass
     hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
     roof, breakdown = None, {}
-    if rank == 0 and args.profile_steps > 0:
+    if args.profile_steps > 0:
+        # every rank runs the instrumented steps (they contain the gradient all-reduce); rank 0 keeps the records
         rec = []
         real_call = _lib.call
 
@@ -242,7 +246,7 @@ def run_ours(args):
 
         for m in (_lib, cb.ops):
             m.call = recording_call
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         for i in range(args.profile_steps):
             step_resident(i)
@@ -250,6 +254,7 @@ def run_ours(args):
         prof_ms = (time.perf_counter() - t0) * 1e3 / args.profile_steps
         for m in (_lib, cb.ops):
             m.call = real_call
+    if rank == 0 and args.profile_steps > 0:
         agg = {}
         for name, a, s, e in rec:
             t = s.elapsed_time(e)
@@ -271,14 +276,15 @@ def run_ours(args):
         breakdown["_ours_total_ms"] = round(sum(v["ms"] for v in agg.values()) / args.profile_steps, 3)
         breakdown["_instrumented_step_ms"] = round(prof_ms, 3)
 
-    if rank == 0 and args.torch_profile:
+    if args.torch_profile:
         from torch.profiler import ProfilerActivity, profile
 
         with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
             step_resident(0)
             torch.cuda.synchronize()
-        with open(args.torch_profile, "w") as f:
-            f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=70))
+        if rank == 0:
+            with open(args.torch_profile, "w") as f:
+                f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=70))
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
