@@ -33,7 +33,7 @@ class MlpDesc(ctypes.Structure):
 class FieldDesc(ctypes.Structure):
     _fields_ = [("aabb", ctypes.c_float * 6), ("moving_step", ctypes.c_float), ("use_div_offsets", ctypes.c_int),
                 ("time_mode", ctypes.c_int), ("time_before_sigma", ctypes.c_int), ("f1", MlpDesc), ("f2", MlpDesc),
-                ("f3", MlpDesc), ("levels", GridLevels)]
+                ("f3", MlpDesc), ("f4", MlpDesc), ("levels", GridLevels)]
 
 
 # p = pointer, i = int, l = int64, f = float, G = GridLevels*, M = MlpDesc*, F = FieldDesc*
@@ -57,6 +57,8 @@ _SIGNATURES = {
     "cednerf_mlp_fwd": "ppMlppp",
     "cednerf_mlp_bwd": "ppppMlpippp",
     "cednerf_field_fwd": "ppppppppilppppFppp",
+    "cednerf_field_train_fwd": "ppppppilpppppFppppppp",
+    "cednerf_field_train_bwd": "ppppppilpppppFpppppppppppppp",
     "cednerf_ray_offsets": "pllpp",
     "cednerf_composite_fwd": "pppppppillpppppppifp",
     "cednerf_composite_bwd": "pppppppillppppppppppfp",
@@ -82,6 +84,9 @@ def load() -> ctypes.CDLL:
     lib.cednerf_last_error.restype = ctypes.c_char_p
     lib.cednerf_scan_workspace_bytes.restype = ctypes.c_int64
     lib.cednerf_launch_count.restype = ctypes.c_int64
+    for name in ("cednerf_field_saved_bytes", "cednerf_field_bwd_workspace_bytes"):
+        getattr(lib, name).restype = ctypes.c_int64
+        getattr(lib, name).argtypes = [ctypes.POINTER(FieldDesc), ctypes.c_int64]
     lib.cednerf_scan_workspace_bytes.argtypes = [ctypes.c_int64]
     for name, sig in _SIGNATURES.items():
         fn = getattr(lib, name)
@@ -93,7 +98,8 @@ def load() -> ctypes.CDLL:
 
 def exported_symbols():
     return sorted(list(_SIGNATURES) + ["cednerf_last_error", "cednerf_abi_version", "cednerf_check_device",
-                                       "cednerf_scan_workspace_bytes", "cednerf_launch_count"])
+                                       "cednerf_scan_workspace_bytes", "cednerf_launch_count", "cednerf_field_saved_bytes",
+                                       "cednerf_field_bwd_workspace_bytes"])
 
 
 def ptr(t: Optional[torch.Tensor]):

@@ -1,0 +1,193 @@
+// Shared pieces of the fused field kernels (inference: field.cu, training: field_train.cu).
+#pragma once
+#include "hashgrid.cuh"
+#include "tc05.cuh"
+
+struct CednerfFieldDesc {
+  float aabb[6];
+  float moving_step;
+  int use_div_offsets;    // deformation net emits 6 values: move = o[:3]*MS + tanh(o[3:])*MS   (model.py:358-363)
+  int time_mode;          // 0 none, 1 SinusoidalEncoder, 2 SinusoidalEncoderWithExp (attenuated by |move|)
+  int time_before_sigma;  // 1: density-MLP input = [hash | time9];  0: colour-MLP input = [sh4 | feat15 | time9]
+  CednerfMlpDesc f1, f2, f3;  // deformation, density, colour networks
+  CednerfMlpDesc f4;          // hash-feature predictor (-f, training only); n_layers == 0 when absent
+  CednerfGridLevels levels;
+};
+
+namespace {
+
+__device__ __forceinline__ void group_sync(int group) { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); }
+
+// Layers of one network on the 128-row tile in `abuf` (one warp-group of 4 warps = one tile).  Hidden activations are
+// written back IN PLACE: the MMA that read the tile has completed (commit -> mbarrier) before any row is overwritten.
+// The last layer's accumulator is left in TMEM columns [0, N_last) of this group's TMEM slice.
+__device__ __forceinline__ void run_chain(const CednerfMlpDesc& d, const uint8_t* wimg, uint8_t* abuf, uint32_t tmem_grp,
+                                          uint32_t tmem_warp, uint64_t* bar, uint32_t& phase, int gtid, int group,
+                                          __half* save = nullptr, int64_t save_layer_stride = 0, int64_t save_row = -1) {
+  const int L = d.n_layers;
+  for (int l = 0; l < L; ++l) {
+    const int K = d.dim_in[l], N = d.dim_out[l];
+    if (gtid == 0) {
+      tc_fence_after();
+      const uint64_t ad = make_desc(smem_u32(abuf), 1, 64);
+      const uint64_t bd = make_desc(smem_u32(wimg + d.image_off[l]), 1, 64);
+      const uint32_t id = make_idesc(128, N, 0, 0);
+      for (int k = 0; k < K / 16; ++k) umma(tmem_grp, ad + 2 * k, bd + 2 * k, id, k > 0);
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    if (l < L - 1) {
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) {
+        uint32_t r[16];
+        tmem_ld16(tmem_warp + cb * 16, r);
+        tmem_ld_wait();
+        uint32_t p[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          p[j] = pack_h2(fmaxf(__uint_as_float(r[2 * j]), 0.f), fmaxf(__uint_as_float(r[2 * j + 1]), 0.f));
+        *reinterpret_cast<uint4*>(abuf + swz(gtid, 2 * cb)) = make_uint4(p[0], p[1], p[2], p[3]);
+        *reinterpret_cast<uint4*>(abuf + swz(gtid, 2 * cb + 1)) = make_uint4(p[4], p[5], p[6], p[7]);
+        if (save && save_row >= 0) {  // post-ReLU activations kept for the backward pass (one 128-byte row per thread)
+          uint4* dst = reinterpret_cast<uint4*>(save + l * save_layer_stride + save_row * 64 + cb * 16);
+          dst[0] = make_uint4(p[0], p[1], p[2], p[3]);
+          dst[1] = make_uint4(p[4], p[5], p[6], p[7]);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      group_sync(group);
+    }
+  }
+}
+
+// value the tensor-core chain hands on: fp32 accumulator rounded to fp16 (tcnn network output precision)
+__device__ __forceinline__ float rnd16(uint32_t acc_bits) { return __half2float(__float2half_rn(__uint_as_float(acc_bits))); }
+
+__device__ __forceinline__ void time_embedding(float tv, float mvnorm, int mode, float* e /*[9]*/) {
+  const float half_pi = 1.5707963267948966f;
+  e[0] = tv;
+  if (mode == 1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float tb = tv * (float)(1 << i);
+      e[1 + i] = sinf(tb);
+      e[5 + i] = sinf(tb + half_pi);
+    }
+  } else {
+    const float scm[4] = {0.f, 2.f, 8.f, 24.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float tb = tv * (float)(1 << i);
+      const float att = expf(-1.f * (mvnorm * scm[i]));
+      e[1 + 2 * i] = sinf(tb) * att;
+      e[2 + 2 * i] = sinf(tb + half_pi) * att;
+    }
+  }
+}
+
+// 2*L hash features of one point, packed as L half2 words (numerics of hashgrid_fwd_kernel)
+template <int LG>
+__device__ __forceinline__ void hash_levels(const float* xn, const __half* __restrict__ table, const CednerfGridLevels& lv,
+                                            int l0, uint32_t* feat) {
+  const __half2* t2 = reinterpret_cast<const __half2*>(table);
+  float frac[LG][3];
+  __half2 v[LG][8];
+#pragma unroll
+  for (int a = 0; a < LG; ++a) {  // issue all 8*LG gathers first ...
+    const int l = l0 + a;
+    const Cell c = locate(xn, lv.scale[l]);
+    frac[a][0] = c.f[0], frac[a][1] = c.f[1], frac[a][2] = c.f[2];
+    uint32_t idx[8];
+    cell_indices(c.g, lv.res[l], lv.size[l], lv.offset[l], lv.hashed[l] != 0, idx);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[a][k] = __ldg(t2 + idx[k]);
+  }
+#pragma unroll
+  for (int a = 0; a < LG; ++a) {  // ... then the weights (recomputed from 3 fractions) and the blend
+    float w[8];
+    cell_weights(frac[a], w);
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float2 f = __half22float2(v[a][k]);
+      a0 = __fadd_rn(a0, __fmul_rn(w[k], f.x));
+      a1 = __fadd_rn(a1, __fmul_rn(w[k], f.y));
+    }
+    feat[l0 + a] = pack_h2(a0, a1);
+  }
+}
+
+
+// position / time of packed sample s (cednerf/utils.py:74-104): x = o + (d * (t0 + t1)) / 2, individually rounded
+__device__ __forceinline__ void packed_sample(const int64_t* __restrict__ ridx, const float* __restrict__ t0,
+                                              const float* __restrict__ t1, const float* __restrict__ rays_o,
+                                              const float* __restrict__ rays_d, const float* __restrict__ ts, int t_stride,
+                                              int64_t s, float* x, float& tv, int64_t& ray) {
+  ray = ridx[s];
+  const float tm = __fadd_rn(t0[s], t1[s]);
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    x[k] = __fadd_rn(rays_o[3 * ray + k], __fmul_rn(__fmul_rn(rays_d[3 * ray + k], tm), 0.5f));
+  tv = ts[ray * t_stride];
+}
+
+// Frequency(4 dims, 4 octaves) of (v0, v1, v2, v3) -> 32 halves in chunks 0..3 of row `row` of a swizzled tile
+__device__ __forceinline__ void frequency_row(uint8_t* tile, int row, float v0, float v1, float v2, float v3) {
+  const float in4[4] = {v0, v1, v2, v3};
+#pragma unroll
+  for (int dim = 0; dim < 4; ++dim) {
+    uint32_t p[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float ph = in4[dim] * (float)(1 << k);
+      p[k] = pack_h2(sinpif(ph), sinpif(ph + 0.5f));
+    }
+    *reinterpret_cast<uint4*>(tile + swz(row, dim)) = make_uint4(p[0], p[1], p[2], p[3]);
+  }
+}
+
+// deformation-net output (fp16 accumulator values) -> move, normalised position, selector (model.py:354-383)
+__device__ __forceinline__ void apply_move(const CednerfFieldDesc& d, const float* x, const float* off /*[6]*/, float* mv,
+                                           float* xn, bool& selector) {
+  selector = true;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    mv[k] = off[k] * d.moving_step;
+    if (d.use_div_offsets) mv[k] = mv[k] + tanhf(off[3 + k]) * d.moving_step;
+    const float xm = x[k] + mv[k];
+    xn[k] = __fdiv_rn(__fsub_rn(xm, d.aabb[k]), __fsub_rn(d.aabb[3 + k], d.aabb[k]));
+    selector = selector && (xn[k] > 0.f) && (xn[k] < 1.f);
+  }
+}
+
+// colour-net input row [SH4(dir) | feat15 | (time 9) | 1.0 ...] -> 32 halves, chunks 0..3 (model.py:447-466)
+__device__ __forceinline__ void colour_input_row(const CednerfFieldDesc& d, uint8_t* tile, int row, const float* dir,
+                                                 const float* feat15, const float* temb) {
+  const float nrm = sqrtf(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+  float v[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) v[k] = ((dir[k] / nrm + 1.f) / 2.f) * 2.f - 1.f;
+  float in[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) in[j] = 1.f;
+  in[0] = 0.28209479177387814f;
+  in[1] = -0.48860251190291987f * v[1];
+  in[2] = 0.48860251190291987f * v[2];
+  in[3] = -0.48860251190291987f * v[0];
+#pragma unroll
+  for (int j = 0; j < 15; ++j) in[4 + j] = feat15[j];
+  if (d.time_mode && !d.time_before_sigma) {
+#pragma unroll
+    for (int j = 0; j < 9; ++j) in[19 + j] = temb[j];
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    *reinterpret_cast<uint4*>(tile + swz(row, c)) =
+        make_uint4(pack_h2(in[8 * c], in[8 * c + 1]), pack_h2(in[8 * c + 2], in[8 * c + 3]),
+                   pack_h2(in[8 * c + 4], in[8 * c + 5]), pack_h2(in[8 * c + 6], in[8 * c + 7]));
+}
+
+}  // namespace

@@ -97,6 +97,8 @@ class DNGPradianceField(torch.nn.Module):
             d.time_mode = 0 if not self.use_time_embedding else (2 if self.use_time_attenuation else 1)
             d.time_before_sigma = int(self.time_inject_before_sigma)
             d.f1, d.f2, d.f3 = self.xyz_wrap.network.desc, self.mlp_base.desc, self.mlp_head.desc
+            if self.use_feat_predict:
+                d.f4 = self.mlp_feat_prediction.network.desc
             d.levels = self.hash_encoder.levels
             self._fdesc, self._fdesc_key = d, key
         return self._fdesc
@@ -107,6 +109,25 @@ class DNGPradianceField(torch.nn.Module):
         images = (self.xyz_wrap.network.weight_image(), self.mlp_base.weight_image(), self.mlp_head.weight_image())
         return ops.field_fwd(self._field_desc(), images, self.hash_encoder.table_f16(), n, sigma_only, packed, points,
                              timestamps, t_stride)
+
+    def fused_train_supported(self) -> bool:
+        return (self.fused_supported() and not self.use_weight_predict
+                and (not self.use_feat_predict or self.hash_encoder.n_levels == 16))
+
+    def fused_train(self, ridx, t0, t1, rays_o, rays_d, timestamps, t_stride):
+        """Training forward of `forward(positions, t, directions)` on packed samples, differentiable w.r.t. every
+        parameter: -> (rgb [n,3], {"density", "base_mlp_out", "interal_output"}) like the op-by-op path."""
+        f4 = self.mlp_feat_prediction.network if self.use_feat_predict else None
+        images = (self.xyz_wrap.network.weight_image(), self.mlp_base.weight_image(), self.mlp_head.weight_image(),
+                  None if f4 is None else f4.weight_image())
+        sigma, rgb, latent, selector, move = ops.FieldTrainFunction.apply(
+            self.xyz_wrap.network.params, self.mlp_base.params, self.mlp_head.params,
+            None if f4 is None else f4.params, self.hash_encoder.params.view(-1, 2), self._field_desc(), images,
+            self.hash_encoder.table_f16(), ridx, t0, t1, rays_o, rays_d, timestamps, t_stride, f4 is not None)
+        io = {"move": torch.linalg.norm(move, dim=-1) if (self.use_time_embedding and self.use_time_attenuation) else move}
+        if self.use_feat_predict:
+            io["selector"], io["latent_losses"] = selector, latent
+        return rgb, {"density": sigma[:, None], "interal_output": io}
 
     def query_move(self, x, t):
         off = self.xyz_wrap(torch.cat([x, t], -1)).float()

@@ -504,3 +504,58 @@ def field_fwd(desc: FieldDesc, images, table_f16, n: int, sigma_only: bool, pack
     call("cednerf_field_fwd", *args, ptr(ts), int(t_stride), n, ptr(images[0]), ptr(images[1]), ptr(images[2]),
          ptr(table_f16), ctypes.byref(desc), ptr(sigma), ptr(rgb), stream())
     return sigma, rgb
+
+
+class FieldTrainFunction(torch.autograd.Function):
+    """Training-mode DNGPradianceField.forward on packed ray samples: one forward launch, backward = one tensor-core
+    launch per network + the hash-grid backward.  Returns (sigma [n], rgb [n,3], latent [n,32] | None, selector, move)."""
+
+    @staticmethod
+    def forward(ctx, p1, p2, p3, p4, table, desc, images, table_f16, ridx, t0, t1, rays_o, rays_d, ts, t_stride,
+                want_latent):
+        _lib.check_device()
+        lib = _lib.load()
+        n, dev = t0.numel(), t0.device
+        ridx = ridx.detach().to(I64).contiguous()
+        t0, t1, rays_o, rays_d = _f32c(t0), _f32c(t1), _f32c(rays_o), _f32c(rays_d)
+        ts = _f32c(ts).view(-1)
+        sigma = torch.empty(n, device=dev)
+        rgb = torch.empty(n, 3, device=dev)
+        latent = torch.empty(n, 32, device=dev) if want_latent else None
+        selector = torch.empty(n, dtype=torch.bool, device=dev)
+        move = torch.empty(n, 3, device=dev)
+        saved = torch.empty(max(int(lib.cednerf_field_saved_bytes(ctypes.byref(desc), n)), 16), dtype=U8, device=dev)
+        call("cednerf_field_train_fwd", ptr(ridx), ptr(t0), ptr(t1), ptr(rays_o), ptr(rays_d), ptr(ts), int(t_stride), n,
+             ptr(images[0]), ptr(images[1]), ptr(images[2]), ptr(images[3]), ptr(table_f16), ctypes.byref(desc),
+             ptr(sigma), ptr(rgb), ptr(latent), ptr(selector), ptr(move), ptr(saved), stream())
+        ctx.save_for_backward(ridx, t0, t1, rays_o, rays_d, ts, sigma, rgb, selector, saved, table_f16, images[0],
+                              images[1], images[2], images[3] if images[3] is not None else images[0])
+        ctx.desc, ctx.t_stride, ctx.has4 = desc, int(t_stride), images[3] is not None and want_latent
+        ctx.shapes = (p1.shape, p2.shape, p3.shape, None if p4 is None else p4.shape, table.shape)
+        ctx.mark_non_differentiable(selector, move)
+        if latent is None:
+            latent = torch.zeros(0, device=dev)
+        return sigma, rgb, latent, selector, move
+
+    @staticmethod
+    def backward(ctx, d_sigma, d_rgb, d_latent, _sel, _mv):
+        ridx, t0, t1, rays_o, rays_d, ts, sigma, rgb, selector, saved, table_f16, i1, i2, i3, i4 = ctx.saved_tensors
+        lib = _lib.load()
+        n, dev = t0.numel(), t0.device
+        s1, s2, s3, s4, st = ctx.shapes
+        g1, g2, g3 = (torch.zeros(s, dtype=F32, device=dev) for s in (s1, s2, s3))
+        g4 = torch.zeros(s4, dtype=F32, device=dev) if (ctx.has4 and s4 is not None) else None
+        gt = torch.zeros(st, dtype=F32, device=dev)
+        d_sigma = torch.zeros(n, device=dev) if d_sigma is None else _f32c(d_sigma)
+        d_rgb = torch.zeros(n, 3, device=dev) if d_rgb is None else _f32c(d_rgb)
+        dl = None
+        if ctx.has4 and d_latent is not None and d_latent.numel():
+            dl = _f32c(d_latent)
+        work = torch.empty(max(int(lib.cednerf_field_bwd_workspace_bytes(ctypes.byref(ctx.desc), n)), 16), dtype=U8,
+                           device=dev)
+        if n:
+            call("cednerf_field_train_bwd", ptr(ridx), ptr(t0), ptr(t1), ptr(rays_o), ptr(rays_d), ptr(ts), ctx.t_stride,
+                 n, ptr(i1), ptr(i2), ptr(i3), ptr(i4) if ctx.has4 else None, ptr(table_f16), ctypes.byref(ctx.desc),
+                 ptr(sigma), ptr(rgb), ptr(selector), ptr(saved), ptr(d_sigma), ptr(d_rgb), ptr(dl), ptr(work), ptr(g1),
+                 ptr(g2), ptr(g3), ptr(g4) if dl is not None else None, ptr(gt), stream())
+        return (g1, g2, g3, g4 if dl is not None else None, gt) + (None,) * 11

@@ -33,8 +33,10 @@ def rendering(t_starts, t_ends, ray_indices, n_rays, rgb_sigma_fn=None, rgb_alph
     io = sres.get("interal_output")
     if io is not None:
         if "latent_losses" in io:
-            extras["latent_losses"] = reduce_along_rays(ray_indices, io["latent_losses"], n_rays,
-                                                        weights[:, None].detach(), "sum")
+            # reduce_along_rays(..., weights.detach(), "sum") (cednerf/render.py:105-113) as one segmented launch
+            ridx = ray_indices.detach().to(torch.int64).contiguous()
+            extras["latent_losses"] = ops.AccumulateFunction.apply(weights.detach(), io["latent_losses"], ridx, offsets,
+                                                                   n_rays)
         if "weight_losses" in io:
             wl = F.huber_loss(io["weight_losses"].float(), trans[:, None], reduction="none")
             extras["weight_losses"] = reduce_along_rays(ray_indices, wl * io["selector"][:, None], n_rays,

@@ -49,6 +49,11 @@ def _field_fns(field, rays, timestamps):
         return field.query_density(x, t)["density"].squeeze(-1)
 
     def rgb_sigma_fn(t0, t1, ridx):
+        if (field.training and torch.is_grad_enabled() and t0.numel() > 0
+                and getattr(field, "fused_train_supported", lambda: False)()
+                and (timestamps.numel() == 1 or timestamps.numel() == rays.origins.shape[0])):
+            return field.fused_train(ridx, t0, t1, rays.origins, rays.viewdirs, timestamps,
+                                     1 if timestamps.numel() == rays.origins.shape[0] else 0)
         if can_fuse(t0) and not field.training:
             sigma, rgb = fused(t0, t1, ridx, False)
             return rgb, {"density": sigma[:, None]}

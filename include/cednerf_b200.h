@@ -137,6 +137,7 @@ typedef struct CednerfFieldDesc {
   int time_mode;         /* 0 none, 1 SinusoidalEncoder, 2 SinusoidalEncoderWithExp */
   int time_before_sigma; /* 1: density input = [hash | time9]; 0: colour input = [sh4 | feat15 | time9] */
   CednerfMlpDesc f1, f2, f3; /* deformation (xyz_wrap), density (mlp_base), colour (mlp_head) */
+  CednerfMlpDesc f4;         /* hash-feature predictor (mlp_feat_prediction, -f); n_layers == 0 when absent */
   CednerfGridLevels levels;
 } CednerfFieldDesc;
 /* DNGPradianceField.query_density / .forward without autograd (cednerf/model.py:367-488) fused with the position
@@ -147,6 +148,27 @@ int cednerf_field_fwd(const int64_t* ray_indices, const float* t_starts, const f
                       const float* rays_d, const float* x, const float* dirs, const float* timestamps, int t_stride,
                       int64_t n, const void* image_deform, const void* image_density, const void* image_colour,
                       const void* table_f16, const CednerfFieldDesc* desc, float* sigma, float* rgb, void* stream);
+
+/* DNGPradianceField.forward in training (cednerf/model.py:468-488, return_interal=True) on packed ray samples, and its
+ * backward.  `saved` (cednerf_field_saved_bytes) carries the activations; the backward accumulates into the fp32
+ * parameter gradients (tcnn flat layout) and the fp32 hash-table gradient (caller zeroes), using `work`
+ * (cednerf_field_bwd_workspace_bytes).  latent / d_latent: huber loss of the feature predictor against the hash
+ * features, [n,32] (nullable: no predictor). */
+int64_t cednerf_field_saved_bytes(const CednerfFieldDesc* desc, int64_t n);
+int64_t cednerf_field_bwd_workspace_bytes(const CednerfFieldDesc* desc, int64_t n);
+int cednerf_field_train_fwd(const int64_t* ray_indices, const float* t_starts, const float* t_ends, const float* rays_o,
+                            const float* rays_d, const float* timestamps, int t_stride, int64_t n,
+                            const void* image_deform, const void* image_density, const void* image_colour,
+                            const void* image_predict, const void* table_f16, const CednerfFieldDesc* desc, float* sigma,
+                            float* rgb, float* latent, uint8_t* selector, float* move, void* saved, void* stream);
+int cednerf_field_train_bwd(const int64_t* ray_indices, const float* t_starts, const float* t_ends, const float* rays_o,
+                            const float* rays_d, const float* timestamps, int t_stride, int64_t n,
+                            const void* image_deform, const void* image_density, const void* image_colour,
+                            const void* image_predict, const void* table_f16, const CednerfFieldDesc* desc,
+                            const float* sigma, const float* rgb, const uint8_t* selector, const void* saved,
+                            const float* d_sigma, const float* d_rgb, const float* d_latent, void* work,
+                            float* d_params_deform, float* d_params_density, float* d_params_colour,
+                            float* d_params_predict, float* g_table, void* stream);
 
 /* ---- K4: compositing ------------------------------------------------------------------------------- */
 /* offsets[r] = first sample of ray r (ray_indices sorted); offsets[n_rays] = n_samples */

@@ -61,7 +61,7 @@ def test_descriptor_structs_match_header_layout():
 
     assert ctypes.sizeof(_lib.GridLevels) == 4 + 5 * 4 * 32
     assert ctypes.sizeof(_lib.MlpDesc) == 4 + 4 * 4 * 5 + 4
-    assert ctypes.sizeof(_lib.FieldDesc) == 6 * 4 + 4 + 3 * 4 + 3 * ctypes.sizeof(_lib.MlpDesc) + ctypes.sizeof(_lib.GridLevels)
+    assert ctypes.sizeof(_lib.FieldDesc) == 6 * 4 + 4 + 3 * 4 + 4 * ctypes.sizeof(_lib.MlpDesc) + ctypes.sizeof(_lib.GridLevels)
 
 
 def test_level_geometry_matches_oracle_and_survey():

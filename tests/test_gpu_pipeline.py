@@ -225,3 +225,55 @@ def test_fused_field_query_matches_modular_path(cb, golden, name):
         s_one, _ = field.fused_query(n, packed=(ridx, t0, t1, o, d), timestamps=ts_ray[:1], t_stride=0)
         s_ref, _ = field.fused_query(n, points=(x, None), timestamps=ts_ray[:1].expand(n, 1).contiguous().view(-1))
     assert torch.equal(s_pk, s_pts) and torch.equal(c_pk, c_pts) and torch.equal(s_one, s_ref)
+
+
+@pytest.mark.parametrize("name,extra", [("plain", {}), ("te_ta_df", {}), ("te_after", {}),
+                                        ("te_ta_df", {"use_feat_predict": True})])
+def test_fused_training_path_matches_op_by_op_path(cb, golden, name, extra):
+    """cednerf_field_train_fwd/bwd (5-7 launches) against the op-by-op autograd path on the same packed samples."""
+    kw = dict(FIELD_KW)
+    if extra.get("use_feat_predict"):
+        kw.update(n_levels=16, log2_hashmap_size=14, dst_resolution=512)  # the predictor regresses 16 x 2 features
+    field = cb.DNGPradianceField(golden["scene.aabbs"][-1], **kw, **FLAG_SETS[name], **extra)
+    with torch.no_grad():
+        field.hash_encoder.params.mul_(5000.0)
+        field.mlp_base.params.mul_(3.0)
+    field = field.to(DEV).train()
+    assert field.fused_train_supported()
+    g = torch.Generator().manual_seed(21)
+    n_rays, n = 64, 1500
+    o = (torch.tensor([0.0, 0.0, -3.0]) + (torch.rand(n_rays, 3, generator=g) - 0.5) * 0.4).to(DEV)
+    d = torch.nn.functional.normalize(torch.randn(n_rays, 3, generator=g) * 0.2 + torch.tensor([0.0, 0.0, 1.0]), dim=-1).to(DEV)
+    ridx = torch.sort(torch.randint(0, n_rays, (n,), generator=g))[0].to(DEV)
+    t0 = (1.5 + torch.rand(n, generator=g) * 3).to(DEV)
+    t1 = t0 + 0.02
+    ts = torch.rand(n_rays, 1, generator=g).to(DEV)
+    g_rgb, g_sig = torch.rand(n, 3, generator=g).to(DEV), torch.rand(n, 1, generator=g).to(DEV)
+    g_lat = torch.rand(n, 32, generator=g).to(DEV) * 0.1
+
+    def loss_of(rgb, res):
+        l = (rgb * g_rgb).sum() + (res["density"] * g_sig).sum()
+        if "latent_losses" in res["interal_output"]:
+            l = l + (res["interal_output"]["latent_losses"] * g_lat).sum()
+        return l * 64.0
+
+    x = o[ridx] + d[ridx] * (t0 + t1)[:, None] / 2.0
+    rgb_m, res_m = field(x, ts[ridx], d[ridx])
+    field.zero_grad()
+    loss_of(rgb_m, res_m).backward()
+    grads_m = {k: p.grad.clone() for k, p in field.named_parameters() if p.grad is not None and p.numel()}
+    rgb_f, res_f = field.fused_train(ridx, t0, t1, o, d, ts, 1)
+    field.zero_grad()
+    loss_of(rgb_f, res_f).backward()
+    torch.testing.assert_close(rgb_f, rgb_m, rtol=0, atol=2e-3)
+    torch.testing.assert_close(res_f["density"], res_m["density"], rtol=8e-3, atol=2e-3)
+    mv_f, mv_m = res_f["interal_output"]["move"], res_m["interal_output"]["move"]
+    torch.testing.assert_close(mv_f, mv_m, rtol=2e-3, atol=2e-3 * float(mv_m.abs().max()))
+    if extra.get("use_feat_predict"):
+        lf, lm = res_f["interal_output"]["latent_losses"], res_m["interal_output"]["latent_losses"]
+        torch.testing.assert_close(lf, lm, rtol=1e-2, atol=2e-3 * float(lm.abs().max()))
+        assert torch.equal(res_f["interal_output"]["selector"], res_m["interal_output"]["selector"])
+    for k, p in field.named_parameters():
+        if k in grads_m:
+            assert p.grad is not None, k
+            assert rel(p.grad, grads_m[k]) < 5e-3, (k, rel(p.grad, grads_m[k]))
