@@ -42,7 +42,8 @@ _SIGNATURES = {
     "cednerf_sort_boundaries": "pplippp",
     "cednerf_occ_pack_bits": "plpp",
     "cednerf_occ_threshold_pack": "plpppp",
-    "cednerf_march": "ipplppiippffffipppppppppppppppppppp",
+    "cednerf_march": "ipplppiippffffippppppppppppppppppppppip",
+    "cednerf_march_fill_runs": "lppppiffppppp",
     "cednerf_exclusive_scan": "plppppp",
     "cednerf_hashgrid_fwd": "pilpGpip",
     "cednerf_hashgrid_bwd": "pilpGpiippp",

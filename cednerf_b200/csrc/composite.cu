@@ -302,6 +302,37 @@ __global__ void accumulate_bwd_kernel(const float* __restrict__ w, const float* 
   if (g_w) g_w[i] = acc;
 }
 
+// wide-channel variants (C in 8..32): one warp per ray / per sample, lane = channel, rows read as coalesced lines
+__global__ void __launch_bounds__(256)
+accumulate_wide_fwd_kernel(const float* __restrict__ w, const float* __restrict__ v, int C,
+                           const int64_t* __restrict__ offsets, int64_t n_rays, float* __restrict__ out, int inplace) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (ray >= n_rays || lane >= C) return;
+  const int64_t s0 = offsets[ray], s1 = offsets[ray + 1];
+  float acc = 0.f;
+  for (int64_t i = s0; i < s1; ++i) acc += w[i] * v[i * C + lane];
+  if (inplace) out[ray * C + lane] += acc;
+  else out[ray * C + lane] = acc;
+}
+
+__global__ void __launch_bounds__(256)
+accumulate_wide_bwd_kernel(const float* __restrict__ w, const float* __restrict__ v, int C,
+                           const int64_t* __restrict__ ridx, int64_t S, const float* __restrict__ g_out,
+                           float* __restrict__ g_w, float* __restrict__ g_v) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= S) return;
+  const int64_t r = ridx[i];
+  const float go = lane < C ? g_out[r * C + lane] : 0.f;
+  if (g_v && lane < C) g_v[i * C + lane] = w[i] * go;
+  if (g_w) {
+    float acc = lane < C ? go * v[i * C + lane] : 0.f;
+    acc = warp_sum(acc);
+    if (lane == 0) g_w[i] = acc;
+  }
+}
+
 int pick_group(int64_t S, int64_t n_rays) {
   const double mean = n_rays > 0 ? (double)S / (double)n_rays : 0.0;
   if (mean <= 6.0) return 4;
@@ -379,6 +410,11 @@ CEDNERF_EXPORT int cednerf_accumulate_fwd(const float* weights, const float* val
   CEDNERF_REQUIRE(n_rays >= 0 && n_samples >= 0 && n_channels >= 1, "bad sizes");
   if (n_rays == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (values && n_channels >= 8 && n_channels <= 32) {
+    accumulate_wide_fwd_kernel<<<cednerf_blocks(n_rays * 32, 256), 256, 0, st>>>(weights, values, n_channels, offsets,
+                                                                                 n_rays, outputs, inplace);
+    return cednerf_check_launch("cednerf_accumulate_fwd");
+  }
   DISPATCH_G(pick_group(n_samples, n_rays), accumulate_fwd_kernel, weights, values, n_channels, offsets, n_rays,
              outputs, inplace);
   return cednerf_check_launch("cednerf_accumulate_fwd");
@@ -390,6 +426,11 @@ CEDNERF_EXPORT int cednerf_accumulate_bwd(const float* weights, const float* val
   CEDNERF_REQUIRE(n_samples >= 0 && n_channels >= 1, "bad sizes");
   if (n_samples == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (values && n_channels >= 8 && n_channels <= 32) {
+    accumulate_wide_bwd_kernel<<<cednerf_blocks(n_samples * 32, 256), 256, 0, st>>>(
+        weights, values, n_channels, ray_indices, n_samples, g_outputs, g_weights, g_values);
+    return cednerf_check_launch("cednerf_accumulate_bwd");
+  }
   accumulate_bwd_kernel<<<cednerf_blocks(n_samples, 256), 256, 0, st>>>(weights, values, n_channels, ray_indices,
                                                                        n_samples, g_outputs, g_weights, g_values);
   return cednerf_check_launch("cednerf_accumulate_bwd");

@@ -53,6 +53,12 @@ struct MarchArgs {
   int32_t* n_intervals;
   int32_t* n_samples;
   float* termination;
+  // run recording (count pass, nullable): a run = maximal stretch of back-to-back samples; (t of its first left edge,
+  // number of samples) is all the fill pass needs to regenerate it with the same recurrence
+  float* run_t;      // [n, run_cap]
+  int32_t* run_n;    // [n, run_cap]
+  int32_t* n_runs;   // [n]  (may exceed run_cap: the ray then takes the full-march fill)
+  int run_cap;
 };
 
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
@@ -166,6 +172,7 @@ __global__ void __launch_bounds__(128) march_kernel(MarchArgs a) {
   int n_iv = 0, n_sm = 0;
   float t_last = near;
   bool continuous = false;
+  int runs = 0, run_len = 0;  // run bookkeeping (count pass with run recording)
   const int limit = a.limit;
   const float step_size = a.step_size, cone = a.cone_angle;
 
@@ -274,6 +281,15 @@ __global__ void __launch_bounds__(128) march_kernel(MarchArgs a) {
               a.ray_indices[k] = r;
             }
           }
+          if (!FILL && a.run_t) {
+            if (!continuous) {  // a new run starts at t_last
+              if (runs > 0 && runs <= a.run_cap) a.run_n[r * a.run_cap + runs - 1] = run_len;
+              if (runs < a.run_cap) a.run_t[r * a.run_cap + runs] = t_last;
+              ++runs;
+              run_len = 0;
+            }
+            ++run_len;
+          }
           n_iv += continuous ? 1 : 2;
           n_sm += 1;
           continuous = true;
@@ -300,9 +316,41 @@ __global__ void __launch_bounds__(128) march_kernel(MarchArgs a) {
       if (done) break;
     }
   }
+  if (!FILL && a.run_t) {
+    if (runs > 0 && runs <= a.run_cap) a.run_n[r * a.run_cap + runs - 1] = run_len;
+    a.n_runs[r] = runs;
+  }
   if (a.n_intervals) a.n_intervals[r] = n_iv;
   if (a.n_samples) a.n_samples[r] = n_sm;
   if (a.termination) a.termination[r] = t_last;
+}
+
+// Fill pass from recorded runs: no grid traversal, just the step recurrence t <- t + clamp(t*cone, step, 1e10) replayed
+// from each run's first left edge (identical fp32 operations, so identical bits).  Rays whose run list overflowed are
+// flagged in `overflow` and filled by the full-march kernel with that flag array as its ray mask.
+__global__ void __launch_bounds__(128)
+march_fill_runs_kernel(int64_t n_rays, const int64_t* __restrict__ sm_starts, const float* __restrict__ run_t,
+                       const int32_t* __restrict__ run_n, const int32_t* __restrict__ n_runs, int run_cap,
+                       float step_size, float cone, float* __restrict__ t_starts, float* __restrict__ t_ends,
+                       int64_t* __restrict__ ray_indices, uint8_t* __restrict__ overflow) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rays) return;
+  const int runs = n_runs[r];
+  const bool over = runs > run_cap;
+  overflow[r] = (uint8_t)over;
+  if (over) return;
+  int64_t k = sm_starts[r];
+  for (int j = 0; j < runs; ++j) {
+    float t = run_t[r * run_cap + j];
+    const int cnt = run_n[r * run_cap + j];
+    for (int i = 0; i < cnt; ++i, ++k) {
+      const float t_next = (step_size <= 0.0f) ? t : t + step_dt(t, cone, step_size);
+      t_starts[k] = t;
+      t_ends[k] = t_next;
+      ray_indices[k] = r;
+      t = t_next;
+    }
+  }
 }
 
 // ---- bit packing of the occupancy grid ------------------------------------------------------------
@@ -456,7 +504,10 @@ CEDNERF_EXPORT int cednerf_march(int fill, const float* rays_o, const float* ray
                                  const int64_t* iv_starts, const int64_t* sm_starts, float* iv_vals, uint8_t* iv_left,
                                  uint8_t* iv_right, int64_t* iv_ray, float* sm_vals, int64_t* sm_ray,
                                  uint8_t* sm_valid, float* t_starts, float* t_ends, int64_t* ray_indices,
-                                 int32_t* n_intervals, int32_t* n_samples, float* termination, void* stream) {
+                                 int32_t* n_intervals, int32_t* n_samples, float* termination, float* run_t,
+                                 int32_t* run_n, int32_t* n_runs, int run_cap, void* stream) {
+  CEDNERF_REQUIRE(!run_t || (!fill && run_n && n_runs && run_cap > 0 && steps_limit <= 0 && step_size > 0.0f),
+                  "run recording: count pass, unlimited steps, positive step size");
   CEDNERF_REQUIRE(n_rays >= 0 && n_levels >= 1 && n_levels <= MARCH_MAX_LEVELS && resolution >= 1,
                   "bad sizes (levels <= 8)");
   CEDNERF_REQUIRE((t_sorted == nullptr) == (t_indices == nullptr) && (t_sorted == nullptr) == (hits == nullptr),
@@ -468,11 +519,24 @@ CEDNERF_EXPORT int cednerf_march(int fill, const float* rays_o, const float* ray
   MarchArgs a{rays_o, rays_d, n_rays, occ_bits, aabbs, n_levels, resolution, near_planes, far_planes, near_const,
               far_const, step_size, cone_angle, steps_limit, rays_mask, t_sorted, t_indices, hits, iv_starts,
               sm_starts, iv_vals, iv_left, iv_right, iv_ray, sm_vals, sm_ray, sm_valid, t_starts, t_ends, ray_indices,
-              n_intervals, n_samples, termination};
+              n_intervals, n_samples, termination, run_t, run_n, n_runs, run_cap};
   const unsigned grid = cednerf_blocks(n_rays, 128);
   if (fill) march_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
   else march_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
   return cednerf_check_launch("cednerf_march");
+}
+
+// Packed fill from the runs a count pass recorded (see march_fill_runs_kernel); `overflow` [n] receives 1 for rays
+// whose run list did not fit - fill those with cednerf_march(fill = 1, rays_mask = overflow, ...).
+CEDNERF_EXPORT int cednerf_march_fill_runs(int64_t n_rays, const int64_t* sm_starts, const float* run_t,
+                                           const int32_t* run_n, const int32_t* n_runs, int run_cap, float step_size,
+                                           float cone_angle, float* t_starts, float* t_ends, int64_t* ray_indices,
+                                           uint8_t* overflow, void* stream) {
+  CEDNERF_REQUIRE(n_rays >= 0 && run_cap > 0 && step_size > 0.0f, "bad arguments");
+  if (n_rays == 0) return 0;
+  march_fill_runs_kernel<<<cednerf_blocks(n_rays, 128), 128, 0, (cudaStream_t)stream>>>(
+      n_rays, sm_starts, run_t, run_n, n_runs, run_cap, step_size, cone_angle, t_starts, t_ends, ray_indices, overflow);
+  return cednerf_check_launch("cednerf_march_fill_runs");
 }
 
 CEDNERF_EXPORT int64_t cednerf_scan_workspace_bytes(int64_t n) {

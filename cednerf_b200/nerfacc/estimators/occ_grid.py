@@ -59,9 +59,12 @@ class OccGridEstimator(torch.nn.Module):
                 near = near + u * render_step_size
         mi = ops.MarchInputs(rays_o, rays_d, occupancy_bits(self.binaries), self.aabbs, int(self.resolution[0]),
                              near, far, float(near_plane), float(far_plane), render_step_size, cone_angle)
-        _, n_sm, _ = mi.count()
+        _, n_sm, _ = mi.count(record_runs=True)
         starts, packed, total = ops.exclusive_scan(n_sm)
-        ridx, t0, t1, _ = mi.fill_packed(starts, int(total.item()))
+        if mi.runs is not None:
+            ridx, t0, t1 = mi.fill_packed_from_runs(starts, int(total.item()))
+        else:
+            ridx, t0, t1, _ = mi.fill_packed(starts, int(total.item()))
         return ridx, t0, t1, packed
 
     @torch.no_grad()

@@ -98,14 +98,38 @@ class MarchInputs:
                 ptr(self.near), ptr(self.far), self.near_const, self.far_const, self.step, self.cone, self.limit,
                 ptr(self.mask), ptr(self.t_sorted), ptr(self.t_indices), ptr(self.hits))
 
-    def count(self):
+    RUN_CAP = 8
+
+    def count(self, record_runs: bool = False):
         dev = self.o.device
         n_iv = torch.empty(self.n, dtype=I32, device=dev)
         n_sm = torch.empty(self.n, dtype=I32, device=dev)
         term = torch.empty(self.n, device=dev)
+        self.runs = None
+        if record_runs and self.limit <= 0 and self.step > 0:
+            self.runs = (torch.empty(self.n, self.RUN_CAP, device=dev), torch.empty(self.n, self.RUN_CAP, dtype=I32, device=dev),
+                         torch.empty(self.n, dtype=I32, device=dev))
+        rt, rn, nr = self.runs if self.runs is not None else (None, None, None)
         call("cednerf_march", *self._common(0), None, None, None, None, None, None, None, None, None, None, None,
-             None, ptr(n_iv), ptr(n_sm), ptr(term), stream())
+             None, ptr(n_iv), ptr(n_sm), ptr(term), ptr(rt), ptr(rn), ptr(nr), self.RUN_CAP if rt is not None else 0,
+             stream())
         return n_iv, n_sm, term
+
+    def fill_packed_from_runs(self, sm_starts, total):
+        """Packed fill replaying the recorded runs; rays with more than RUN_CAP runs take the full-march fill."""
+        dev = self.o.device
+        t0 = torch.empty(total, device=dev)
+        t1 = torch.empty(total, device=dev)
+        ridx = torch.empty(total, dtype=I64, device=dev)
+        overflow = torch.empty(self.n, dtype=torch.bool, device=dev)
+        rt, rn, nr = self.runs
+        call("cednerf_march_fill_runs", self.n, ptr(sm_starts), ptr(rt), ptr(rn), ptr(nr), self.RUN_CAP, self.step,
+             self.cone, ptr(t0), ptr(t1), ptr(ridx), ptr(overflow), stream())
+        user_mask, self.mask = self.mask, overflow  # (the packed two-pass path never carries a user mask)
+        call("cednerf_march", *self._common(1), None, ptr(sm_starts), None, None, None, None, None, None, None,
+             ptr(t0), ptr(t1), ptr(ridx), None, None, None, None, None, None, 0, stream())
+        self.mask = user_mask
+        return ridx, t0, t1
 
     def fill_packed(self, sm_starts, total):
         dev = self.o.device
@@ -114,7 +138,7 @@ class MarchInputs:
         ridx = torch.empty(total, dtype=I64, device=dev)
         term = torch.empty(self.n, device=dev)
         call("cednerf_march", *self._common(1), None, ptr(sm_starts), None, None, None, None, None, None, None,
-             ptr(t0), ptr(t1), ptr(ridx), None, None, ptr(term), stream())
+             ptr(t0), ptr(t1), ptr(ridx), None, None, ptr(term), None, None, None, 0, stream())
         return ridx, t0, t1, term
 
     def fill_nerfacc(self, iv_starts, sm_starts, n_iv_total, n_sm_total):
@@ -131,7 +155,7 @@ class MarchInputs:
         term = torch.empty(self.n, device=dev)
         call("cednerf_march", *self._common(1), ptr(iv_starts), ptr(sm_starts), ptr(iv_vals), ptr(iv_left),
              ptr(iv_right), ptr(iv_ray), ptr(sm_vals), ptr(sm_ray), ptr(sm_valid), None, None, None, ptr(n_iv),
-             ptr(n_sm), ptr(term), stream())
+             ptr(n_sm), ptr(term), None, None, None, 0, stream())
         return (iv_vals, iv_left, iv_right, iv_ray), (sm_vals, sm_ray, sm_valid), n_iv, n_sm, term
 
 

@@ -63,7 +63,14 @@ int cednerf_march(int fill, const float* rays_o, const float* rays_d, int64_t n_
                   const int64_t* iv_starts, const int64_t* sm_starts, float* iv_vals, uint8_t* iv_left,
                   uint8_t* iv_right, int64_t* iv_ray, float* sm_vals, int64_t* sm_ray, uint8_t* sm_valid,
                   float* t_starts, float* t_ends, int64_t* ray_indices, int32_t* n_intervals, int32_t* n_samples,
-                  float* termination, void* stream);
+                  float* termination, float* run_t /*nullable: [n,run_cap], count pass only*/,
+                  int32_t* run_n /*[n,run_cap]*/, int32_t* n_runs /*[n]*/, int run_cap, void* stream);
+/* Packed fill that replays the runs a count pass recorded (first left edge + length of every stretch of back-to-back
+ * samples): no second grid traversal.  overflow[r] = 1 where a ray had more than run_cap runs; fill those rays with
+ * cednerf_march(fill = 1, rays_mask = overflow). */
+int cednerf_march_fill_runs(int64_t n_rays, const int64_t* sm_starts, const float* run_t, const int32_t* run_n,
+                            const int32_t* n_runs, int run_cap, float step_size, float cone_angle, float* t_starts,
+                            float* t_ends, int64_t* ray_indices, uint8_t* overflow, void* stream);
 /* cumsum between the two traversal passes (nerfacc: torch.cumsum + .item()); stays on the device */
 int64_t cednerf_scan_workspace_bytes(int64_t n);
 int cednerf_exclusive_scan(const int32_t* counts, int64_t n, int64_t* starts /*nullable*/,

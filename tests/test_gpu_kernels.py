@@ -65,6 +65,27 @@ def test_march_two_pass_bit_exact(cb, levels, res, step, cone, inside):
     assert bool((ridx_g[1:] >= ridx_g[:-1]).all()) and bool((t1_g > t0_g).all())
 
 
+@pytest.mark.parametrize("cap", [1, 3, 8])
+def test_march_fill_from_recorded_runs(cb, cap, monkeypatch):
+    """The fill pass that replays the count pass's runs (and its full-march fallback for rays with more than `cap`
+    runs) emits exactly the oracle's packed samples."""
+    est, o, d, g = make_scene(17, 3000, 16, 2, occ=0.25)
+    near = torch.full((o.shape[0],), 0.2) + torch.rand(o.shape[0], generator=g) * 2e-2
+    far = torch.full((o.shape[0],), 1e10)
+    ridx, t0, t1, packed, _ = nf.traverse_grids(o, d, est.binaries, est.aabbs, near, far, 2e-2, 0.004, packed_only=True)
+    ops = cb.ops
+    monkeypatch.setattr(ops.MarchInputs, "RUN_CAP", cap)
+    mi = ops.MarchInputs(o.to(DEV), d.to(DEV), ops.pack_occupancy(est.binaries.to(DEV)), est.aabbs.to(DEV), 16,
+                         near.to(DEV), far.to(DEV), 0.0, 1e10, 2e-2, 0.004)
+    _, n_sm, _ = mi.count(record_runs=True)
+    n_runs = mi.runs[2]
+    assert int(n_runs.max()) > cap or cap == 8            # the fallback is exercised for the small capacities
+    starts, packed_g, total = ops.exclusive_scan(n_sm)
+    r_g, a_g, b_g = mi.fill_packed_from_runs(starts, int(total.item()))
+    assert torch.equal(packed_g.cpu(), packed)
+    assert torch.equal(r_g.cpu(), ridx) and torch.equal(a_g.cpu(), t0) and torch.equal(b_g.cpu(), t1)
+
+
 def test_ray_aabb_and_sort(cb):
     est, o, d, _ = make_scene(11, 4096, 16, 4)
     o[:7] = 0.0  # origins inside all boxes
@@ -205,16 +226,18 @@ def test_volrend_api_and_accumulate(cb):
                                                       early_stop_eps=1e-2, alpha_thre=0.05)
     assert (vis_g.cpu() != vis).float().mean() < 1e-3  # threshold ties only
     # accumulate: out-of-place with autograd, and in place
-    vals = torch.rand(ridx.numel(), 5, generator=g)
-    gout = torch.rand(n_rays, 5, generator=g)
-    wv, vv = w.clone().requires_grad_(True), vals.clone().requires_grad_(True)
-    (nf.accumulate_along_rays(wv, vv, ridx, n_rays) * gout).sum().backward()
-    wg, vg = to(w).requires_grad_(True), to(vals).requires_grad_(True)
-    out_g = cb.nerfacc.accumulate_along_rays(wg, vg, to(ridx), n_rays)
-    (out_g * to(gout)).sum().backward()
-    torch.testing.assert_close(out_g.detach().cpu(), nf.accumulate_along_rays(w, vals, ridx, n_rays), rtol=1e-5, atol=1e-5)
-    torch.testing.assert_close(wg.grad.cpu(), wv.grad, rtol=1e-5, atol=1e-6)
-    torch.testing.assert_close(vg.grad.cpu(), vv.grad, rtol=1e-5, atol=1e-6)
+    for n_ch in (5, 12, 32):  # narrow (group-per-ray) and wide (lane = channel) kernels
+        vals = torch.rand(ridx.numel(), n_ch, generator=g)
+        gout = torch.rand(n_rays, n_ch, generator=g)
+        wv, vv = w.clone().requires_grad_(True), vals.clone().requires_grad_(True)
+        (nf.accumulate_along_rays(wv, vv, ridx, n_rays) * gout).sum().backward()
+        wg, vg = to(w).requires_grad_(True), to(vals).requires_grad_(True)
+        out_g = cb.nerfacc.accumulate_along_rays(wg, vg, to(ridx), n_rays)
+        (out_g * to(gout)).sum().backward()
+        torch.testing.assert_close(out_g.detach().cpu(), nf.accumulate_along_rays(w, vals, ridx, n_rays), rtol=1e-5,
+                                   atol=1e-5)
+        torch.testing.assert_close(wg.grad.cpu(), wv.grad, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(vg.grad.cpu(), vv.grad, rtol=1e-5, atol=1e-6)
     acc = torch.rand(n_rays, 1, generator=g)
     acc_g = to(acc).clone()
     cb.nerfacc.accumulate_along_rays_(to(w), None, to(ridx), acc_g)
