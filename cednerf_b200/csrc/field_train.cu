@@ -516,7 +516,8 @@ __global__ void __launch_bounds__(MLP_TILE) field_bwd_kernel(TrainArgs a) {
           const uint64_t ad = make_desc(smem_u32(gbuf[cur]), 64, 64);
           const uint64_t bd = make_desc(smem_u32(ibuf[cur]), 64, 64);
           const uint32_t id = make_idesc(64, K_in, 1, 1);
-          const uint32_t acc = tmem_base + 64u * (uint32_t)(l + 1);
+          // M = 64 accumulators occupy 16 of the 32 lanes of each TMEM sub-partition: two layers share a column block
+          const uint32_t acc = tmem_base + 64u * (uint32_t)(1 + (l >> 1)) + ((uint32_t)((l & 1) * 16) << 16);
           for (int k = 0; k < MLP_TILE / 16; ++k) umma(acc, ad + 128 * k, bd + 128 * k, id, (iter > 0) || (k > 0));
         }
         if (need_dgrad) {
@@ -600,12 +601,13 @@ __global__ void __launch_bounds__(MLP_TILE) field_bwd_kernel(TrainArgs a) {
     tc_fence_after();
     for (int l = 0; l < L; ++l) {
       const int K_in = d.dim_in[l], N_out = d.dim_out[l];
-      const int m = warp * 16 + lane;
+      const int half = l & 1;                       // which 16-lane half of the sub-partition holds this layer
+      const int m = warp * 16 + (lane & 15);
       for (int cb = 0; cb < K_in / 16; ++cb) {
         uint32_t r[16];
-        tmem_ld16(tmem_warp + 64u * (uint32_t)(l + 1) + cb * 16, r);
+        tmem_ld16(tmem_warp + 64u * (uint32_t)(1 + (l >> 1)) + cb * 16, r);
         tmem_ld_wait();
-        if (lane < 16 && m < N_out) {
+        if ((lane >> 4) == half && m < N_out) {
           float* dst = d_params + d.param_off[l] + m * K_in + cb * 16;
 #pragma unroll
           for (int j = 0; j < 16; ++j) atomicAdd(dst + j, __uint_as_float(r[j]));
@@ -651,7 +653,7 @@ int launch_bwd(TrainArgs a, cudaStream_t st) {
     configured = true;
   }
   const CednerfMlpDesc& d = NET == 1 ? a.d.f1 : (NET == 2 ? a.d.f2 : (NET == 3 ? a.d.f3 : a.d.f4));
-  uint32_t cols = 64u * (uint32_t)(d.n_layers + 1), alloc = 64;
+  uint32_t cols = 64u * (uint32_t)(1 + (d.n_layers + 1) / 2), alloc = 64;
   while (alloc < cols) alloc <<= 1;
   a.tmem_cols = alloc;
   const int64_t tiles = (a.n + MLP_TILE - 1) / MLP_TILE;

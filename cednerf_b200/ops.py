@@ -98,7 +98,7 @@ class MarchInputs:
                 ptr(self.near), ptr(self.far), self.near_const, self.far_const, self.step, self.cone, self.limit,
                 ptr(self.mask), ptr(self.t_sorted), ptr(self.t_indices), ptr(self.hits))
 
-    RUN_CAP = 8
+    RUN_CAP = 16
 
     def count(self, record_runs: bool = False):
         dev = self.o.device

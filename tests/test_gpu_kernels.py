@@ -65,7 +65,7 @@ def test_march_two_pass_bit_exact(cb, levels, res, step, cone, inside):
     assert bool((ridx_g[1:] >= ridx_g[:-1]).all()) and bool((t1_g > t0_g).all())
 
 
-@pytest.mark.parametrize("cap", [1, 3, 8])
+@pytest.mark.parametrize("cap", [1, 3, 16])
 def test_march_fill_from_recorded_runs(cb, cap, monkeypatch):
     """The fill pass that replays the count pass's runs (and its full-march fallback for rays with more than `cap`
     runs) emits exactly the oracle's packed samples."""
@@ -79,7 +79,7 @@ def test_march_fill_from_recorded_runs(cb, cap, monkeypatch):
                          near.to(DEV), far.to(DEV), 0.0, 1e10, 2e-2, 0.004)
     _, n_sm, _ = mi.count(record_runs=True)
     n_runs = mi.runs[2]
-    assert int(n_runs.max()) > cap or cap == 8            # the fallback is exercised for the small capacities
+    assert int(n_runs.max()) > cap or cap == 16            # the fallback is exercised for the small capacities
     starts, packed_g, total = ops.exclusive_scan(n_sm)
     r_g, a_g, b_g = mi.fill_packed_from_runs(starts, int(total.item()))
     assert torch.equal(packed_g.cpu(), packed)
