@@ -47,6 +47,7 @@ _SIGNATURES = {
     "cednerf_exclusive_scan": "plppppp",
     "cednerf_hashgrid_fwd": "pilpGpip",
     "cednerf_hashgrid_bwd": "pilpGpiippp",
+    "cednerf_hashgrid_bwd_table_lm": "pilGppp",
     "cednerf_hashgrid4d_fwd": "pilpGpiip",
     "cednerf_hashgrid4d_bwd": "pilGpiipip",
     "cednerf_cast_f32_to_f16": "pplp",

@@ -265,7 +265,7 @@ CEDNERF_EXPORT int cednerf_field_fwd(const int64_t* ray_indices, const float* t_
   CEDNERF_REQUIRE((ray_indices && t_starts && t_ends && rays_o && rays_d) || (!ray_indices && x), "need packed samples or points");
   CEDNERF_REQUIRE(!rgb || ray_indices || dirs, "colour needs directions");
   if (n == 0) return 0;
-  const int n_groups = 3;  // 3 tiles (12 warps) per CTA, 2 CTAs per SM: 24 warps/SM at <= 85 registers/thread
+  const int n_groups = 3;  // 3 tiles (12 warps) per CTA, 2 CTAs per SM: 24 warps/SM at 80 registers/thread (4 x 64 regs spills: 1.6x slower)
   const int smem = desc->f1.image_bytes + desc->f2.image_bytes + (rgb ? desc->f3.image_bytes : 0) +
                    n_groups * MLP_TILE_BYTES + 2048;
   static bool configured = false;

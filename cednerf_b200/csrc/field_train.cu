@@ -35,7 +35,7 @@ __host__ __device__ inline SavedLayout saved_layout(const CednerfFieldDesc& d, i
 }
 
 struct BwdWorkLayout {
-  int64_t d_o2, d_in2, d_in4, g_xn, total;
+  int64_t d_o2, d_in2, d_in4, g_xn, dy_lm, total;
 };
 
 __host__ __device__ inline BwdWorkLayout bwd_layout(const CednerfFieldDesc& d, int64_t n) {
@@ -45,6 +45,7 @@ __host__ __device__ inline BwdWorkLayout bwd_layout(const CednerfFieldDesc& d, i
   w.d_in2 = off, off += n * d.f2.dim_in[0] * 2;
   w.d_in4 = off, off += n * 64;
   w.g_xn = off, off += (n * 12 + 15) / 16 * 16;
+  w.dy_lm = off, off += (int64_t)d.levels.n_levels * n * 4;  // hash-feature gradient, [level][sample] half2
   w.total = off;
   return w;
 }
@@ -366,6 +367,7 @@ __device__ __forceinline__ void make_dout(const TrainArgs& a, const SavedLayout&
           // the hash features are the huber target too: dL/dfeat -= dL/dpred (added to the density net's input gradient)
           __half2 acc = __hsub2(*reinterpret_cast<const __half2*>(&gw[j]), *reinterpret_cast<const __half2*>(&dw));
           gw[j] = *reinterpret_cast<uint32_t*>(&acc);
+          reinterpret_cast<uint32_t*>(a.work + wl.dy_lm)[(int64_t)(4 * c + j) * a.n + s] = gw[j];
         }
         gs[c] = make_uint4(gw[0], gw[1], gw[2], gw[3]);
       }
@@ -587,6 +589,12 @@ __global__ void __launch_bounds__(MLP_TILE) field_bwd_kernel(TrainArgs a) {
               for (int j = 0; j < 8; ++j) p[j] = pack_h2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
               reinterpret_cast<uint4*>(out)[2 * cb] = make_uint4(p[0], p[1], p[2], p[3]);
               reinterpret_cast<uint4*>(out)[2 * cb + 1] = make_uint4(p[4], p[5], p[6], p[7]);
+              if constexpr (NET == 2) {  // level-major copy of the hash-feature part for the table-gradient kernel
+                uint32_t* lm = reinterpret_cast<uint32_t*>(a.work + wl.dy_lm);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (8 * cb + j < a.d.levels.n_levels) lm[(int64_t)(8 * cb + j) * n + s] = p[j];
+              }
             }
           }
         }
@@ -665,6 +673,8 @@ int launch_bwd(TrainArgs a, cudaStream_t st) {
 }  // namespace
 
 // hash-grid backward of hashgrid.cu (table gradient with run aggregation, dL/dx)
+extern "C" int cednerf_hashgrid_bwd_table_lm(const float* x, int x_stride, int64_t n, const CednerfGridLevels* levels,
+                                             const void* dy_lm_f16, float* g_table, void* stream);
 extern "C" int cednerf_hashgrid_bwd(const float* x, int x_stride, int64_t n, const void* table_f16,
                                     const CednerfGridLevels* levels, const void* dy, int dy_stride, int dy_is_f16,
                                     float* g_table, float* g_x, void* stream);
@@ -763,8 +773,10 @@ CEDNERF_EXPORT int cednerf_field_train_bwd(const int64_t* ray_indices, const flo
   }
   const float* xn = reinterpret_cast<const float*>((const uint8_t*)saved + sl.xn);
   float* g_xn = reinterpret_cast<float*>((uint8_t*)work + wl.g_xn);
+  rc = cednerf_hashgrid_bwd_table_lm(xn, 3, n, &desc->levels, (const uint8_t*)work + wl.dy_lm, g_table, stream);
+  if (rc) return rc;
   rc = cednerf_hashgrid_bwd(xn, 3, n, table_f16, &desc->levels, (const uint8_t*)work + wl.d_in2, desc->f2.dim_in[0], 1,
-                            g_table, g_xn, stream);
+                            nullptr, g_xn, stream);
   if (rc) return rc;
   if ((rc = launch_bwd<1>(a, st))) return rc;
   return cednerf_check_launch("cednerf_field_train_bwd", launches + 1);

@@ -167,7 +167,7 @@ hashgrid_bwd_kernel(const float* __restrict__ x, int x_stride, int64_t n, const 
 // DyNeRF scene the content occupies [-1,1]^3 of a [-8,8]^3 grid: the 16^3 level sees ~64 distinct entries in total).
 // Lanes are grouped into runs of equal cell; each run is summed with a segmented shuffle scan and only its last lane
 // issues the vector reduction.  Fine levels degenerate to runs of one lane (one reduction per corner, as before).
-template <typename GradT>
+template <typename GradT, bool LEVEL_MAJOR>
 __global__ void __launch_bounds__(256)
 hashgrid_bwd_table_kernel(const float* __restrict__ x, int x_stride, int64_t n, CednerfGridLevels lv,
                           const GradT* __restrict__ dy, int dy_stride, float* __restrict__ g_table) {
@@ -181,8 +181,13 @@ hashgrid_bwd_table_kernel(const float* __restrict__ x, int x_stride, int64_t n, 
   const bool hashed = lv.hashed[l] != 0;
   float d0 = 0.f, d1 = 0.f;
   if (active) {
-    d0 = (float)dy[s * dy_stride + 2 * l];
-    d1 = (float)dy[s * dy_stride + 2 * l + 1];
+    if (LEVEL_MAJOR) {  // dy stored [level][sample][2]: one coalesced 4-byte read per lane, each byte read once
+      d0 = (float)dy[((int64_t)l * n + s) * 2];
+      d1 = (float)dy[((int64_t)l * n + s) * 2 + 1];
+    } else {
+      d0 = (float)dy[s * dy_stride + 2 * l];
+      d1 = (float)dy[s * dy_stride + 2 * l + 1];
+    }
   }
   // run structure: a lane starts a run when its cell differs from the previous lane's
   const uint32_t px = __shfl_up_sync(0xffffffffu, c.g[0], 1), py = __shfl_up_sync(0xffffffffu, c.g[1], 1),
@@ -259,9 +264,9 @@ CEDNERF_EXPORT int cednerf_hashgrid_bwd(const float* x, int x_stride, int64_t n,
   if (g_table) {
     dim3 grid(cednerf_blocks(n, 256), levels->n_levels);
     if (dy_is_f16)
-      hashgrid_bwd_table_kernel<__half><<<grid, 256, 0, st>>>(x, x_stride, n, *levels, (const __half*)dy, dy_stride, g_table);
+      hashgrid_bwd_table_kernel<__half, false><<<grid, 256, 0, st>>>(x, x_stride, n, *levels, (const __half*)dy, dy_stride, g_table);
     else
-      hashgrid_bwd_table_kernel<float><<<grid, 256, 0, st>>>(x, x_stride, n, *levels, (const float*)dy, dy_stride, g_table);
+      hashgrid_bwd_table_kernel<float, false><<<grid, 256, 0, st>>>(x, x_stride, n, *levels, (const float*)dy, dy_stride, g_table);
     ++launches;
   }
   if (g_x) {
@@ -275,6 +280,19 @@ CEDNERF_EXPORT int cednerf_hashgrid_bwd(const float* x, int x_stride, int64_t n,
     ++launches;
   }
   return cednerf_check_launch("cednerf_hashgrid_bwd", launches);
+}
+
+// Table gradient from a LEVEL-MAJOR fp16 gradient dy_lm[level][sample][2] (what the fused density-net backward
+// writes): every level pass streams its own 4 bytes/sample instead of striding through a [n, 2L] row-major matrix.
+CEDNERF_EXPORT int cednerf_hashgrid_bwd_table_lm(const float* x, int x_stride, int64_t n, const CednerfGridLevels* levels,
+                                                 const void* dy_lm_f16, float* g_table, void* stream) {
+  CEDNERF_REQUIRE(check_levels(levels), "bad level table");
+  CEDNERF_REQUIRE(n >= 0 && x_stride >= 3 && dy_lm_f16 && g_table, "bad arguments");
+  if (n == 0) return 0;
+  dim3 grid(cednerf_blocks(n, 256), levels->n_levels);
+  hashgrid_bwd_table_kernel<__half, true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_stride, n, *levels,
+                                                                                 (const __half*)dy_lm_f16, 0, g_table);
+  return cednerf_check_launch("cednerf_hashgrid_bwd_table_lm");
 }
 
 CEDNERF_EXPORT int cednerf_hashgrid4d_fwd(const float* xyzt, int x_stride, int64_t n, const void* table_f16,

@@ -94,6 +94,9 @@ int cednerf_hashgrid_fwd(const float* x, int x_stride, int64_t n, const void* ta
 int cednerf_hashgrid_bwd(const float* x, int x_stride, int64_t n, const void* table_f16,
                          const CednerfGridLevels* levels, const void* dy, int dy_stride, int dy_is_f16,
                          float* g_table /*nullable*/, float* g_x /*nullable*/, void* stream);
+/* table gradient from a level-major fp16 gradient dy_lm[level][sample][2] (written by the fused density-net backward) */
+int cednerf_hashgrid_bwd_table_lm(const float* x, int x_stride, int64_t n, const CednerfGridLevels* levels,
+                                  const void* dy_lm_f16, float* g_table, void* stream);
 /* 4-D (xyz+t, 4 key-frames x 2 features per entry) — hash_encoder_inter.py:121-199 / :202-275 */
 int cednerf_hashgrid4d_fwd(const float* xyzt, int x_stride, int64_t n, const void* table_f16,
                            const CednerfGridLevels* levels, void* out_f16, int out_stride, int taichi_compat,
