@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--cpu-rays", type=int, default=2048, help="rays per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=3, help="instrumented steps for the per-kernel breakdown")
+    ap.add_argument("--render-frames", type=int, default=2, help="full frames per rank for the render leg (0 = skip)")
     ap.add_argument("--torch-profile", default="", help="write a torch.profiler kernel table of one step to this file")
     return ap.parse_args()
 
@@ -286,6 +287,36 @@ def run_ours(args):
             with open(args.torch_profile, "w") as f:
                 f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=70))
 
+    # ---- render leg (BASELINE.json configs[3]): full 1352 x 1014 frames through render_image_test, frames sharded over
+    # ranks with no collective; reported beside the train-step headline --------------------------------------------------
+    render = None
+    if args.render_frames > 0:
+        field.eval(), est.eval()
+        o, d = workload.frame_rays(cfg, 0)
+        frame = cb.Rays(o.to(dev).view(cfg.height, cfg.width, 3), d.to(dev).view(cfg.height, cfg.width, 3))
+        black = torch.zeros(3, device=dev)
+        frames = dp.shard_interleaved(args.render_frames * world, rank, world)   # weak scaling: render_frames per rank
+
+        def render_one(i):
+            t = torch.tensor([[frames[i % len(frames)] / 300.0]], device=dev)     # t = i / 300 (dnerf_3d_video_IS.py:366)
+            return cb.render_image_test(1024, field, est, frame, render_bkgd=black, timestamps=t, **rk)[3]
+
+        render_one(0)
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        n_render = sum(render_one(i) for i in range(len(frames)))
+        r1.record()
+        barrier()
+        ms_r = dp.max_over_ranks(r0.elapsed_time(r1), dev)
+        n_render_all = dp.sum_over_ranks(n_render, dev)
+        rays_r = cfg.width * cfg.height * len(frames) * world
+        render = {"workload": f"{cfg.width}x{cfg.height} frames, render_image_test(max_samples=1024), "
+                              f"{len(frames)} frame(s)/GPU, frame-sharded, no collective",
+                  "rays_per_s": round(rays_r / (ms_r * 1e-3), 1), "samples_per_s": round(n_render_all / (ms_r * 1e-3), 1),
+                  "ms_per_frame": round(ms_r / len(frames), 3), "samples_per_ray": round(n_render_all / rays_r, 3)}
+        field.train(), est.train()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = run_reference_steps(args.cpu_rays, steps=2, warmup=1)
@@ -309,7 +340,7 @@ def run_ours(args):
                        "parallelism": f"dp{world}" if world > 1 else "single"},
             "e2e": {"value": round(rays_all / (ms_e2e * 1e-3), 1), "unit": "rays/s", "ms_per_step": round(ms_e2e, 4),
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "render": render,
             "breakdown": breakdown,
         }
         print(json.dumps(line), flush=True)

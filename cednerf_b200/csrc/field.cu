@@ -106,8 +106,9 @@ __global__ void __launch_bounds__(384, 2) field_fwd_kernel(FieldFwdArgs a) {
         uint32_t p[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float ph = in4[dim] * (float)(1 << k);
-          p[k] = pack_h2(sinpif(ph), sinpif(ph + 0.5f));
+          float sn, cs;  // sin(pi ph) and sin(pi (ph + 1/2)) = cos(pi ph): one range reduction for the pair
+          sincospif(in4[dim] * (float)(1 << k), &sn, &cs);
+          p[k] = pack_h2(sn, cs);
         }
         *reinterpret_cast<uint4*>(abuf0 + swz(gtid, dim)) = make_uint4(p[0], p[1], p[2], p[3]);
       }
@@ -136,36 +137,47 @@ __global__ void __launch_bounds__(384, 2) field_fwd_kernel(FieldFwdArgs a) {
     // ---- density net input: [hash 2L | time 9 | 1.0 padding] (model.py:384-403) -------------------------------
     float temb[9];
     {
-      uint32_t feat[16];
+      // every 32-bit word (two fp16 columns) goes straight to this thread's row of the operand tile: nothing but the
+      // gathers in flight stays in registers
+      auto put_word = [&](int w, uint32_t v) {
+        *reinterpret_cast<uint32_t*>(abuf0 + swz(gtid, w >> 2) + ((w & 3) << 2)) = v;
+      };
+      const int k2 = d.f2.dim_in[0];
+      if ((L & 3) == 0) {
 #pragma unroll
-      for (int l = 0; l < 16; ++l) feat[l] = one2;
-      if ((L & 1) == 0) {
+        for (int l0 = 0; l0 < 16; l0 += 4)
+          if (l0 < L) {  // 32 gathers in flight per thread; the four levels fill exactly one 16-byte chunk of the row
+            uint32_t f4w[4];
+            hash_levels<4>(xn, a.table, d.levels, 0, f4w, l0);
+            *reinterpret_cast<uint4*>(abuf0 + swz(gtid, l0 >> 2)) = make_uint4(f4w[0], f4w[1], f4w[2], f4w[3]);
+          }
+      } else if ((L & 1) == 0) {
 #pragma unroll
         for (int l0 = 0; l0 < 16; l0 += 2)
-          if (l0 < L) hash_levels<2>(xn, a.table, d.levels, l0, feat);
+          if (l0 < L) {
+            uint32_t f2w[2];
+            hash_levels<2>(xn, a.table, d.levels, 0, f2w, l0);
+            *reinterpret_cast<uint2*>(abuf0 + swz(gtid, l0 >> 2) + ((l0 & 3) << 2)) = make_uint2(f2w[0], f2w[1]);
+          }
       } else {
 #pragma unroll
         for (int l0 = 0; l0 < 16; ++l0)
-          if (l0 < L) hash_levels<1>(xn, a.table, d.levels, l0, feat);
+          if (l0 < L) {
+            uint32_t f1w[1];
+            hash_levels<1>(xn, a.table, d.levels, 0, f1w, l0);
+            put_word(l0, f1w[0]);
+          }
       }
       if (d.time_mode) time_embedding(tv, mvnorm, d.time_mode, temb);  // after the gathers: keeps registers free
-      const int k2 = d.f2.dim_in[0];
-      uint32_t row[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) row[j] = one2;
-#pragma unroll
-      for (int l = 0; l < 16; ++l)
-        if (l < L) row[l] = feat[l];
+      int w = L;
       if (d.time_mode && d.time_before_sigma) {
         // 9 time features start at column 2L (even): pairs (e0,e1) .. (e6,e7), then (e8, 1.0)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) row[L + j] = pack_h2(temb[2 * j], temb[2 * j + 1]);
-        row[L + 4] = pack_h2(temb[8], 1.f);
+        for (int j = 0; j < 4; ++j) put_word(L + j, pack_h2(temb[2 * j], temb[2 * j + 1]));
+        put_word(L + 4, pack_h2(temb[8], 1.f));
+        w = L + 5;
       }
-#pragma unroll
-      for (int c = 0; c < 8; ++c)
-        if (c * 8 < k2)
-          *reinterpret_cast<uint4*>(abuf0 + swz(gtid, c)) = make_uint4(row[4 * c], row[4 * c + 1], row[4 * c + 2], row[4 * c + 3]);
+      for (; 2 * w < k2; ++w) put_word(w, one2);  // tcnn pads the input to a multiple of 16 with 1.0
     }
     fence_proxy_async();
     tc_fence_before();
@@ -265,7 +277,7 @@ CEDNERF_EXPORT int cednerf_field_fwd(const int64_t* ray_indices, const float* t_
   CEDNERF_REQUIRE((ray_indices && t_starts && t_ends && rays_o && rays_d) || (!ray_indices && x), "need packed samples or points");
   CEDNERF_REQUIRE(!rgb || ray_indices || dirs, "colour needs directions");
   if (n == 0) return 0;
-  const int n_groups = 3;  // 3 tiles (12 warps) per CTA, 2 CTAs per SM: 24 warps/SM at 80 registers/thread (4 x 64 regs spills: 1.6x slower)
+  const int n_groups = 3;  // 3 tiles (12 warps) per CTA, 2 CTAs/SM = 24 warps at 80 registers (4 tiles at 64 registers measured 1.3x slower)
   const int smem = desc->f1.image_bytes + desc->f2.image_bytes + (rgb ? desc->f3.image_bytes : 0) +
                    n_groups * MLP_TILE_BYTES + 2048;
   static bool configured = false;

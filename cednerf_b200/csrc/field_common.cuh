@@ -91,13 +91,13 @@ __device__ __forceinline__ void time_embedding(float tv, float mvnorm, int mode,
 // 2*L hash features of one point, packed as L half2 words (numerics of hashgrid_fwd_kernel)
 template <int LG>
 __device__ __forceinline__ void hash_levels(const float* xn, const __half* __restrict__ table, const CednerfGridLevels& lv,
-                                            int l0, uint32_t* feat) {
+                                            int l0, uint32_t* feat, int level_base = 0) {
   const __half2* t2 = reinterpret_cast<const __half2*>(table);
   float frac[LG][3];
   __half2 v[LG][8];
 #pragma unroll
   for (int a = 0; a < LG; ++a) {  // issue all 8*LG gathers first ...
-    const int l = l0 + a;
+    const int l = level_base + l0 + a;
     const Cell c = locate(xn, lv.scale[l]);
     frac[a][0] = c.f[0], frac[a][1] = c.f[1], frac[a][2] = c.f[2];
     uint32_t idx[8];
@@ -142,8 +142,9 @@ __device__ __forceinline__ void frequency_row(uint8_t* tile, int row, float v0, 
     uint32_t p[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float ph = in4[dim] * (float)(1 << k);
-      p[k] = pack_h2(sinpif(ph), sinpif(ph + 0.5f));
+      float sn, cs;  // sin(pi ph) and sin(pi (ph + 1/2)) = cos(pi ph): one range reduction for the pair
+      sincospif(in4[dim] * (float)(1 << k), &sn, &cs);
+      p[k] = pack_h2(sn, cs);
     }
     *reinterpret_cast<uint4*>(tile + swz(row, dim)) = make_uint4(p[0], p[1], p[2], p[3]);
   }
