@@ -76,7 +76,7 @@ struct CompositeFwdArgs {
   float* opacity;  // [n_rays] or null
   float* depth;    // [n_rays] or null
   float* depth_raw;  // [n_rays] or null (un-normalised, saved for backward)
-  int accumulate_inplace;  // 1: += into colors/opacity/depth, no normalise / background
+  int accumulate_inplace;  // 1: += into colors/opacity/depth, no normalise / background; 2: same, prefix = 1 - opacity[ray]
   float depth_eps;
 };
 
@@ -88,10 +88,12 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(CompositeFwdArgs a) 
   if (ray >= a.n_rays) return;  // whole groups exit together
   const int64_t s0 = a.offsets[ray], s1 = a.offsets[ray + 1];
   float carry = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, co = 0.f, cd = 0.f;
+  // mode 2: continue a ray across marching rounds - the transmittance so far is 1 - opacity[ray] (utils.py:274-281)
+  const float ray_prefix = (a.accumulate_inplace == 2 && s0 < s1) ? 1.f - a.opacity[ray] : 1.f;
   for (int64_t base = s0; base < s1; base += G) {
     const int64_t i = base + gl;
     const bool ok = i < s1;
-    float ta = 0.f, tb = 0.f, sg = 0.f, pf = 1.f;
+    float ta = 0.f, tb = 0.f, sg = 0.f, pf = ray_prefix;
     if (ok) {
       ta = a.t0[i];
       tb = a.t1[i];

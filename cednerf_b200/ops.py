@@ -420,6 +420,15 @@ def accumulate_inplace(weights, values, offsets, outputs):
          stream())
 
 
+def composite_round_(t_starts, t_ends, sigmas, rgbs, offsets, rgb, opacity, depth):
+    """One marching round of render_image_test in one launch: weights with prefix transmittance 1 - opacity[ray], then
+    rgb / opacity / depth accumulated in place (cednerf/utils.py:274-299)."""
+    t0, t1, sg, c = _f32c(t_starts), _f32c(t_ends), _f32c(sigmas), _f32c(rgbs)
+    assert rgb.is_contiguous() and opacity.is_contiguous() and depth.is_contiguous()
+    call("cednerf_composite_fwd", ptr(t0), ptr(t1), ptr(sg), ptr(c), None, ptr(offsets), None, 0, t0.numel(), rgb.shape[0],
+         None, None, None, ptr(rgb), ptr(opacity), ptr(depth), None, 2, 0.0, stream())
+
+
 class CompositeFunction(torch.autograd.Function):
     """Fused rendering(): (sigmas, rgbs) -> (colors, opacity, depth, weights, trans, alphas).
 

@@ -107,29 +107,29 @@ def render_image_test(max_samples, radiance_field, estimator, rays, near_plane=0
     far = torch.full((n,), float(far_plane), device=dev)
     t_mins, t_maxs, hits = nerfacc.ray_aabb_intersect(rays.origins, rays.viewdirs, estimator.aabbs)
     t_sorted, t_indices = ops.sort_boundaries(t_mins, t_maxs)
+    bits = nerfacc.grid.occupancy_bits(estimator.binaries)
+    res = int(estimator.binaries.shape[1])
     done = total = 0
     while done < max_samples:
-        n_alive = int(alive.sum())
+        n_alive = int(alive.sum())                     # the reference's host read (utils.py:231)
         if n_alive == 0:
             break
         k = max(min(n // n_alive, 64), min_samples)
         done += k
-        iv, sm, term = nerfacc.traverse_grids(rays.origins, rays.viewdirs, estimator.binaries, estimator.aabbs, near,
-                                              far, render_step_size, cone_angle, k, True, alive, t_sorted, t_indices,
-                                              hits)
-        t0, t1 = iv.vals[iv.is_left], iv.vals[iv.is_right]
-        ridx = sm.ray_indices[sm.is_valid]
-        if ridx.numel():
+        # traverse_grids(..., k, over_allocate=True, alive, ...) of utils.py:245-264, emitted directly in packed form:
+        # same samples, no interval flags to compact afterwards
+        mi = ops.MarchInputs(rays.origins, rays.viewdirs, bits, estimator.aabbs, res, near, far, 0.0, float("inf"),
+                             render_step_size, cone_angle, k, alive, t_sorted, t_indices, hits)
+        _, n_sm, term = mi.count()
+        starts, _, n_tot = ops.exclusive_scan(n_sm, want_packed=False)
+        n_round = int(n_tot.item())
+        if n_round:
+            ridx, t0, t1, _ = mi.fill_packed(starts, n_round)
             rgbs, sres = rgb_sigma_fn(t0, t1, ridx)
-            offsets = ops.ray_offsets(ridx, n)
-            w, _, _ = ops.RenderWeightFunction.apply(t0, t1, sres["density"].squeeze(-1), offsets, n,
-                                                     1 - opacity[ridx].squeeze(-1))
-            ops.accumulate_inplace(w, rgbs, offsets, rgb)
-            ops.accumulate_inplace(w, None, offsets, opacity)
-            ops.accumulate_inplace(w, (t0 + t1)[:, None] / 2.0, offsets, depth)
+            ops.composite_round_(t0, t1, sres["density"].squeeze(-1), rgbs, torch.cat([starts, n_tot]), rgb, opacity, depth)
         near = term
-        alive = (opacity.view(-1) <= 1 - early_stop_eps) & (sm.packed_info[:, 1] == k)
-        total += ridx.shape[0]
+        alive = (opacity.view(-1) <= 1 - early_stop_eps) & (n_sm == k)
+        total += n_round
     rgb = rgb + render_bkgd * (1.0 - opacity)
     depth = depth / opacity.clamp_min(torch.finfo(torch.float32).eps)
     return rgb.view(*shape[:-1], -1), opacity.view(*shape[:-1], -1), depth.view(*shape[:-1], -1), total

@@ -183,7 +183,10 @@ int cednerf_field_train_bwd(const int64_t* ray_indices, const float* t_starts, c
 /* ---- K4: compositing ------------------------------------------------------------------------------- */
 /* offsets[r] = first sample of ray r (ray_indices sorted); offsets[n_rays] = n_samples */
 int cednerf_ray_offsets(const int64_t* ray_indices, int64_t n_samples, int64_t n_rays, int64_t* offsets, void* stream);
-/* nerfacc.render_weight_from_density (+ accumulate_along_rays x3, depth normalise, background) —
+/* accumulate_inplace: 0 = write colours/opacity/depth (normalised depth, background blend); 1 = add the raw sums into
+ * them (accumulate_along_rays_); 2 = as 1 with prefix transmittance 1 - opacity[ray] read before the update (one marching
+ * round of render_image_test, cednerf/utils.py:274-299).
+ * nerfacc.render_weight_from_density (+ accumulate_along_rays x3, depth normalise, background) —
  * cednerf/render.py:81-87, :158-174; prefix_trans / in-place form cednerf/utils.py:274-299 */
 int cednerf_composite_fwd(const float* t_starts, const float* t_ends, const float* sigmas, const float* rgbs,
                           const float* prefix_trans, const int64_t* offsets, const float* bkgd, int bkgd_stride,
