@@ -315,6 +315,30 @@ def run_ours(args):
                               f"{len(frames)} frame(s)/GPU, frame-sharded, no collective",
                   "rays_per_s": round(rays_r / (ms_r * 1e-3), 1), "samples_per_s": round(n_render_all / (ms_r * 1e-3), 1),
                   "ms_per_frame": round(ms_r / len(frames), 3), "samples_per_ray": round(n_render_all / rays_r, 3)}
+        if rank == 0 and args.profile_steps > 0:   # per-entry-point share of one frame
+            rec_r = []
+            real_call = _lib.call
+
+            def rec_call(name, *a2):
+                s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s_.record()
+                real_call(name, *a2)
+                e_.record()
+                rec_r.append((name, s_, e_))
+
+            for m in (_lib, cb.ops):
+                m.call = rec_call
+            render_one(0)
+            torch.cuda.synchronize()
+            for m in (_lib, cb.ops):
+                m.call = real_call
+            agg_r = {}
+            for name, s_, e_ in rec_r:
+                d_ = agg_r.setdefault(name, [0.0, 0])
+                d_[0] += s_.elapsed_time(e_)
+                d_[1] += 1
+            render["breakdown_ms_per_frame"] = {k: [round(v[0], 3), v[1]] for k, v in
+                                                sorted(agg_r.items(), key=lambda kv: -kv[1][0])}
         field.train(), est.train()
 
     cpu = None

@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(128) march_kernel(MarchArgs a) {
     if (a.n_intervals) a.n_intervals[r] = 0;
     if (a.n_samples) a.n_samples[r] = 0;
     if (a.termination) a.termination[r] = near;
+    if (!FILL && a.n_runs) a.n_runs[r] = 0;
     return;
   }
   const int L = a.n_levels, m = 2 * L, res = a.res;
@@ -506,8 +507,8 @@ CEDNERF_EXPORT int cednerf_march(int fill, const float* rays_o, const float* ray
                                  uint8_t* sm_valid, float* t_starts, float* t_ends, int64_t* ray_indices,
                                  int32_t* n_intervals, int32_t* n_samples, float* termination, float* run_t,
                                  int32_t* run_n, int32_t* n_runs, int run_cap, void* stream) {
-  CEDNERF_REQUIRE(!run_t || (!fill && run_n && n_runs && run_cap > 0 && steps_limit <= 0 && step_size > 0.0f),
-                  "run recording: count pass, unlimited steps, positive step size");
+  CEDNERF_REQUIRE(!run_t || (!fill && run_n && n_runs && run_cap > 0 && step_size > 0.0f),
+                  "run recording: count pass, positive step size");
   CEDNERF_REQUIRE(n_rays >= 0 && n_levels >= 1 && n_levels <= MARCH_MAX_LEVELS && resolution >= 1,
                   "bad sizes (levels <= 8)");
   CEDNERF_REQUIRE((t_sorted == nullptr) == (t_indices == nullptr) && (t_sorted == nullptr) == (hits == nullptr),

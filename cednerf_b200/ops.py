@@ -106,7 +106,7 @@ class MarchInputs:
         n_sm = torch.empty(self.n, dtype=I32, device=dev)
         term = torch.empty(self.n, device=dev)
         self.runs = None
-        if record_runs and self.limit <= 0 and self.step > 0:
+        if record_runs and self.step > 0:
             self.runs = (torch.empty(self.n, self.RUN_CAP, device=dev), torch.empty(self.n, self.RUN_CAP, dtype=I32, device=dev),
                          torch.empty(self.n, dtype=I32, device=dev))
         rt, rn, nr = self.runs if self.runs is not None else (None, None, None)
@@ -125,7 +125,8 @@ class MarchInputs:
         rt, rn, nr = self.runs
         call("cednerf_march_fill_runs", self.n, ptr(sm_starts), ptr(rt), ptr(rn), ptr(nr), self.RUN_CAP, self.step,
              self.cone, ptr(t0), ptr(t1), ptr(ridx), ptr(overflow), stream())
-        user_mask, self.mask = self.mask, overflow  # (the packed two-pass path never carries a user mask)
+        # overflow is 0 for rays the caller masked out (their run count is 0), so it can stand in as the ray mask
+        user_mask, self.mask = self.mask, overflow
         call("cednerf_march", *self._common(1), None, ptr(sm_starts), None, None, None, None, None, None, None,
              ptr(t0), ptr(t1), ptr(ridx), None, None, None, None, None, None, 0, stream())
         self.mask = user_mask

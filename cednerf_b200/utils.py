@@ -120,11 +120,14 @@ def render_image_test(max_samples, radiance_field, estimator, rays, near_plane=0
         # same samples, no interval flags to compact afterwards
         mi = ops.MarchInputs(rays.origins, rays.viewdirs, bits, estimator.aabbs, res, near, far, 0.0, float("inf"),
                              render_step_size, cone_angle, k, alive, t_sorted, t_indices, hits)
-        _, n_sm, term = mi.count()
+        _, n_sm, term = mi.count(record_runs=True)
         starts, _, n_tot = ops.exclusive_scan(n_sm, want_packed=False)
         n_round = int(n_tot.item())
         if n_round:
-            ridx, t0, t1, _ = mi.fill_packed(starts, n_round)
+            if mi.runs is not None:
+                ridx, t0, t1 = mi.fill_packed_from_runs(starts, n_round)
+            else:
+                ridx, t0, t1, _ = mi.fill_packed(starts, n_round)
             rgbs, sres = rgb_sigma_fn(t0, t1, ridx)
             ops.composite_round_(t0, t1, sres["density"].squeeze(-1), rgbs, torch.cat([starts, n_tot]), rgb, opacity, depth)
         near = term
