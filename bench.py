@@ -35,7 +35,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=2 ** 18, help="rays per rank per step")
-    ap.add_argument("--cpu-rays", type=int, default=2048, help="rays per step of the bounded CPU sample")
+    ap.add_argument("--cpu-rays", type=int, default=4096, help="rays per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=3, help="instrumented steps for the per-kernel breakdown")
     ap.add_argument("--render-frames", type=int, default=2, help="full frames per rank for the render leg (0 = skip)")
@@ -270,8 +270,13 @@ def run_ours(args):
         top = max((n for n in agg if agg[n]["has_bytes"]), key=lambda n: agg[n]["ms"])
         d = agg[top]
         achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+        traffic = None  # dram__bytes_read + dram__bytes_write per launch of that kernel, from the committed ncu capture
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get(top, {}).get("bytes_per_launch")
+        except (OSError, ValueError):
+            pass
         roof = {"kernel": top, "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
-                "frac": round(achieved / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(achieved / hbm_peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "avg_launch_ms": round(d["ms"] / d["launches"], 4), "bytes_per_launch": d["bytes"] // d["launches"],
                 "share_of_step": round(d["ms"] / args.profile_steps / prof_ms, 3)}
         breakdown["_ours_total_ms"] = round(sum(v["ms"] for v in agg.values()) / args.profile_steps, 3)
@@ -343,7 +348,7 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = run_reference_steps(args.cpu_rays, steps=2, warmup=1)
+        cpu = run_reference_steps(args.cpu_rays, steps=3, warmup=1)
 
     if rank == 0:
         rays_all = args.rays * world
