@@ -502,9 +502,10 @@ __global__ void __launch_bounds__(MLP_TILE) field_bwd_kernel(TrainArgs a) {
     const int rows_valid = (int)((n - row0) < MLP_TILE ? (n - row0) : MLP_TILE);
     const int64_t s = row0 + tid;
     const bool ok = tid < rows_valid;
-    make_dout<NET>(a, sl, wl, gbuf[0], tid, s, ok);
-    if (L > 1) load_tile(ibuf[0], hidden + ((int64_t)(L - 2) * n + row0) * 64, 64, rows_valid);
+    if (L > 1) load_tile_async(ibuf[0], hidden + ((int64_t)(L - 2) * n + row0) * 64, 64, rows_valid);
     else make_input<NET>(a, sl, ibuf[0], tid, s, ok);
+    make_dout<NET>(a, sl, wl, gbuf[0], tid, s, ok);
+    cp_async_wait_all();
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -531,7 +532,7 @@ __global__ void __launch_bounds__(MLP_TILE) field_bwd_kernel(TrainArgs a) {
         umma_commit(&bar);
       }
       if (l > 0) {
-        if (l > 1) load_tile(ibuf[cur ^ 1], hidden + ((int64_t)(l - 2) * n + row0) * 64, 64, rows_valid);
+        if (l > 1) load_tile_async(ibuf[cur ^ 1], hidden + ((int64_t)(l - 2) * n + row0) * 64, 64, rows_valid);
         else make_input<NET>(a, sl, ibuf[cur ^ 1], tid, s, ok);
       }
       mbar_wait(&bar, phase);
@@ -599,6 +600,7 @@ __global__ void __launch_bounds__(MLP_TILE) field_bwd_kernel(TrainArgs a) {
           }
         }
       }
+      cp_async_wait_all();  // the prefetched next-layer tile has landed
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();

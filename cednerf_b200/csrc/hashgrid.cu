@@ -193,17 +193,16 @@ hashgrid_bwd_table_kernel(const float* __restrict__ x, int x_stride, int64_t n, 
   const uint32_t px = __shfl_up_sync(0xffffffffu, c.g[0], 1), py = __shfl_up_sync(0xffffffffu, c.g[1], 1),
                  pz = __shfl_up_sync(0xffffffffu, c.g[2], 1);
   const bool head = lane == 0 || px != c.g[0] || py != c.g[1] || pz != c.g[2];
-  int run_start = head ? lane : 0;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) run_start = max(run_start, __shfl_up_sync(0xffffffffu, run_start, o));
   const unsigned heads = __ballot_sync(0xffffffffu, head);
+  const int run_start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));  // highest head at or below this lane
   const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+  // scan depth follows the longest run in the warp: 0 steps at fine levels (every lane its own run), 5 at the coarsest
+  const int max_len = __reduce_max_sync(0xffffffffu, lane - run_start + 1);
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const float w = corner_weight(c, k);
     float v0 = w * d0, v1 = w * d1;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
+    for (int o = 1; o < max_len; o <<= 1) {
       const float u0 = __shfl_up_sync(0xffffffffu, v0, o), u1 = __shfl_up_sync(0xffffffffu, v1, o);
       if (lane - o >= run_start) {
         v0 += u0;

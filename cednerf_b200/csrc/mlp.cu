@@ -170,9 +170,10 @@ __global__ void __launch_bounds__(MLP_TILE) mlp_bwd_kernel(MlpBwdArgs a) {
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
     const int64_t row0 = tile * MLP_TILE;
     const int rows_valid = (int)((a.n - row0) < MLP_TILE ? (a.n - row0) : MLP_TILE);
-    load_tile(gbuf[0], a.d_out + row0 * d.dim_out[L - 1], d.dim_out[L - 1], rows_valid);
-    if (L > 1) load_tile(ibuf[0], a.hidden + ((int64_t)(L - 2) * a.n + row0) * 64, 64, rows_valid);
-    else load_tile(ibuf[0], a.x + row0 * d.dim_in[0], d.dim_in[0], rows_valid);
+    load_tile_async(gbuf[0], a.d_out + row0 * d.dim_out[L - 1], d.dim_out[L - 1], rows_valid);
+    if (L > 1) load_tile_async(ibuf[0], a.hidden + ((int64_t)(L - 2) * a.n + row0) * 64, 64, rows_valid);
+    else load_tile_async(ibuf[0], a.x + row0 * d.dim_in[0], d.dim_in[0], rows_valid);
+    cp_async_wait_all();
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -201,8 +202,8 @@ __global__ void __launch_bounds__(MLP_TILE) mlp_bwd_kernel(MlpBwdArgs a) {
       }
       // prefetch the next (earlier) layer's input tile while the tensor core runs
       if (l > 0) {
-        if (l > 1) load_tile(ibuf[cur ^ 1], a.hidden + ((int64_t)(l - 2) * a.n + row0) * 64, 64, rows_valid);
-        else load_tile(ibuf[cur ^ 1], a.x + row0 * d.dim_in[0], d.dim_in[0], rows_valid);
+        if (l > 1) load_tile_async(ibuf[cur ^ 1], a.hidden + ((int64_t)(l - 2) * a.n + row0) * 64, 64, rows_valid);
+        else load_tile_async(ibuf[cur ^ 1], a.x + row0 * d.dim_in[0], d.dim_in[0], rows_valid);
       }
       mbar_wait(&bar, phase);
       phase ^= 1;
@@ -257,6 +258,7 @@ __global__ void __launch_bounds__(MLP_TILE) mlp_bwd_kernel(MlpBwdArgs a) {
           }
         }
       }
+      cp_async_wait_all();  // the prefetched next-layer tile has landed
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();

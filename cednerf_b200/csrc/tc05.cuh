@@ -103,6 +103,22 @@ __device__ __forceinline__ void load_tile(uint8_t* tile, const __half* __restric
     *reinterpret_cast<uint4*>(tile + swz(r, c)) = v;
   }
 }
+// same as load_tile but with cp.async (LDGSTS): the copies are in flight while the thread goes on to wait for the tensor
+// core and run its epilogue; cp_async_wait_all() + fence.proxy.async must precede the MMA that reads the tile
+__device__ __forceinline__ void load_tile_async(uint8_t* tile, const __half* __restrict__ g, int width, int rows_valid) {
+  const int cpr = width >> 3;
+  const int total = MLP_TILE * cpr;
+  const uint4* src = reinterpret_cast<const uint4*>(g);
+  for (int q = threadIdx.x; q < total; q += blockDim.x) {
+    const int r = q / cpr, c = q - r * cpr;
+    const uint32_t dst = smem_u32(tile + swz(r, c));
+    const int bytes = r < rows_valid ? 16 : 0;  // src-size 0: the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src + (r < rows_valid ? q : 0)), "r"(bytes)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // swizzled tile -> global [rows_valid, width] fp16 row-major (coalesced 16-byte chunks)
 __device__ __forceinline__ void store_tile(const uint8_t* tile, __half* __restrict__ g, int width, int rows_valid) {
   const int cpr = width >> 3;
