@@ -83,7 +83,8 @@ class OccGridEstimator(torch.nn.Module):
                 assert sigmas.shape == t0.shape, f"sigmas must have shape {tuple(t0.shape)}"
                 keep = ops.visibility_mask(t0, t1, sigmas, ops.offsets_from_packed(packed), rays_o.shape[0],
                                            early_stop_eps, alpha_thre)
-                ridx, t0, t1 = ridx[keep], t0[keep], t1[keep]
+                sel = torch.nonzero(keep).squeeze(-1)  # one compaction (one host read), three gathers
+                ridx, t0, t1 = ridx[sel], t0[sel], t1[sel]
         return ridx, t0, t1
 
     @torch.no_grad()
