@@ -198,21 +198,38 @@ hashgrid_bwd_table_kernel(const float* __restrict__ x, int x_stride, int64_t n, 
   const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
   // scan depth follows the longest run in the warp: 0 steps at fine levels (every lane its own run), 5 at the coarsest
   const int max_len = __reduce_max_sync(0xffffffffu, lane - run_start + 1);
+  // corners come in x-pairs (k, k+1): when the two table entries form an aligned 16-byte pair (dense levels: even
+  // index; hashed levels: even x, because the x term of the hash is x itself) one 16-byte reduction carries both
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const float w = corner_weight(c, k);
-    float v0 = w * d0, v1 = w * d1;
+  for (int kp = 0; kp < 4; ++kp) {
+    float v[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float w = corner_weight(c, 2 * kp + h);
+      v[2 * h] = w * d0;
+      v[2 * h + 1] = w * d1;
+    }
     for (int o = 1; o < max_len; o <<= 1) {
-      const float u0 = __shfl_up_sync(0xffffffffu, v0, o), u1 = __shfl_up_sync(0xffffffffu, v1, o);
-      if (lane - o >= run_start) {
-        v0 += u0;
-        v1 += u1;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float u = __shfl_up_sync(0xffffffffu, v[j], o);
+        if (lane - o >= run_start) v[j] += u;
       }
     }
-    if (tail && (v0 != 0.f || v1 != 0.f)) {
-      const uint32_t idx =
-          off + corner_index(c.g[0] + (k & 1), c.g[1] + ((k >> 1) & 1), c.g[2] + ((k >> 2) & 1), res, size, hashed);
-      atomicAdd(reinterpret_cast<float2*>(g_table) + idx, make_float2(v0, v1));
+    if (tail) {
+      const uint32_t gy = c.g[1] + (kp & 1), gz = c.g[2] + (kp >> 1);
+      const uint32_t i0 = off + corner_index(c.g[0], gy, gz, res, size, hashed);
+      const uint32_t i1 = off + corner_index(c.g[0] + 1, gy, gz, res, size, hashed);
+      float2* t2 = reinterpret_cast<float2*>(g_table);
+      if ((i0 ^ i1) == 1u) {
+        const bool even = (i0 & 1u) == 0u;
+        const float4 val = even ? make_float4(v[0], v[1], v[2], v[3]) : make_float4(v[2], v[3], v[0], v[1]);
+        if (val.x != 0.f || val.y != 0.f || val.z != 0.f || val.w != 0.f)
+          atomicAdd(reinterpret_cast<float4*>(t2 + (i0 & ~1u)), val);
+      } else {
+        if (v[0] != 0.f || v[1] != 0.f) atomicAdd(t2 + i0, make_float2(v[0], v[1]));
+        if (v[2] != 0.f || v[3] != 0.f) atomicAdd(t2 + i1, make_float2(v[2], v[3]));
+      }
     }
   }
 }
