@@ -143,30 +143,22 @@ __global__ void __launch_bounds__(384, 2) field_fwd_kernel(FieldFwdArgs a) {
         *reinterpret_cast<uint32_t*>(abuf0 + swz(gtid, w >> 2) + ((w & 3) << 2)) = v;
       };
       const int k2 = d.f2.dim_in[0];
+      // runtime loops over level groups (not unrolled: the fully unrolled 16-level body was 340 KB of SASS and the
+      // kernel spent 18 % of its stall samples waiting for instructions)
       if ((L & 3) == 0) {
-#pragma unroll
-        for (int l0 = 0; l0 < 16; l0 += 4)
-          if (l0 < L) {  // 32 gathers in flight per thread; the four levels fill exactly one 16-byte chunk of the row
-            uint32_t f4w[4];
-            hash_levels<4>(xn, a.table, d.levels, 0, f4w, l0);
-            *reinterpret_cast<uint4*>(abuf0 + swz(gtid, l0 >> 2)) = make_uint4(f4w[0], f4w[1], f4w[2], f4w[3]);
-          }
-      } else if ((L & 1) == 0) {
-#pragma unroll
-        for (int l0 = 0; l0 < 16; l0 += 2)
-          if (l0 < L) {
-            uint32_t f2w[2];
-            hash_levels<2>(xn, a.table, d.levels, 0, f2w, l0);
-            *reinterpret_cast<uint2*>(abuf0 + swz(gtid, l0 >> 2) + ((l0 & 3) << 2)) = make_uint2(f2w[0], f2w[1]);
-          }
+#pragma unroll 1
+        for (int l0 = 0; l0 < L; l0 += 4) {  // 32 gathers in flight per thread; four levels = one 16-byte chunk of the row
+          uint32_t f4w[4];
+          hash_levels<4>(xn, a.table, d.levels, 0, f4w, l0);
+          *reinterpret_cast<uint4*>(abuf0 + swz(gtid, l0 >> 2)) = make_uint4(f4w[0], f4w[1], f4w[2], f4w[3]);
+        }
       } else {
-#pragma unroll
-        for (int l0 = 0; l0 < 16; ++l0)
-          if (l0 < L) {
-            uint32_t f1w[1];
-            hash_levels<1>(xn, a.table, d.levels, 0, f1w, l0);
-            put_word(l0, f1w[0]);
-          }
+#pragma unroll 1
+        for (int l0 = 0; l0 < L; ++l0) {
+          uint32_t f1w[1];
+          hash_levels<1>(xn, a.table, d.levels, 0, f1w, l0);
+          put_word(l0, f1w[0]);
+        }
       }
       if (d.time_mode) time_embedding(tv, mvnorm, d.time_mode, temb);  // after the gathers: keeps registers free
       int w = L;

@@ -91,8 +91,7 @@ __global__ void __launch_bounds__(MLP_TILE) mlp_fwd_kernel(MlpFwdArgs a) {
           tmem_ld_wait();
           uint32_t p[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            p[j] = pack_h2(fmaxf(__uint_as_float(r[2 * j]), 0.f), fmaxf(__uint_as_float(r[2 * j + 1]), 0.f));
+          for (int j = 0; j < 8; ++j) p[j] = pack_relu_h2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
           *reinterpret_cast<uint4*>(nxt + swz(tid, 2 * cb)) = make_uint4(p[0], p[1], p[2], p[3]);
           *reinterpret_cast<uint4*>(nxt + swz(tid, 2 * cb + 1)) = make_uint4(p[4], p[5], p[6], p[7]);
         }

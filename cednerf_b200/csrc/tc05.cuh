@@ -130,6 +130,13 @@ __device__ __forceinline__ void store_tile(const uint8_t* tile, __half* __restri
   }
 }
 
+// ReLU fused into the fp32 -> fp16x2 conversion (cvt.rn.relu): one instruction per pair of activations
+__device__ __forceinline__ uint32_t pack_relu_h2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
