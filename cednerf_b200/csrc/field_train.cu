@@ -181,37 +181,37 @@ __global__ void __launch_bounds__(256, 2) field_train_fwd_kernel(TrainArgs a) {
     // ---- density net input: [hash 2L | time 9 | 1.0 ...] ---------------------------------------------------------
     float temb[9];
     {
-      uint32_t feat[16];
-#pragma unroll
-      for (int l = 0; l < 16; ++l) feat[l] = one2;
-      if ((L & 1) == 0) {
-#pragma unroll
-        for (int l0 = 0; l0 < 16; l0 += 2)
-          if (l0 < L) hash_levels<2>(xn, a.table, d.levels, l0, feat);
+      auto put_word = [&](int w, uint32_t v) {
+        *reinterpret_cast<uint32_t*>(abuf + swz(gtid, w >> 2) + ((w & 3) << 2)) = v;
+      };
+      if ((L & 3) == 0) {
+#pragma unroll 1
+        for (int l0 = 0; l0 < L; l0 += 4) {
+          uint32_t f4w[4];
+          hash_levels<4>(xn, a.table, d.levels, 0, f4w, l0);
+          *reinterpret_cast<uint4*>(abuf + swz(gtid, l0 >> 2)) = make_uint4(f4w[0], f4w[1], f4w[2], f4w[3]);
+        }
       } else {
-#pragma unroll
-        for (int l0 = 0; l0 < 16; ++l0)
-          if (l0 < L) hash_levels<1>(xn, a.table, d.levels, l0, feat);
+#pragma unroll 1
+        for (int l0 = 0; l0 < L; ++l0) {
+          uint32_t f1w[1];
+          hash_levels<1>(xn, a.table, d.levels, 0, f1w, l0);
+          put_word(l0, f1w[0]);
+        }
       }
       if (d.time_mode) time_embedding(tv, mvnorm, d.time_mode, temb);
-      uint32_t row[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) row[j] = one2;
-#pragma unroll
-      for (int l = 0; l < 16; ++l)
-        if (l < L) row[l] = feat[l];
+      int w = L;
       if (d.time_mode && d.time_before_sigma) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) row[L + j] = pack_h2(temb[2 * j], temb[2 * j + 1]);
-        row[L + 4] = pack_h2(temb[8], 1.f);
+        for (int j = 0; j < 4; ++j) put_word(L + j, pack_h2(temb[2 * j], temb[2 * j + 1]));
+        put_word(L + 4, pack_h2(temb[8], 1.f));
+        w = L + 5;
       }
-#pragma unroll
-      for (int c = 0; c < 8; ++c)
-        if (c * 8 < k2) {
-          const uint4 v = make_uint4(row[4 * c], row[4 * c + 1], row[4 * c + 2], row[4 * c + 3]);
-          *reinterpret_cast<uint4*>(abuf + swz(gtid, c)) = v;
-          if (ok) reinterpret_cast<uint4*>(a.saved + sl.in2 + s * k2 * 2)[c] = v;
-        }
+      for (; 2 * w < k2; ++w) put_word(w, one2);
+      if (ok) {  // keep this thread's operand row for the backward pass (weight gradient of the first density layer)
+        uint4* dst = reinterpret_cast<uint4*>(a.saved + sl.in2 + s * k2 * 2);
+        for (int c = 0; c * 8 < k2; ++c) dst[c] = *reinterpret_cast<const uint4*>(abuf + swz(gtid, c));
+      }
     }
     fence_proxy_async();
     tc_fence_before();
