@@ -99,20 +99,7 @@ __global__ void __launch_bounds__(384, 2) field_fwd_kernel(FieldFwdArgs a) {
       }
     }
     // ---- deformation net input: Frequency(x, y, z, t), 4 octaves (model.py:205-213) ---------------------------
-    {
-      const float in4[4] = {x[0], x[1], x[2], tv};
-#pragma unroll
-      for (int dim = 0; dim < 4; ++dim) {
-        uint32_t p[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float sn, cs;  // sin(pi ph) and sin(pi (ph + 1/2)) = cos(pi ph): one range reduction for the pair
-          sincospif(in4[dim] * (float)(1 << k), &sn, &cs);
-          p[k] = pack_h2(sn, cs);
-        }
-        *reinterpret_cast<uint4*>(abuf0 + swz(gtid, dim)) = make_uint4(p[0], p[1], p[2], p[3]);
-      }
-    }
+    frequency_row(abuf0, gtid, x[0], x[1], x[2], tv);
     fence_proxy_async();
     tc_fence_before();
     group_sync(group);

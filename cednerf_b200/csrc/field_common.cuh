@@ -87,11 +87,15 @@ __device__ __forceinline__ void time_embedding(float tv, float mvnorm, int mode,
   }
 }
 
-// 2*L hash features of one point, packed as L half2 words (numerics of hashgrid_fwd_kernel)
+// 2*L hash features of one point, packed as L half2 words.  Cell, corner indices and weights are exactly those of
+// hashgrid_fwd_kernel; the blend accumulates with fused multiply-adds (one rounding per term instead of two), so a
+// feature can differ from the stand-alone encoder by one fp16 ulp when the fp32 sum sits on a rounding boundary.
+// Index arithmetic is arranged for few instructions per gather: the level's table base is formed once, hashed levels
+// mask the six per-axis terms first (one LOP3 per corner), dense levels whose eight corners are all in range (every
+// point inside the box) address them as base + {0, 1, res, res + 1, ...}.
 template <int LG>
 __device__ __forceinline__ void hash_levels(const float* xn, const __half* __restrict__ table, const CednerfGridLevels& lv,
                                             int l0, uint32_t* feat, int level_base = 0) {
-  const __half2* t2 = reinterpret_cast<const __half2*>(table);
   float frac[LG][3];
   __half2 v[LG][8];
 #pragma unroll
@@ -99,10 +103,32 @@ __device__ __forceinline__ void hash_levels(const float* xn, const __half* __res
     const int l = level_base + l0 + a;
     const Cell c = locate(xn, lv.scale[l]);
     frac[a][0] = c.f[0], frac[a][1] = c.f[1], frac[a][2] = c.f[2];
-    uint32_t idx[8];
-    cell_indices(c.g, lv.res[l], lv.size[l], lv.offset[l], lv.hashed[l] != 0, idx);
+    const uint32_t res = lv.res[l], size = lv.size[l];
+    const __half2* tl = reinterpret_cast<const __half2*>(table) + lv.offset[l];
+    if (lv.hashed[l]) {  // power-of-two table: (x ^ y P1 ^ z P2) & mask == (x & mask) ^ (y P1 & mask) ^ (z P2 & mask)
+      const uint32_t mask = size - 1u;
+      const uint32_t y0 = c.g[1] * 2654435761u, z0 = c.g[2] * 805459861u;
+      const uint32_t hx[2] = {c.g[0] & mask, (c.g[0] + 1u) & mask};
+      const uint32_t hy[2] = {y0 & mask, (y0 + 2654435761u) & mask};
+      const uint32_t hz[2] = {z0 & mask, (z0 + 805459861u) & mask};
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[a][k] = __ldg(t2 + idx[k]);
+      for (int k = 0; k < 8; ++k) v[a][k] = __ldg(tl + (hx[k & 1] ^ hy[(k >> 1) & 1] ^ hz[k >> 2]));
+    } else {
+      const uint32_t r2 = res * res;
+      const uint32_t base = c.g[0] + c.g[1] * res + c.g[2] * r2;
+      if (base < size - (1u + res + r2)) {  // all eight corners in range: no wrap
+        const __half2* p = tl + base;
+        v[a][0] = __ldg(p), v[a][1] = __ldg(p + 1);
+        v[a][2] = __ldg(p + res), v[a][3] = __ldg(p + res + 1);
+        v[a][4] = __ldg(p + r2), v[a][5] = __ldg(p + r2 + 1);
+        v[a][6] = __ldg(p + r2 + res), v[a][7] = __ldg(p + r2 + res + 1);
+      } else {  // points outside the box (masked by the selector afterwards): the reference's wrap
+        uint32_t idx[8];
+        cell_indices(c.g, res, size, 0u, false, idx);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[a][k] = __ldg(tl + idx[k]);
+      }
+    }
   }
 #pragma unroll
   for (int a = 0; a < LG; ++a) {  // ... then the weights (recomputed from 3 fractions) and the blend
@@ -112,13 +138,22 @@ __device__ __forceinline__ void hash_levels(const float* xn, const __half* __res
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float2 f = __half22float2(v[a][k]);
-      a0 = __fadd_rn(a0, __fmul_rn(w[k], f.x));
-      a1 = __fadd_rn(a1, __fmul_rn(w[k], f.y));
+      a0 = fmaf(w[k], f.x, a0);
+      a1 = fmaf(w[k], f.y, a1);
     }
     feat[l0 + a] = pack_h2(a0, a1);
   }
 }
 
+// sin(pi y), cos(pi y) on the special-function unit: y - 2 rint(y / 2) is exact in fp32 and lies in [-1, 1], where
+// MUFU.SIN / MUFU.COS are accurate to 2^-21 absolute (tcnn's Frequency encoding uses __sinf the same way); the result is
+// rounded to fp16 (half ulp 2^-12) right after.
+__device__ __forceinline__ void sincospi_fast(float y, float& sn, float& cs) {
+  const float r = fmaf(-2.f, rintf(0.5f * y), y);
+  const float a = r * 3.14159265358979323846f;
+  sn = __sinf(a);
+  cs = __cosf(a);
+}
 
 // position / time of packed sample s (cednerf/utils.py:74-104): x = o + (d * (t0 + t1)) / 2, individually rounded
 __device__ __forceinline__ void packed_sample(const int64_t* __restrict__ ridx, const float* __restrict__ t0,
@@ -142,7 +177,7 @@ __device__ __forceinline__ void frequency_row(uint8_t* tile, int row, float v0, 
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float sn, cs;  // sin(pi ph) and sin(pi (ph + 1/2)) = cos(pi ph): one range reduction for the pair
-      sincospif(in4[dim] * (float)(1 << k), &sn, &cs);
+      sincospi_fast(in4[dim] * (float)(1 << k), sn, cs);
       p[k] = pack_h2(sn, cs);
     }
     *reinterpret_cast<uint4*>(tile + swz(row, dim)) = make_uint4(p[0], p[1], p[2], p[3]);
