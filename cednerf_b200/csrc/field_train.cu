@@ -95,7 +95,7 @@ __device__ __forceinline__ void load_off(const TrainArgs& a, const SavedLayout& 
 }
 
 // =============================================================================================== forward
-__global__ void __launch_bounds__(256, 2) field_train_fwd_kernel(TrainArgs a) {
+__global__ void __launch_bounds__(768, 1) field_train_fwd_kernel(TrainArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const CednerfFieldDesc& d = a.d;
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(256, 2) field_train_fwd_kernel(TrainArgs a) {
   uint8_t* abuf = reinterpret_cast<uint8_t*>(
                       (reinterpret_cast<uintptr_t>(w4 + (has4 ? d.f4.image_bytes : 0)) + 1023) & ~(uintptr_t)1023) +
                   (size_t)group * MLP_TILE_BYTES;
-  __shared__ uint64_t bars[4];
+  __shared__ uint64_t bars[8];
   __shared__ uint32_t tmem_base_s;
   uint64_t* bar = &bars[group];
   {
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256, 2) field_train_fwd_kernel(TrainArgs a) {
       for (int q = tid; q < bytes[k] / 16; q += blockDim.x)
         reinterpret_cast<uint4*>(dst[k])[q] = __ldg(reinterpret_cast<const uint4*>(src[k]) + q);
   }
-  const uint32_t tmem_cols = n_groups <= 1 ? 64 : (n_groups == 2 ? 128 : 256);
+  const uint32_t tmem_cols = n_groups <= 1 ? 64 : (n_groups == 2 ? 128 : (n_groups <= 4 ? 256 : 512));
   if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
   if (gtid == 0) mbar_init(bar, 1);
   if (tid == 0) fence_barrier_init();
@@ -702,13 +702,13 @@ CEDNERF_EXPORT int cednerf_field_train_fwd(const int64_t* ray_indices, const flo
                   "bad arguments");
   CEDNERF_REQUIRE(desc->f4.n_layers == 0 || image_predict, "feature predictor image missing");
   if (n == 0) return 0;
-  const int n_groups = 2;
+  const int n_groups = 6;  // one CTA per SM: six 128-sample tiles in flight (24 warps) share one copy of the weight images
   const int smem = desc->f1.image_bytes + desc->f2.image_bytes + desc->f3.image_bytes +
                    (desc->f4.n_layers > 0 ? desc->f4.image_bytes : 0) + n_groups * MLP_TILE_BYTES + 2048;
-  CEDNERF_REQUIRE(smem <= 112 * 1024, "networks too large for the fused kernel");
+  CEDNERF_REQUIRE(smem <= 224 * 1024, "networks too large for the fused kernel");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(field_train_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(field_train_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) {
       cednerf_set_error("cednerf_field_train_fwd: %s", cudaGetErrorString(e));
       return (int)e;
@@ -726,7 +726,7 @@ CEDNERF_EXPORT int cednerf_field_train_fwd(const int64_t* ray_indices, const flo
   a.d = *desc;
   const int64_t tiles = (n + MLP_TILE - 1) / MLP_TILE;
   const int64_t ctas = (tiles + n_groups - 1) / n_groups;
-  const int64_t max_ctas = (int64_t)cednerf_num_sms() * 2;
+  const int64_t max_ctas = (int64_t)cednerf_num_sms();
   field_train_fwd_kernel<<<(unsigned)(ctas < max_ctas ? ctas : max_ctas), n_groups * MLP_TILE, smem, (cudaStream_t)stream>>>(a);
   return cednerf_check_launch("cednerf_field_train_fwd");
 }
