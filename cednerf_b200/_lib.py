@@ -36,7 +36,19 @@ class FieldDesc(ctypes.Structure):
                 ("f3", MlpDesc), ("f4", MlpDesc), ("levels", GridLevels)]
 
 
-# p = pointer, i = int, l = int64, f = float, G = GridLevels*, M = MlpDesc*, F = FieldDesc*
+OPT_MAX_TENSORS = 8
+
+
+class AdamTensors(ctypes.Structure):
+    _fields_ = [("n_tensors", ctypes.c_int), ("p", ctypes.c_void_p * OPT_MAX_TENSORS),
+                ("g", ctypes.c_void_p * OPT_MAX_TENSORS), ("m", ctypes.c_void_p * OPT_MAX_TENSORS),
+                ("v", ctypes.c_void_p * OPT_MAX_TENSORS), ("p16", ctypes.c_void_p * OPT_MAX_TENSORS),
+                ("n", ctypes.c_int64 * OPT_MAX_TENSORS), ("lr", ctypes.c_float * OPT_MAX_TENSORS),
+                ("weight_decay", ctypes.c_float * OPT_MAX_TENSORS),
+                ("chunk_begin", ctypes.c_int64 * (OPT_MAX_TENSORS + 1))]
+
+
+# p = pointer, i = int, l = int64, f = float, A = AdamTensors*, G = GridLevels*, M = MlpDesc*, F = FieldDesc*
 _SIGNATURES = {
     "cednerf_ray_aabb_intersect": "pplpifffpppp",
     "cednerf_sort_boundaries": "pplippp",
@@ -67,9 +79,12 @@ _SIGNATURES = {
     "cednerf_visibility_mask": "ppppllffpp",
     "cednerf_accumulate_fwd": "ppipllpip",
     "cednerf_accumulate_bwd": "ppiplpppp",
+    "cednerf_nonfinite_check": "App",
+    "cednerf_adam_step": "Apippfffip",
 }
 _CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_int64, "f": ctypes.c_float,
-       "G": ctypes.POINTER(GridLevels), "M": ctypes.POINTER(MlpDesc), "F": ctypes.POINTER(FieldDesc)}
+       "G": ctypes.POINTER(GridLevels), "M": ctypes.POINTER(MlpDesc), "F": ctypes.POINTER(FieldDesc),
+       "A": ctypes.POINTER(AdamTensors)}
 
 _lib = None
 

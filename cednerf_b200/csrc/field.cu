@@ -12,6 +12,7 @@
 // weight images resident in shared memory, the accumulator comes back from TMEM with tcgen05.ld.
 // Adjacent threads hold adjacent samples of the same ray, so one gather instruction touches one level for 32
 // neighbouring samples: coarse and middle levels coalesce into few sectors, L1/L2 serve the reuse.
+#include <cstdlib>
 #include "field_common.cuh"
 
 namespace {
@@ -36,9 +37,9 @@ struct FieldFwdArgs {
   CednerfFieldDesc d;
 };
 
-#define FIELD_MAX_GROUPS 4
+#define FIELD_MAX_GROUPS 8
 
-__global__ void __launch_bounds__(384, 2) field_fwd_kernel(FieldFwdArgs a) {
+__global__ void __launch_bounds__(1024, 1) field_fwd_kernel(FieldFwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const CednerfFieldDesc& d = a.d;
@@ -62,7 +63,7 @@ __global__ void __launch_bounds__(384, 2) field_fwd_kernel(FieldFwdArgs a) {
   if (want_rgb)
     for (int q = tid; q < d.f3.image_bytes / 16; q += blockDim.x)
       reinterpret_cast<uint4*>(w3)[q] = __ldg(reinterpret_cast<const uint4*>(a.img3) + q);
-  const uint32_t tmem_cols = n_groups <= 1 ? 64 : (n_groups == 2 ? 128 : 256);
+  const uint32_t tmem_cols = n_groups <= 1 ? 64 : (n_groups == 2 ? 128 : (n_groups <= 4 ? 256 : 512));
   if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
   if (gtid == 0) mbar_init(bar, 1);
   if (tid == 0) fence_barrier_init();
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(384, 2) field_fwd_kernel(FieldFwdArgs a) {
   const int L = d.levels.n_levels;
   const uint32_t one2 = 0x3C003C00u;  // half2(1, 1): tcnn's input padding value
 
-  for (int64_t tile = (int64_t)blockIdx.x * n_groups + group; tile < n_tiles; tile += (int64_t)gridDim.x * n_groups) {
+  for (int64_t tile = blockIdx.x + (int64_t)gridDim.x * group; tile < n_tiles; tile += (int64_t)gridDim.x * n_groups) {
     const int64_t s = tile * MLP_TILE + gtid;
     const bool ok = s < a.n;
     // ---- the sample: position, time, direction (cednerf/utils.py:74-104) -------------------------------------
@@ -134,9 +135,10 @@ __global__ void __launch_bounds__(384, 2) field_fwd_kernel(FieldFwdArgs a) {
       // kernel spent 18 % of its stall samples waiting for instructions)
       if ((L & 3) == 0) {
 #pragma unroll 1
-        for (int l0 = 0; l0 < L; l0 += 4) {  // 32 gathers in flight per thread; four levels = one 16-byte chunk of the row
+        for (int l0 = 0; l0 < L; l0 += 4) {  // 16 gathers in flight per thread; four levels = one 16-byte chunk of the row
           uint32_t f4w[4];
-          hash_levels<4>(xn, a.table, d.levels, 0, f4w, l0);
+          hash_levels<2>(xn, a.table, d.levels, 0, f4w, l0);
+          hash_levels<2>(xn, a.table, d.levels, 0, f4w + 2, l0 + 2);
           *reinterpret_cast<uint4*>(abuf0 + swz(gtid, l0 >> 2)) = make_uint4(f4w[0], f4w[1], f4w[2], f4w[3]);
         }
       } else {
@@ -256,25 +258,31 @@ CEDNERF_EXPORT int cednerf_field_fwd(const int64_t* ray_indices, const float* t_
   CEDNERF_REQUIRE((ray_indices && t_starts && t_ends && rays_o && rays_d) || (!ray_indices && x), "need packed samples or points");
   CEDNERF_REQUIRE(!rgb || ray_indices || dirs, "colour needs directions");
   if (n == 0) return 0;
-  const int n_groups = 3;  // 3 tiles (12 warps) per CTA, 2 CTAs/SM = 24 warps at 80 registers (4 tiles at 64 registers measured 1.3x slower)
+  // one CTA per SM, eight 128-sample tiles in flight (32 warps at 64 registers) sharing one copy of the weight images
+  static int n_groups = 0;
+  if (!n_groups) {
+    const char* e = getenv("CEDNERF_FIELD_GROUPS");
+    n_groups = e ? atoi(e) : 8;
+    if (n_groups < 1 || n_groups > FIELD_MAX_GROUPS) n_groups = 8;
+  }
   const int smem = desc->f1.image_bytes + desc->f2.image_bytes + (rgb ? desc->f3.image_bytes : 0) +
                    n_groups * MLP_TILE_BYTES + 2048;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(field_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(field_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) {
       cednerf_set_error("cednerf_field_fwd: %s", cudaGetErrorString(e));
       return (int)e;
     }
     configured = true;
   }
-  CEDNERF_REQUIRE(smem <= 112 * 1024, "networks too large for the fused kernel");
+  CEDNERF_REQUIRE(smem <= 224 * 1024, "networks too large for the fused kernel");
   FieldFwdArgs a{ray_indices, t_starts, t_ends, rays_o, rays_d, x, dirs, timestamps, t_stride, n,
                  (const uint8_t*)image_deform, (const uint8_t*)image_density, (const uint8_t*)image_colour,
                  (const __half*)table_f16, sigma, rgb, *desc};
   const int64_t tiles = (n + MLP_TILE - 1) / MLP_TILE;
-  const int64_t ctas = (tiles + n_groups - 1) / n_groups;
-  const int64_t max_ctas = (int64_t)cednerf_num_sms() * 2;
+  const int64_t ctas = tiles;  // tiles go round-robin over CTAs first, then over the groups of a CTA
+  const int64_t max_ctas = (int64_t)cednerf_num_sms();
   field_fwd_kernel<<<(unsigned)(ctas < max_ctas ? ctas : max_ctas), n_groups * MLP_TILE, smem, (cudaStream_t)stream>>>(a);
   return cednerf_check_launch("cednerf_field_fwd");
 }

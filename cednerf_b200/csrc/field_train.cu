@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(768, 1) field_train_fwd_kernel(TrainArgs a) {
   const SavedLayout sl = saved_layout(d, n);
   const int k2 = d.f2.dim_in[0];
 
-  for (int64_t tile = (int64_t)blockIdx.x * n_groups + group; tile < n_tiles; tile += (int64_t)gridDim.x * n_groups) {
+  for (int64_t tile = blockIdx.x + (int64_t)gridDim.x * group; tile < n_tiles; tile += (int64_t)gridDim.x * n_groups) {
     const int64_t s = tile * MLP_TILE + gtid;
     const bool ok = s < n;
     const int64_t srow = ok ? s : -1;
@@ -725,7 +725,7 @@ CEDNERF_EXPORT int cednerf_field_train_fwd(const int64_t* ray_indices, const flo
   a.saved = (uint8_t*)saved;
   a.d = *desc;
   const int64_t tiles = (n + MLP_TILE - 1) / MLP_TILE;
-  const int64_t ctas = (tiles + n_groups - 1) / n_groups;
+  const int64_t ctas = tiles;  // tiles go round-robin over CTAs first, then over the groups of a CTA
   const int64_t max_ctas = (int64_t)cednerf_num_sms();
   field_train_fwd_kernel<<<(unsigned)(ctas < max_ctas ? ctas : max_ctas), n_groups * MLP_TILE, smem, (cudaStream_t)stream>>>(a);
   return cednerf_check_launch("cednerf_field_train_fwd");

@@ -194,17 +194,39 @@ def cast_f16(src: torch.Tensor) -> torch.Tensor:
     return dst
 
 
+def _cap(n: int) -> int:
+    return (int(n) + 32767) // 32768 * 32768
+
+
+_param_epoch = 0
+
+
+def note_parameter_gradient():
+    """Called by the backward of every op that produces a parameter gradient: an optimiser step is about to follow, and
+    some optimisers (torch's fused Adam) update parameters without bumping their autograd version, so derived fp16
+    copies made before this point must not be trusted afterwards."""
+    global _param_epoch
+    _param_epoch += 1
+
+
 class _F16Cache:
-    """fp16 working copy of an fp32 master parameter, refreshed when the parameter's version changes."""
+    """fp16 working copy (or packed weight image) of an fp32 master parameter.  The reference re-casts on every forward
+    (hash_encoder_half.py:381-385); here the copy is reused until the parameter may have changed: its version counter
+    moved, or a backward pass produced parameter gradients since the copy was made (see note_parameter_gradient).
+    optim.FusedAdam writes the copy inside its update pass and re-validates it with `adopt`."""
 
     def __init__(self):
-        self.key, self.val = None, None
+        self.key, self.val, self.epoch = None, None, -1
 
     def get(self, p: torch.Tensor, make):
         key = (p.data_ptr(), p._version, p.numel())
-        if key != self.key:
-            self.val, self.key = make(p), key
+        if key != self.key or self.epoch != _param_epoch:
+            self.val, self.key, self.epoch = make(p), key, _param_epoch
         return self.val
+
+    def adopt(self, p: torch.Tensor):
+        """`val` now holds the copy of the current contents of `p` (written by the optimiser)."""
+        self.key, self.epoch = (p.data_ptr(), p._version, p.numel()), _param_epoch
 
 
 class HashGridFunction(torch.autograd.Function):
@@ -226,6 +248,7 @@ class HashGridFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
+        note_parameter_gradient()
         xs, table_f16 = ctx.saved_tensors
         n, xd = xs.shape
         nf = 2 * ctx.levels.n_levels
@@ -321,6 +344,7 @@ class MlpFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
+        note_parameter_gradient()
         x16, hidden, image = ctx.saved_tensors
         desc = ctx.desc
         n = x16.shape[0]
@@ -558,7 +582,9 @@ class FieldTrainFunction(torch.autograd.Function):
         latent = torch.empty(n, 32, device=dev) if want_latent else None
         selector = torch.empty(n, dtype=torch.bool, device=dev)
         move = torch.empty(n, 3, device=dev)
-        saved = torch.empty(max(int(lib.cednerf_field_saved_bytes(ctypes.byref(desc), n)), 16), dtype=U8, device=dev)
+        # capacity in steps of 32 Ki samples: the visible-sample count changes a little every step, and a 1 GB buffer that
+        # grows by a few KB would make the caching allocator cudaMalloc (and sometimes free + retry) in the hot loop
+        saved = torch.empty(max(int(lib.cednerf_field_saved_bytes(ctypes.byref(desc), _cap(n))), 16), dtype=U8, device=dev)
         call("cednerf_field_train_fwd", ptr(ridx), ptr(t0), ptr(t1), ptr(rays_o), ptr(rays_d), ptr(ts), int(t_stride), n,
              ptr(images[0]), ptr(images[1]), ptr(images[2]), ptr(images[3]), ptr(table_f16), ctypes.byref(desc),
              ptr(sigma), ptr(rgb), ptr(latent), ptr(selector), ptr(move), ptr(saved), stream())
@@ -573,6 +599,7 @@ class FieldTrainFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_sigma, d_rgb, d_latent, _sel, _mv):
+        note_parameter_gradient()
         ridx, t0, t1, rays_o, rays_d, ts, sigma, rgb, selector, saved, table_f16, i1, i2, i3, i4 = ctx.saved_tensors
         lib = _lib.load()
         n, dev = t0.numel(), t0.device
@@ -585,7 +612,7 @@ class FieldTrainFunction(torch.autograd.Function):
         dl = None
         if ctx.has4 and d_latent is not None and d_latent.numel():
             dl = _f32c(d_latent)
-        work = torch.empty(max(int(lib.cednerf_field_bwd_workspace_bytes(ctypes.byref(ctx.desc), n)), 16), dtype=U8,
+        work = torch.empty(max(int(lib.cednerf_field_bwd_workspace_bytes(ctypes.byref(ctx.desc), _cap(n))), 16), dtype=U8,
                            device=dev)
         if n:
             call("cednerf_field_train_bwd", ptr(ridx), ptr(t0), ptr(t1), ptr(rays_o), ptr(rays_d), ptr(ts), ctx.t_stride,

@@ -35,6 +35,7 @@ class Encoding(torch.nn.Module):
             self.params = torch.nn.Parameter((torch.rand(total * self.n_features, generator=g) * 2 - 1) * 1e-4)
             self.n_output_dims = self.n_levels * self.n_features
             self._f16 = ops._F16Cache()
+            self.params._cednerf_f16 = self._f16  # lets optim.FusedAdam write the fp16 copy inside its update pass
         elif ot == "Frequency":
             self.n_frequencies = int(cfg["n_frequencies"])
             self.n_output_dims = n_input_dims * 2 * self.n_frequencies

@@ -211,6 +211,33 @@ int cednerf_accumulate_bwd(const float* weights, const float* values /*nullable*
                            const int64_t* ray_indices, int64_t n_samples, const float* g_outputs,
                            float* g_weights /*nullable*/, float* g_values /*nullable*/, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Optimiser step of the training loop: grad_scaler.step(optimizer) with apex.optimizers.FusedAdam /
+ * torch.optim.Adam(lr, eps=1e-15) — train_real.py:252, 267-274, 412-420.  Up to 8 parameter tensors per call. */
+#define CEDNERF_OPT_MAX_TENSORS 8
+typedef struct CednerfAdamTensors {
+  int n_tensors;
+  float* p[CEDNERF_OPT_MAX_TENSORS];        /* fp32 master parameters (updated in place) */
+  const float* g[CEDNERF_OPT_MAX_TENSORS];  /* gradients (scaled by the loss scale) */
+  float* m[CEDNERF_OPT_MAX_TENSORS];        /* exp_avg */
+  float* v[CEDNERF_OPT_MAX_TENSORS];        /* exp_avg_sq */
+  void* p16[CEDNERF_OPT_MAX_TENSORS];       /* nullable: fp16 working copy written with p (hash table) */
+  int64_t n[CEDNERF_OPT_MAX_TENSORS];
+  float lr[CEDNERF_OPT_MAX_TENSORS];
+  float weight_decay[CEDNERF_OPT_MAX_TENSORS];
+  int64_t chunk_begin[CEDNERF_OPT_MAX_TENSORS + 1]; /* scratch, filled by the library */
+} CednerfAdamTensors;
+/* GradScaler's inf/nan check (torch._amp_foreach_non_finite_check_and_unscale_ without the write-back):
+ * *found_inf (device, caller-zeroed) = 1 when any gradient element is not finite. */
+int cednerf_nonfinite_check(const CednerfAdamTensors* tensors, float* found_inf, void* stream);
+/* unscale (g / *grad_scale) + Adam + fp16 copy in one pass; skipped when *found_inf != 0; *step (device float) advances
+ * first (advance_step != 0) unless skipped and feeds the bias corrections.  adam_w_mode: apex's decoupled weight decay,
+ * else torch Adam's L2 term (identical for weight_decay == 0, the reference's setting). */
+int cednerf_adam_step(const CednerfAdamTensors* tensors, float* step, int advance_step, const float* grad_scale /*nullable*/,
+                      const float* found_inf /*nullable*/, float beta1, float beta2, float eps, int adam_w_mode,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,6 +43,8 @@ def test_ctypes_signatures_match_header():
                 sig += "G"
             elif "CednerfMlpDesc" in a:
                 sig += "M"
+            elif "CednerfAdamTensors" in a:
+                sig += "A"
             elif "*" in a:
                 sig += "p"
             elif a.startswith("int64_t"):
@@ -61,6 +63,8 @@ def test_descriptor_structs_match_header_layout():
 
     assert ctypes.sizeof(_lib.GridLevels) == 4 + 5 * 4 * 32
     assert ctypes.sizeof(_lib.MlpDesc) == 4 + 4 * 4 * 5 + 4
+    # n_tensors (+ padding to 8), five pointer arrays, n[8], lr[8], weight_decay[8], chunk_begin[9]
+    assert ctypes.sizeof(_lib.AdamTensors) == 8 + 5 * 8 * 8 + 8 * 8 + 2 * 4 * 8 + 9 * 8
     assert ctypes.sizeof(_lib.FieldDesc) == 6 * 4 + 4 + 3 * 4 + 4 * ctypes.sizeof(_lib.MlpDesc) + ctypes.sizeof(_lib.GridLevels)
 
 
