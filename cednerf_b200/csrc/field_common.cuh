@@ -93,14 +93,13 @@ __device__ __forceinline__ void time_embedding(float tv, float mvnorm, int mode,
 // Index arithmetic is arranged for few instructions per gather: the level's table base is formed once, hashed levels
 // mask the six per-axis terms first (one LOP3 per corner), dense levels whose eight corners are all in range (every
 // point inside the box) address them as base + {0, 1, res, res + 1, ...}.
+// the 8*LG gathers of levels l_first .. l_first+LG-1 (fractions kept for the weights)
 template <int LG>
-__device__ __forceinline__ void hash_levels(const float* xn, const __half* __restrict__ table, const CednerfGridLevels& lv,
-                                            int l0, uint32_t* feat, int level_base = 0) {
-  float frac[LG][3];
-  __half2 v[LG][8];
+__device__ __forceinline__ void hash_issue(const float* xn, const __half* __restrict__ table, const CednerfGridLevels& lv,
+                                           int l_first, float (*frac)[3], __half2 (*v)[8]) {
 #pragma unroll
-  for (int a = 0; a < LG; ++a) {  // issue all 8*LG gathers first ...
-    const int l = level_base + l0 + a;
+  for (int a = 0; a < LG; ++a) {
+    const int l = l_first + a;
     const Cell c = locate(xn, lv.scale[l]);
     frac[a][0] = c.f[0], frac[a][1] = c.f[1], frac[a][2] = c.f[2];
     const uint32_t res = lv.res[l], size = lv.size[l];
@@ -130,6 +129,14 @@ __device__ __forceinline__ void hash_levels(const float* xn, const __half* __res
       }
     }
   }
+}
+
+template <int LG>
+__device__ __forceinline__ void hash_levels(const float* xn, const __half* __restrict__ table, const CednerfGridLevels& lv,
+                                            int l0, uint32_t* feat, int level_base = 0) {
+  float frac[LG][3];
+  __half2 v[LG][8];
+  hash_issue<LG>(xn, table, lv, level_base + l0, frac, v);  // issue all 8*LG gathers first ...
 #pragma unroll
   for (int a = 0; a < LG; ++a) {  // ... then the weights (recomputed from 3 fractions) and the blend
     float w[8];

@@ -460,17 +460,28 @@ __device__ __forceinline__ void make_input(const TrainArgs& a, const SavedLayout
   }
 }
 
+// Four 128-sample tiles in flight per SM (one warp-group each, one CTA per SM).  Every group owns its tile buffers and
+// its input-gradient accumulator; the weight-gradient accumulators are SHARED by the groups: tcgen05.mma instructions
+// of a CTA execute in issue order, whichever thread issued them, so D += A*B from different groups onto the same TMEM
+// tile is the same read-modify-write chain as the k-loop of one thread.  They are zeroed once (tcgen05.st) and flushed
+// once per CTA with fp32 atomics.
+#define BWD_GROUPS 4
+#define BWD_GROUP_SMEM (3 * MLP_TILE_BYTES)
+
 template <int NET>
-__global__ void __launch_bounds__(MLP_TILE) field_bwd_kernel(TrainArgs a) {
+__global__ void __launch_bounds__(BWD_GROUPS * MLP_TILE, 1) field_bwd_kernel(TrainArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const CednerfMlpDesc& d = net_desc<NET>(a.d);
+  const int n_groups = blockDim.x / MLP_TILE;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, group = tid / MLP_TILE, gtid = tid % MLP_TILE;
   uint8_t* wsm = smem;
-  uint8_t* gbuf[2] = {smem + MLP_MAX_LAYERS * 8192, smem + MLP_MAX_LAYERS * 8192 + MLP_TILE_BYTES};
-  uint8_t* ibuf[2] = {smem + MLP_MAX_LAYERS * 8192 + 2 * MLP_TILE_BYTES, smem + MLP_MAX_LAYERS * 8192 + 3 * MLP_TILE_BYTES};
-  __shared__ uint64_t bar;
+  uint8_t* gsm = smem + ((d.image_bytes + 1023) & ~1023) + (size_t)group * BWD_GROUP_SMEM;
+  uint8_t* gbuf = gsm;  // output-gradient tile of the current layer; the next layer's is written over it in place
+  uint8_t* ibuf[2] = {gsm + MLP_TILE_BYTES, gsm + 2 * MLP_TILE_BYTES};
+  __shared__ uint64_t bars[BWD_GROUPS];
   __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint64_t* bar = &bars[group];
   const int64_t n = a.n;
   const SavedLayout sl = saved_layout(a.d, n);
   const BwdWorkLayout wl = bwd_layout(a.d, n);
@@ -478,76 +489,82 @@ __global__ void __launch_bounds__(MLP_TILE) field_bwd_kernel(TrainArgs a) {
   const __half* hidden = reinterpret_cast<const __half*>(
       a.saved + (NET == 1 ? sl.h1 : (NET == 2 ? sl.h2 : (NET == 3 ? sl.h3 : sl.h4))));
   float* d_params = a.d_params[NET - 1];
+  const int L = d.n_layers;
   for (int q = tid; q < d.image_bytes / 16; q += blockDim.x)
     reinterpret_cast<uint4*>(wsm)[q] = __ldg(reinterpret_cast<const uint4*>(image) + q);
   if (warp == 0) tmem_alloc(&tmem_base_s, a.tmem_cols);
-  if (tid == 0) {
-    mbar_init(&bar, 1);
-    fence_barrier_init();
-  }
+  if (gtid == 0) mbar_init(bar, 1);
+  if (tid == 0) fence_barrier_init();
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  const uint32_t tmem_warp = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const uint32_t tmem_grp = tmem_base + 64u * (uint32_t)group;                    // dgrad accumulator of this group
+  const uint32_t tmem_warp = tmem_grp + ((uint32_t)((warp & 3) * 32) << 16);
+  const uint32_t wg_base = tmem_base + 64u * (uint32_t)n_groups;                  // shared wgrad accumulators
+  const uint32_t wg_warp = wg_base + ((uint32_t)((warp & 3) * 32) << 16);
+  if (group == 0) {
+    for (int cb = 0; cb < 4 * ((L + 1) / 2); ++cb) tmem_st16_fill(wg_warp + cb * 16, 0u);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
   uint32_t phase = 0;
-  const int L = d.n_layers;
   const int64_t n_tiles = (n + MLP_TILE - 1) / MLP_TILE;
   const bool want_dx = NET != 1;  // the deformation net's input (x, t) carries no gradient
-  int64_t iter = 0;
 
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
+  for (int64_t tile = blockIdx.x + (int64_t)gridDim.x * group; tile < n_tiles; tile += (int64_t)gridDim.x * n_groups) {
     const int64_t row0 = tile * MLP_TILE;
     const int rows_valid = (int)((n - row0) < MLP_TILE ? (n - row0) : MLP_TILE);
-    const int64_t s = row0 + tid;
-    const bool ok = tid < rows_valid;
-    if (L > 1) load_tile_async(ibuf[0], hidden + ((int64_t)(L - 2) * n + row0) * 64, 64, rows_valid);
-    else make_input<NET>(a, sl, ibuf[0], tid, s, ok);
-    make_dout<NET>(a, sl, wl, gbuf[0], tid, s, ok);
+    const int64_t s = row0 + gtid;
+    const bool ok = gtid < rows_valid;
+    if (L > 1) load_tile_async(ibuf[0], hidden + ((int64_t)(L - 2) * n + row0) * 64, 64, rows_valid, gtid, MLP_TILE);
+    else make_input<NET>(a, sl, ibuf[0], gtid, s, ok);
+    make_dout<NET>(a, sl, wl, gbuf, gtid, s, ok);
     cp_async_wait_all();
     fence_proxy_async();
     tc_fence_before();
-    __syncthreads();
+    group_sync(group);
     int cur = 0;
     for (int l = L - 1; l >= 0; --l) {
       const int K_in = d.dim_in[l], N_out = d.dim_out[l];
       const bool need_dgrad = (l > 0) || want_dx;
-      if (tid == 0) {
+      if (gtid == 0) {
         tc_fence_after();
         {
-          const uint64_t ad = make_desc(smem_u32(gbuf[cur]), 64, 64);
+          const uint64_t ad = make_desc(smem_u32(gbuf), 64, 64);
           const uint64_t bd = make_desc(smem_u32(ibuf[cur]), 64, 64);
           const uint32_t id = make_idesc(64, K_in, 1, 1);
           // M = 64 accumulators occupy 16 of the 32 lanes of each TMEM sub-partition: two layers share a column block
-          const uint32_t acc = tmem_base + 64u * (uint32_t)(1 + (l >> 1)) + ((uint32_t)((l & 1) * 16) << 16);
-          for (int k = 0; k < MLP_TILE / 16; ++k) umma(acc, ad + 128 * k, bd + 128 * k, id, (iter > 0) || (k > 0));
+          const uint32_t acc = wg_base + 64u * (uint32_t)(l >> 1) + ((uint32_t)((l & 1) * 16) << 16);
+          for (int k = 0; k < MLP_TILE / 16; ++k) umma(acc, ad + 128 * k, bd + 128 * k, id, 1u);
         }
         if (need_dgrad) {
-          const uint64_t ad = make_desc(smem_u32(gbuf[cur]), 1, 64);
+          const uint64_t ad = make_desc(smem_u32(gbuf), 1, 64);
           const uint64_t bd = make_desc(smem_u32(wsm + d.image_off[l]), 64, 64);
           const uint32_t id = make_idesc(128, K_in, 0, 1);
-          for (int k = 0; k < N_out / 16; ++k) umma(tmem_base, ad + 2 * k, bd + 128 * k, id, k > 0);
+          for (int k = 0; k < N_out / 16; ++k) umma(tmem_grp, ad + 2 * k, bd + 128 * k, id, k > 0);
         }
-        umma_commit(&bar);
+        umma_commit(bar);
       }
       if (l > 0) {
-        if (l > 1) load_tile_async(ibuf[cur ^ 1], hidden + ((int64_t)(l - 2) * n + row0) * 64, 64, rows_valid);
-        else make_input<NET>(a, sl, ibuf[cur ^ 1], tid, s, ok);
+        if (l > 1) load_tile_async(ibuf[cur ^ 1], hidden + ((int64_t)(l - 2) * n + row0) * 64, 64, rows_valid, gtid, MLP_TILE);
+        else make_input<NET>(a, sl, ibuf[cur ^ 1], gtid, s, ok);
       }
-      mbar_wait(&bar, phase);
+      mbar_wait(bar, phase);
       phase ^= 1;
       tc_fence_after();
       if (l > 0) {
-        uint8_t* nxt = gbuf[cur ^ 1];
         const uint8_t* act = ibuf[cur];
 #pragma unroll
         for (int cb = 0; cb < 4; ++cb) {
           uint32_t r[16];
           tmem_ld16(tmem_warp + cb * 16, r);
           tmem_ld_wait();
-          const uint4 m0 = *reinterpret_cast<const uint4*>(act + swz(tid, 2 * cb));
-          const uint4 m1 = *reinterpret_cast<const uint4*>(act + swz(tid, 2 * cb + 1));
+          const uint4 m0 = *reinterpret_cast<const uint4*>(act + swz(gtid, 2 * cb));
+          const uint4 m1 = *reinterpret_cast<const uint4*>(act + swz(gtid, 2 * cb + 1));
           const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
           uint32_t p[8];
 #pragma unroll
@@ -556,8 +573,9 @@ __global__ void __launch_bounds__(MLP_TILE) field_bwd_kernel(TrainArgs a) {
             const float hi = (mw[j] & 0x7FFF0000u) && !(mw[j] & 0x80000000u) ? __uint_as_float(r[2 * j + 1]) : 0.f;
             p[j] = pack_h2(lo, hi);
           }
-          *reinterpret_cast<uint4*>(nxt + swz(tid, 2 * cb)) = make_uint4(p[0], p[1], p[2], p[3]);
-          *reinterpret_cast<uint4*>(nxt + swz(tid, 2 * cb + 1)) = make_uint4(p[4], p[5], p[6], p[7]);
+          // in place: every MMA that read this tile has completed, and a thread only touches its own row
+          *reinterpret_cast<uint4*>(gbuf + swz(gtid, 2 * cb)) = make_uint4(p[0], p[1], p[2], p[3]);
+          *reinterpret_cast<uint4*>(gbuf + swz(gtid, 2 * cb + 1)) = make_uint4(p[4], p[5], p[6], p[7]);
         }
       } else if (want_dx) {
         if constexpr (NET == 3) {
@@ -603,19 +621,21 @@ __global__ void __launch_bounds__(MLP_TILE) field_bwd_kernel(TrainArgs a) {
       cp_async_wait_all();  // the prefetched next-layer tile has landed
       fence_proxy_async();
       tc_fence_before();
-      __syncthreads();
+      group_sync(group);
       cur ^= 1;
     }
   }
-  if (iter > 0) {
-    tc_fence_after();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (group == 0) {  // every CTA added into zero-initialised accumulators: flush them all (zeros where it had no tile)
     for (int l = 0; l < L; ++l) {
       const int K_in = d.dim_in[l], N_out = d.dim_out[l];
       const int half = l & 1;                       // which 16-lane half of the sub-partition holds this layer
       const int m = warp * 16 + (lane & 15);
       for (int cb = 0; cb < K_in / 16; ++cb) {
         uint32_t r[16];
-        tmem_ld16(tmem_warp + 64u * (uint32_t)(1 + (l >> 1)) + cb * 16, r);
+        tmem_ld16(wg_warp + 64u * (uint32_t)(l >> 1) + cb * 16, r);
         tmem_ld_wait();
         if ((lane >> 4) == half && m < N_out) {
           float* dst = d_params + d.param_off[l] + m * K_in + cb * 16;
@@ -630,7 +650,58 @@ __global__ void __launch_bounds__(MLP_TILE) field_bwd_kernel(TrainArgs a) {
   if (warp == 0) tmem_dealloc(tmem_base, a.tmem_cols);
 }
 
-constexpr int BWD_SMEM = MLP_MAX_LAYERS * 8192 + 4 * MLP_TILE_BYTES + 1024;
+// dL/dx_norm of the hash encoding from the level-major feature gradient (tcnn's kernel_grid_backward_input form,
+// SURVEY.md E2q): one thread per sample walks all levels with the gather arithmetic of the forward (two levels = 16
+// gathers in flight), reads its 4 bytes of dy per level coalesced, keeps the three sums in registers and writes them
+// once.  Replaces the (sample, level)-per-thread kernel of hashgrid.cu on this path (0.38 ms -> see profiles/).
+__global__ void __launch_bounds__(256) hashgrid_bwd_input_lm_kernel(const float* __restrict__ xn, int64_t n,
+                                                                    const __half* __restrict__ table, CednerfGridLevels lv,
+                                                                    const __half2* __restrict__ dy_lm, float* __restrict__ g_x) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const float x[3] = {xn[3 * s], xn[3 * s + 1], xn[3 * s + 2]};
+  float gx[3] = {0.f, 0.f, 0.f};
+  const int L = lv.n_levels;
+  auto level_terms = [&](const float* f, const __half2* v, int l) {
+    const float2 d = __half22float2(dy_lm[(int64_t)l * n + s]);
+    float dot[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float2 t = __half22float2(v[k]);
+      dot[k] = t.x * d.x + t.y * d.y;
+    }
+    const float wx[2] = {1.f - f[0], f[0]}, wy[2] = {1.f - f[1], f[1]}, wz[2] = {1.f - f[2], f[2]};
+    float a[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        a[0] += wy[p] * wz[q] * (dot[1 + 2 * p + 4 * q] - dot[0 + 2 * p + 4 * q]);
+        a[1] += wx[p] * wz[q] * (dot[p + 2 + 4 * q] - dot[p + 0 + 4 * q]);
+        a[2] += wx[p] * wy[q] * (dot[p + 2 * q + 4] - dot[p + 2 * q]);
+      }
+    const float sc = lv.scale[l];
+    gx[0] += a[0] * sc, gx[1] += a[1] * sc, gx[2] += a[2] * sc;
+  };
+  int l0 = 0;
+#pragma unroll 1
+  for (; l0 + 2 <= L; l0 += 2) {
+    float frac[2][3];
+    __half2 v[2][8];
+    hash_issue<2>(x, table, lv, l0, frac, v);
+    level_terms(frac[0], v[0], l0);
+    level_terms(frac[1], v[1], l0 + 1);
+  }
+  if (l0 < L) {
+    float frac[1][3];
+    __half2 v[1][8];
+    hash_issue<1>(x, table, lv, l0, frac, v);
+    level_terms(frac[0], v[0], l0);
+  }
+  g_x[3 * s] = gx[0], g_x[3 * s + 1] = gx[1], g_x[3 * s + 2] = gx[2];
+}
+
+constexpr int BWD_SMEM_MAX = 226 * 1024;  // 227 KB opt-in limit minus the kernel's 1 KB of static shared memory
 
 int check_train_desc(const CednerfFieldDesc* d) {
   if (!d) return 0;
@@ -655,7 +726,7 @@ template <int NET>
 int launch_bwd(TrainArgs a, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(field_bwd_kernel<NET>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(field_bwd_kernel<NET>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM_MAX);
     if (e != cudaSuccess) {
       cednerf_set_error("cednerf_field_train_bwd: %s", cudaGetErrorString(e));
       return (int)e;
@@ -663,12 +734,15 @@ int launch_bwd(TrainArgs a, cudaStream_t st) {
     configured = true;
   }
   const CednerfMlpDesc& d = NET == 1 ? a.d.f1 : (NET == 2 ? a.d.f2 : (NET == 3 ? a.d.f3 : a.d.f4));
-  uint32_t cols = 64u * (uint32_t)(1 + (d.n_layers + 1) / 2), alloc = 64;
+  int groups = BWD_GROUPS;  // as many tiles in flight as shared memory (weights + 48 KB per group) and TMEM allow
+  const int fixed = ((d.image_bytes + 1023) & ~1023) + 2048;
+  while (groups > 1 && (fixed + groups * BWD_GROUP_SMEM > BWD_SMEM_MAX || 64 * (groups + (d.n_layers + 1) / 2) > 512)) --groups;
+  uint32_t cols = 64u * (uint32_t)(groups + (d.n_layers + 1) / 2), alloc = 64;
   while (alloc < cols) alloc <<= 1;
   a.tmem_cols = alloc;
   const int64_t tiles = (a.n + MLP_TILE - 1) / MLP_TILE;
-  const int64_t max_ctas = (int64_t)cednerf_num_sms() * (alloc <= 256 ? 2 : 1);
-  field_bwd_kernel<NET><<<(unsigned)(tiles < max_ctas ? tiles : max_ctas), MLP_TILE, BWD_SMEM, st>>>(a);
+  const int64_t max_ctas = (int64_t)cednerf_num_sms();
+  field_bwd_kernel<NET><<<(unsigned)(tiles < max_ctas ? tiles : max_ctas), groups * MLP_TILE, fixed + groups * BWD_GROUP_SMEM, st>>>(a);
   return 0;
 }
 
@@ -777,9 +851,8 @@ CEDNERF_EXPORT int cednerf_field_train_bwd(const int64_t* ray_indices, const flo
   float* g_xn = reinterpret_cast<float*>((uint8_t*)work + wl.g_xn);
   rc = cednerf_hashgrid_bwd_table_lm(xn, 3, n, &desc->levels, (const uint8_t*)work + wl.dy_lm, g_table, stream);
   if (rc) return rc;
-  rc = cednerf_hashgrid_bwd(xn, 3, n, table_f16, &desc->levels, (const uint8_t*)work + wl.d_in2, desc->f2.dim_in[0], 1,
-                            nullptr, g_xn, stream);
-  if (rc) return rc;
+  hashgrid_bwd_input_lm_kernel<<<cednerf_blocks(n, 256), 256, 0, st>>>(
+      xn, n, (const __half*)table_f16, desc->levels, reinterpret_cast<const __half2*>((const uint8_t*)work + wl.dy_lm), g_xn);
   if ((rc = launch_bwd<1>(a, st))) return rc;
-  return cednerf_check_launch("cednerf_field_train_bwd", launches + 1);
+  return cednerf_check_launch("cednerf_field_train_bwd", launches + 2);
 }

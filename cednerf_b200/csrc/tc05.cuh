@@ -90,6 +90,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 16 columns x this warp's 32 lanes <- one value (used to zero accumulators that several issuers add into)
+__device__ __forceinline__ void tmem_st16_fill(uint32_t taddr, uint32_t v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
+      "r"(v)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // byte offset of 16-byte chunk `c` of row `r` inside a swizzled [rows][128 B] tile (tile base 1024-aligned)
 __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * MLP_ROW_BYTES + ((c ^ (r & 7)) << 4)); }
@@ -108,11 +116,13 @@ __device__ __forceinline__ void load_tile(uint8_t* tile, const __half* __restric
 }
 // same as load_tile but with cp.async (LDGSTS): the copies are in flight while the thread goes on to wait for the tensor
 // core and run its epilogue; cp_async_wait_all() + fence.proxy.async must precede the MMA that reads the tile
-__device__ __forceinline__ void load_tile_async(uint8_t* tile, const __half* __restrict__ g, int width, int rows_valid) {
+__device__ __forceinline__ void load_tile_async(uint8_t* tile, const __half* __restrict__ g, int width, int rows_valid,
+                                                int tid = -1, int n_threads = 0) {
   const int cpr = width >> 3;
   const int total = MLP_TILE * cpr;
   const uint4* src = reinterpret_cast<const uint4*>(g);
-  for (int q = threadIdx.x; q < total; q += blockDim.x) {
+  if (tid < 0) tid = threadIdx.x, n_threads = blockDim.x;  // default: the whole CTA loads the tile
+  for (int q = tid; q < total; q += n_threads) {
     const int r = q / cpr, c = q - r * cpr;
     const uint32_t dst = smem_u32(tile + swz(r, c));
     const int bytes = r < rows_valid ? 16 : 0;  // src-size 0: the 16 destination bytes are zero-filled
