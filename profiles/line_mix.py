@@ -13,6 +13,9 @@ def main():
     if len(sys.argv) > 4:
         cmd += ["--launch-skip", sys.argv[4], "--launch-count", "1"]
     rows = list(csv.reader(io.StringIO(subprocess.run(cmd, capture_output=True, text=True).stdout)))
+    sel = os.environ.get("KSEL", "")  # substring of the full kernel name (template arguments), e.g. KSEL="(bool)0"
+    k0 = next(i for i, r in enumerate(rows) if r and r[0] == "Kernel Name" and sel in r[1])
+    rows = rows[k0:]
     hi = next(i for i, r in enumerate(rows) if "Source" in r and "# Samples" in r)
     hdr = rows[hi]; ix = {h: i for i, h in enumerate(hdr)}
     kname = rows[hi - 1][1]

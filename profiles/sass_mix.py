@@ -4,6 +4,7 @@
     python profiles/sass_mix.py gpurun_out/prof.ncu-rep field_fwd_kernel [launch-id]
 """
 import collections
+import os
 import csv
 import io
 import subprocess
@@ -17,6 +18,9 @@ def main():
         cmd += ["--launch-skip", sys.argv[3], "--launch-count", "1"]
     txt = subprocess.run(cmd, capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
+    sel = os.environ.get("KSEL", "")  # substring of the full kernel name (template arguments), e.g. KSEL="(bool)0"
+    k0 = next(i for i, r in enumerate(rows) if r and r[0] == "Kernel Name" and sel in r[1])
+    rows = rows[k0:]
     hi = next(i for i, r in enumerate(rows) if "Source" in r and "# Samples" in r)
     hdr = rows[hi]
     ix = {h: i for i, h in enumerate(hdr)}
