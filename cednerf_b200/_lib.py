@@ -72,7 +72,7 @@ _SIGNATURES = {
     "cednerf_mlp_bwd": "ppppMlpippp",
     "cednerf_field_fwd": "ppppppppilppppFppp",
     "cednerf_field_train_fwd": "ppppppilpppppFppppppp",
-    "cednerf_field_train_bwd": "ppppppilpppppFpppppppppppppp",
+    "cednerf_field_train_bwd": "ppppppilpppppFpppppppppppppip",
     "cednerf_ray_offsets": "pllpp",
     "cednerf_composite_fwd": "pppppppillpppppppifp",
     "cednerf_composite_bwd": "pppppppillppppppppppfp",

@@ -815,8 +815,9 @@ CEDNERF_EXPORT int cednerf_field_train_bwd(const int64_t* ray_indices, const flo
                                            const uint8_t* selector, const void* saved, const float* d_sigma,
                                            const float* d_rgb, const float* d_latent, void* work, float* d_params_deform,
                                            float* d_params_density, float* d_params_colour, float* d_params_predict,
-                                           float* g_table, void* stream) {
+                                           float* g_table, int phase, void* stream) {
   CEDNERF_REQUIRE(check_train_desc(desc), "bad field descriptor");
+  CEDNERF_REQUIRE(phase >= 0 && phase <= 2, "phase: 0 all, 1 up to the table gradient, 2 the rest");
   CEDNERF_REQUIRE(n >= 0 && ray_indices && t_starts && t_ends && rays_o && rays_d && timestamps && rgb && selector &&
                       saved && d_sigma && d_rgb && work && d_params_deform && d_params_density && d_params_colour &&
                       g_table,
@@ -839,18 +840,22 @@ CEDNERF_EXPORT int cednerf_field_train_bwd(const int64_t* ray_indices, const flo
   a.d = *desc;
   const SavedLayout sl = saved_layout(*desc, n);  // offsets follow the FORWARD's descriptor
   const BwdWorkLayout wl = bwd_layout(*desc, n);
-  int rc;
-  if ((rc = launch_bwd<3>(a, st))) return rc;
-  if ((rc = launch_bwd<2>(a, st))) return rc;
-  int launches = 2;
-  if (has4) {
-    if ((rc = launch_bwd<4>(a, st))) return rc;
-    ++launches;
-  }
+  int rc, launches = 0;
   const float* xn = reinterpret_cast<const float*>((const uint8_t*)saved + sl.xn);
   float* g_xn = reinterpret_cast<float*>((uint8_t*)work + wl.g_xn);
-  rc = cednerf_hashgrid_bwd_table_lm(xn, 3, n, &desc->levels, (const uint8_t*)work + wl.dy_lm, g_table, stream);
-  if (rc) return rc;
+  if (phase != 2) {
+    if ((rc = launch_bwd<3>(a, st))) return rc;
+    if ((rc = launch_bwd<2>(a, st))) return rc;
+    launches += 2;
+    if (has4) {
+      if ((rc = launch_bwd<4>(a, st))) return rc;
+      ++launches;
+    }
+    rc = cednerf_hashgrid_bwd_table_lm(xn, 3, n, &desc->levels, (const uint8_t*)work + wl.dy_lm, g_table, stream);
+    if (rc) return rc;
+    // g_table is complete here: with phase == 1 the caller can start its all-reduce while phase 2 runs
+    if (phase == 1) return cednerf_check_launch("cednerf_field_train_bwd", launches);
+  }
   hashgrid_bwd_input_lm_kernel<<<cednerf_blocks(n, 256), 256, 0, st>>>(
       xn, n, (const __half*)table_f16, desc->levels, reinterpret_cast<const __half2*>((const uint8_t*)work + wl.dy_lm), g_xn);
   if ((rc = launch_bwd<1>(a, st))) return rc;

@@ -564,6 +564,17 @@ def field_fwd(desc: FieldDesc, images, table_f16, n: int, sigma_only: bool, pack
     return sigma, rgb
 
 
+_table_grad_hook = None
+
+
+def set_table_grad_hook(fn):
+    """fn(g_table) is called from the fused training backward as soon as the hash-table gradient is complete, before
+    the encoding's dL/dx and the deformation-net backward are launched (dp.GradAllReducer starts its all-reduce there).
+    None removes the hook."""
+    global _table_grad_hook
+    _table_grad_hook = fn
+
+
 class FieldTrainFunction(torch.autograd.Function):
     """Training-mode DNGPradianceField.forward on packed ray samples: one forward launch, backward = one tensor-core
     launch per network + the hash-grid backward.  Returns (sigma [n], rgb [n,3], latent [n,32] | None, selector, move)."""
@@ -614,9 +625,14 @@ class FieldTrainFunction(torch.autograd.Function):
             dl = _f32c(d_latent)
         work = torch.empty(max(int(lib.cednerf_field_bwd_workspace_bytes(ctypes.byref(ctx.desc), _cap(n))), 16), dtype=U8,
                            device=dev)
-        if n:
-            call("cednerf_field_train_bwd", ptr(ridx), ptr(t0), ptr(t1), ptr(rays_o), ptr(rays_d), ptr(ts), ctx.t_stride,
-                 n, ptr(i1), ptr(i2), ptr(i3), ptr(i4) if ctx.has4 else None, ptr(table_f16), ctypes.byref(ctx.desc),
-                 ptr(sigma), ptr(rgb), ptr(selector), ptr(saved), ptr(d_sigma), ptr(d_rgb), ptr(dl), ptr(work), ptr(g1),
-                 ptr(g2), ptr(g3), ptr(g4) if dl is not None else None, ptr(gt), stream())
+        hook = _table_grad_hook
+        for phase in ((1, 2) if hook is not None else (0,)):
+            if n:
+                call("cednerf_field_train_bwd", ptr(ridx), ptr(t0), ptr(t1), ptr(rays_o), ptr(rays_d), ptr(ts),
+                     ctx.t_stride, n, ptr(i1), ptr(i2), ptr(i3), ptr(i4) if ctx.has4 else None, ptr(table_f16),
+                     ctypes.byref(ctx.desc), ptr(sigma), ptr(rgb), ptr(selector), ptr(saved), ptr(d_sigma), ptr(d_rgb),
+                     ptr(dl), ptr(work), ptr(g1), ptr(g2), ptr(g3), ptr(g4) if dl is not None else None, ptr(gt), phase,
+                     stream())
+            if phase == 1:
+                hook(gt)  # the 191 MB table gradient is complete: its all-reduce overlaps the rest of the backward
         return (g1, g2, g3, g4 if dl is not None else None, gt) + (None,) * 11

@@ -54,6 +54,71 @@ def test_gradient_allreduce_matches_single_process(tmp_path):
     assert got["ms"] == 2.0 and got["tot"] == 64.0
 
 
+class _TwoGradNode(torch.autograd.Function):
+    """Stand-in for ops.FieldTrainFunction: ONE autograd node that produces the table gradient first and the other
+    gradients afterwards, calling the table-gradient hook in between (what the fused backward does on the GPU)."""
+
+    @staticmethod
+    def forward(ctx, w, table, x, idx):
+        ctx.save_for_backward(w, table, x, idx)
+        return x @ w + table[idx].sum(-1, keepdim=True)
+
+    @staticmethod
+    def backward(ctx, g):
+        from cednerf_b200 import ops
+
+        w, table, x, idx = ctx.saved_tensors
+        gt = torch.zeros_like(table).index_add_(0, idx, g.sum(-1, keepdim=True).expand(-1, 2).contiguous())
+        if ops._table_grad_hook is not None:
+            ops._table_grad_hook(gt)       # all-reduce starts here ...
+        gw = x.t() @ g                      # ... and overlaps the rest of the node's work
+        return gw, gt, None, None
+
+
+def _worker_early(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cednerf_b200 import dp, ops
+
+    g = torch.Generator().manual_seed(11)
+    w = torch.nn.Parameter(torch.randn(8, 3, generator=g))
+    table = torch.nn.Parameter(torch.randn(500, 2, generator=g))
+    x_all, y_all = torch.randn(64, 8, generator=g), torch.randn(64, 3, generator=g)
+    idx_all = torch.randint(0, 500, (64,), generator=g)
+    reducer = dp.GradAllReducer([w, table], world)
+    assert ops._table_grad_hook is not None
+    lo, hi = dp.shard_range(64, rank, world)
+    res = {}
+    for it in range(2):  # second pass: .grad already exists, autograd accumulates into it and the early path stands down
+        pred = _TwoGradNode.apply(w, table, x_all[lo:hi], idx_all[lo:hi])
+        torch.nn.functional.mse_loss(pred, y_all[lo:hi]).backward()
+        reducer.wait()
+        res[f"w{it}"], res[f"table{it}"] = w.grad.clone(), table.grad.clone()
+    reducer.remove()
+    assert ops._table_grad_hook is None
+    if rank == 0:
+        torch.save(res, out)
+    dist.destroy_process_group()
+
+
+def test_table_gradient_allreduce_started_inside_the_fused_backward(tmp_path):
+    out = str(tmp_path / "dp_early.pt")
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_worker_early, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    g = torch.Generator().manual_seed(11)
+    w = torch.nn.Parameter(torch.randn(8, 3, generator=g))
+    table = torch.nn.Parameter(torch.randn(500, 2, generator=g))
+    x_all, y_all = torch.randn(64, 8, generator=g), torch.randn(64, 3, generator=g)
+    idx_all = torch.randint(0, 500, (64,), generator=g)
+    pred = _TwoGradNode.apply(w, table, x_all, idx_all)
+    torch.nn.functional.mse_loss(pred, y_all).backward()
+    for it in range(2):
+        torch.testing.assert_close(got[f"w{it}"], w.grad * (it + 1), rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(got[f"table{it}"], table.grad * (it + 1), rtol=1e-5, atol=1e-7)
+
+
 def test_sharding_helpers():
     from cednerf_b200 import dp
 
