@@ -132,13 +132,12 @@ __global__ void __launch_bounds__(896, 1) field_fwd_kernel(FieldFwdArgs a) {
       const int k2 = d.f2.dim_in[0];
       // runtime loops over level groups (not unrolled: the fully unrolled 16-level body was 340 KB of SASS and the
       // kernel spent 18 % of its stall samples waiting for instructions)
-      if ((L & 3) == 0) {
+      if ((L & 1) == 0) {
 #pragma unroll 1
-        for (int l0 = 0; l0 < L; l0 += 4) {  // 16 gathers in flight per thread; four levels = one 16-byte chunk of the row
-          uint32_t f4w[4];
-          hash_levels<2>(xn, a.table, d.levels, 0, f4w, l0);
-          hash_levels<2>(xn, a.table, d.levels, 0, f4w + 2, l0 + 2);
-          *reinterpret_cast<uint4*>(abuf0 + swz(gtid, l0 >> 2)) = make_uint4(f4w[0], f4w[1], f4w[2], f4w[3]);
+        for (int l0 = 0; l0 < L; l0 += 2) {  // 16 gathers in flight per thread; two levels = 8 bytes of the row
+          uint32_t f2w[2];
+          hash_levels<2>(xn, a.table, d.levels, 0, f2w, l0);
+          *reinterpret_cast<uint2*>(abuf0 + swz(gtid, l0 >> 2) + ((l0 & 2) << 2)) = make_uint2(f2w[0], f2w[1]);
         }
       } else {
 #pragma unroll 1

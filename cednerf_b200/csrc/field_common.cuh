@@ -65,6 +65,9 @@ __device__ __forceinline__ void run_chain(const CednerfMlpDesc& d, const uint8_t
 // value the tensor-core chain hands on: fp32 accumulator rounded to fp16 (tcnn network output precision)
 __device__ __forceinline__ float rnd16(uint32_t acc_bits) { return __half2float(__float2half_rn(__uint_as_float(acc_bits))); }
 
+// Time embedding on the special-function unit: arguments are t 2^i (+ pi/2) with t in [0, 1], i <= 3, i.e. below 10 rad,
+// where __sinf's fp32 argument scaling is good to ~6e-7 absolute; the nine values are rounded to fp16 (half ulp 2.4e-4)
+// as soon as they enter the MLP input row.  (Full-precision sinf was 1200 SASS instructions and ~160 executed per sample.)
 __device__ __forceinline__ void time_embedding(float tv, float mvnorm, int mode, float* e /*[9]*/) {
   const float half_pi = 1.5707963267948966f;
   e[0] = tv;
@@ -72,27 +75,26 @@ __device__ __forceinline__ void time_embedding(float tv, float mvnorm, int mode,
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float tb = tv * (float)(1 << i);
-      e[1 + i] = sinf(tb);
-      e[5 + i] = sinf(tb + half_pi);
+      e[1 + i] = __sinf(tb);
+      e[5 + i] = __sinf(tb + half_pi);
     }
   } else {
     const float scm[4] = {0.f, 2.f, 8.f, 24.f};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float tb = tv * (float)(1 << i);
-      const float att = expf(-1.f * (mvnorm * scm[i]));
-      e[1 + 2 * i] = sinf(tb) * att;
-      e[2 + 2 * i] = sinf(tb + half_pi) * att;
+      const float att = __expf(-1.f * (mvnorm * scm[i]));
+      e[1 + 2 * i] = __sinf(tb) * att;
+      e[2 + 2 * i] = __sinf(tb + half_pi) * att;
     }
   }
 }
 
-// 2*L hash features of one point, packed as L half2 words.  Cell, corner indices and weights are exactly those of
-// hashgrid_fwd_kernel; the blend accumulates with fused multiply-adds (one rounding per term instead of two), so a
-// feature can differ from the stand-alone encoder by one fp16 ulp when the fp32 sum sits on a rounding boundary.
-// Index arithmetic is arranged for few instructions per gather: the level's table base is formed once, hashed levels
-// mask the six per-axis terms first (one LOP3 per corner), dense levels whose eight corners are all in range (every
-// point inside the box) address them as base + {0, 1, res, res + 1, ...}.
+__device__ __noinline__ uint32_t wrapped_corner(uint32_t base, int k, uint32_t res, uint32_t r2, uint32_t size) {
+  const uint32_t h = base + (uint32_t)(k & 1) + (uint32_t)((k >> 1) & 1) * res + (uint32_t)(k >> 2) * r2;
+  return h >= size ? h % size : h;
+}
+
 // the 8*LG gathers of levels l_first .. l_first+LG-1 (fractions kept for the weights)
 template <int LG>
 __device__ __forceinline__ void hash_issue(const float* xn, const __half* __restrict__ table, const CednerfGridLevels& lv,
@@ -121,11 +123,10 @@ __device__ __forceinline__ void hash_issue(const float* xn, const __half* __rest
         v[a][2] = __ldg(p + res), v[a][3] = __ldg(p + res + 1);
         v[a][4] = __ldg(p + r2), v[a][5] = __ldg(p + r2 + 1);
         v[a][6] = __ldg(p + r2 + res), v[a][7] = __ldg(p + r2 + res + 1);
-      } else {  // points outside the box (masked by the selector afterwards): the reference's wrap
-        uint32_t idx[8];
-        cell_indices(c.g, res, size, 0u, false, idx);
+      } else {  // points outside the box (masked by the selector afterwards): the reference's wrap, out of line - it
+                // is rare, and eight inlined integer modulos per level were 600 SASS instructions
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[a][k] = __ldg(tl + idx[k]);
+        for (int k = 0; k < 8; ++k) v[a][k] = __ldg(tl + wrapped_corner(base, k, res, r2, size));
       }
     }
   }
