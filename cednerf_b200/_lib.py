@@ -54,6 +54,7 @@ _SIGNATURES = {
     "cednerf_sort_boundaries": "pplippp",
     "cednerf_occ_pack_bits": "plpp",
     "cednerf_occ_threshold_pack": "plpppp",
+    "cednerf_occ_mark_invisible": "pipiipiiiifpp",
     "cednerf_march": "ipplppiippffffippppppppppppppppppppppip",
     "cednerf_march_fill_runs": "lppppiffppppp",
     "cednerf_exclusive_scan": "plppppp",

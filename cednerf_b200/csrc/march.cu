@@ -495,6 +495,89 @@ CEDNERF_EXPORT int cednerf_occ_threshold_pack(const float* occs, int64_t n_cells
   return cednerf_check_launch("cednerf_occ_threshold_pack");
 }
 
+namespace {
+
+// OccGridEstimator.mark_invisible_cells (nerfacc; called at train_real.py:205-211): a cell (its lower corner mapped with
+// coord / (res - 1), as nerfacc does) stays valid (occs = 0) when at least one camera sees it at depth >= near_plane
+// and no camera sees it closer than near_plane; every other cell gets occs = -1 and is never sampled or updated again.
+// One thread per cell, cameras staged through shared memory; every product and sum is individually rounded in the
+// order oracle/nerfacc_ref.py fixes, so the result is bit-comparable.
+__global__ void __launch_bounds__(256) occ_mark_invisible_kernel(const float* __restrict__ K, int n_K,
+                                                                 const float* __restrict__ c2w, int n_cams, int c2w_rows,
+                                                                 const float* __restrict__ aabbs, int res,
+                                                                 int64_t cells_per_level, int64_t n_cells, float width,
+                                                                 float height, float near, float* __restrict__ occs) {
+  __shared__ float cam[64][21];  // w2c_R (9), w2c_T (3), K (9)
+  const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = cell < n_cells;
+  float xw[3] = {0.f, 0.f, 0.f};
+  if (active) {
+    const int level = (int)(cell / cells_per_level);
+    const int64_t c = cell - (int64_t)level * cells_per_level;
+    const int coord[3] = {(int)(c / ((int64_t)res * res)), (int)((c / res) % res), (int)(c % res)};
+    const float* bx = aabbs + 6 * level;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float x01 = __fdiv_rn((float)coord[k], (float)(res - 1));
+      xw[k] = __fadd_rn(bx[k], __fmul_rn(x01, __fsub_rn(bx[3 + k], bx[k])));
+    }
+  }
+  bool covered = false, too_near = false;
+  for (int c0 = 0; c0 < n_cams; c0 += 64) {
+    const int nc = n_cams - c0 < 64 ? n_cams - c0 : 64;
+    __syncthreads();
+    for (int q = threadIdx.x; q < nc; q += blockDim.x) {
+      const float* m = c2w + (int64_t)(c0 + q) * c2w_rows * 4;
+      const float* k = K + (n_K == 1 ? 0 : (int64_t)(c0 + q) * 9);
+      float* d = cam[q];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) d[3 * i + j] = m[4 * j + i];  // w2c_R = R^T
+        d[9 + i] = -__fadd_rn(__fadd_rn(__fmul_rn(m[i], m[3]), __fmul_rn(m[4 + i], m[7])), __fmul_rn(m[8 + i], m[11]));
+      }
+#pragma unroll
+      for (int j = 0; j < 9; ++j) d[12 + j] = k[j];
+    }
+    __syncthreads();
+    if (active) {
+      for (int q = 0; q < nc; ++q) {
+        const float* d = cam[q];
+        float xc[3], uvd[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          xc[i] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(d[3 * i], xw[0]), __fmul_rn(d[3 * i + 1], xw[1])),
+                                      __fmul_rn(d[3 * i + 2], xw[2])),
+                            d[9 + i]);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          uvd[i] = __fadd_rn(__fadd_rn(__fmul_rn(d[12 + 3 * i], xc[0]), __fmul_rn(d[12 + 3 * i + 1], xc[1])),
+                             __fmul_rn(d[12 + 3 * i + 2], xc[2]));
+        const float u = __fdiv_rn(uvd[0], uvd[2]), v = __fdiv_rn(uvd[1], uvd[2]);
+        const bool in_image = uvd[2] >= 0.f && u >= 0.f && u < width && v >= 0.f && v < height;
+        covered = covered || (uvd[2] >= near && in_image);
+        too_near = too_near || (uvd[2] < near && in_image);
+      }
+    }
+  }
+  if (active) occs[cell] = (covered && !too_near) ? 0.f : -1.f;
+}
+
+}  // namespace
+
+// K: [n_K, 3, 3] with n_K == 1 (shared intrinsics) or n_cams; c2w: [n_cams, c2w_rows (3 or 4), 4]; occs: [L * res^3].
+CEDNERF_EXPORT int cednerf_occ_mark_invisible(const float* K, int n_K, const float* c2w, int n_cams, int c2w_rows,
+                                              const float* aabbs, int n_levels, int resolution, int width, int height,
+                                              float near_plane, float* occs, void* stream) {
+  CEDNERF_REQUIRE(K && c2w && aabbs && occs, "null argument");
+  CEDNERF_REQUIRE(n_cams >= 1 && (n_K == 1 || n_K == n_cams) && (c2w_rows == 3 || c2w_rows == 4), "bad camera arrays");
+  CEDNERF_REQUIRE(n_levels >= 1 && resolution >= 2, "bad grid");
+  const int64_t cpl = (int64_t)resolution * resolution * resolution, n_cells = cpl * n_levels;
+  occ_mark_invisible_kernel<<<cednerf_blocks(n_cells, 256), 256, 0, (cudaStream_t)stream>>>(
+      K, n_K, c2w, n_cams, c2w_rows, aabbs, resolution, cpl, n_cells, (float)width, (float)height, near_plane, occs);
+  return cednerf_check_launch("cednerf_occ_mark_invisible");
+}
+
 // March one pass.  fill == 0: count only (n_intervals / n_samples / termination).  fill == 1: write the
 // outputs at the offsets given by iv_starts / sm_starts.  near/far: per-ray arrays or null (constants).
 CEDNERF_EXPORT int cednerf_march(int fill, const float* rays_o, const float* rays_d, int64_t n_rays,

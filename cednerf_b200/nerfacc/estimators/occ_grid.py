@@ -88,6 +88,20 @@ class OccGridEstimator(torch.nn.Module):
         return ridx, t0, t1
 
     @torch.no_grad()
+    def mark_invisible_cells(self, K, c2w, width: int, height: int, near_plane: float = 0.0, chunk: int = 32 ** 3):
+        """nerfacc's call of train_real.py:205-211: occs = -1 for cells outside every camera frustum (or closer than
+        near_plane to one); `_update` never touches them again.  `chunk` is accepted and ignored (one launch)."""
+        assert K.dim() == 3 and K.shape[1:] == (3, 3)
+        assert c2w.dim() == 3 and (c2w.shape[1:] == (3, 4) or c2w.shape[1:] == (4, 4))
+        assert K.shape[0] == c2w.shape[0] or K.shape[0] == 1
+        dev = self.device
+        K, c2w = K.to(dev, torch.float32).contiguous(), c2w.to(dev, torch.float32).contiguous()
+        ops.call("cednerf_occ_mark_invisible", ops.ptr(K), K.shape[0], ops.ptr(c2w), c2w.shape[0], c2w.shape[1],
+                 ops.ptr(self.aabbs), self.levels, int(self.resolution[0]), int(width), int(height), float(near_plane),
+                 ops.ptr(self.occs), ops.stream())
+        self.occs.add_(0)  # bump the version: `occs.mean()` is cached per version for `.sampling`
+
+    @torch.no_grad()
     def update_every_n_steps(self, step: int, occ_eval_fn: Callable, occ_thre: float = 1e-2, ema_decay: float = 0.95,
                              warmup_steps: int = 256, n: int = 16, rng=None):
         if not self.training:

@@ -50,6 +50,12 @@ int cednerf_occ_pack_bits(const uint8_t* binaries, int64_t n_cells, uint32_t* bi
 /* binaries = occs > *threshold_dev, plus the bit field (last line of OccGridEstimator._update; train_real.py:332-336) */
 int cednerf_occ_threshold_pack(const float* occs, int64_t n_cells, const float* threshold_dev, uint8_t* binaries,
                                uint32_t* bits, void* stream);
+/* OccGridEstimator.mark_invisible_cells(K, c2w, width, height, near_plane) — train_real.py:205-211 (nerfacc): occs = -1
+ * for cells no camera sees at depth >= near_plane or some camera sees closer than that, else 0.
+ * K [n_K,3,3] (n_K == 1 or n_cams), c2w [n_cams, c2w_rows (3|4), 4], occs [n_levels * resolution^3]. */
+int cednerf_occ_mark_invisible(const float* K, int n_K, const float* c2w, int n_cams, int c2w_rows, const float* aabbs,
+                               int n_levels, int resolution, int width, int height, float near_plane, float* occs,
+                               void* stream);
 /* nerfacc.traverse_grids — cednerf/utils.py:245-264 (eval) and inside OccGridEstimator.sampling,
  * cednerf/utils.py:115-125 (train).  fill == 0 counts (n_intervals / n_samples / termination);
  * fill == 1 writes at iv_starts / sm_starts.  near/far: per-ray arrays or (nullable) -> the constants.

@@ -392,6 +392,34 @@ class OccGridEstimator(torch.nn.Module):
         return ridx, t0, t1
 
     @torch.no_grad()
+    def mark_invisible_cells(self, K, c2w, width, height, near_plane=0.0, chunk=32 ** 3):
+        """nerfacc OccGridEstimator.mark_invisible_cells, called at train_real.py:205-211 [UPSTREAM, restated from nerfacc
+        0.5.x: parity unpinned].  Cells are taken at coord / (res - 1); a cell is valid (occs = 0) when some camera sees
+        it at depth >= near_plane and no camera sees it closer; otherwise occs = -1.  The 3x3 products are written out
+        term by term (left-to-right sums, every operation rounded in fp32) so the CUDA kernel can be bit-compared."""
+        K, c2w = K.float().cpu(), c2w.float().cpu()
+        n_cams = c2w.shape[0]
+        rt = c2w[:, :3, :3].transpose(2, 1)                      # w2c_R
+        t = c2w[:, :3, 3]
+        w2c_t = -((rt[:, :, 0] * t[:, 0:1] + rt[:, :, 1] * t[:, 1:2]) + rt[:, :, 2] * t[:, 2:3])   # [C,3]
+        kk = K.expand(n_cams, 3, 3)
+        res = self.resolution.float()
+        for lvl in range(self.levels):
+            for i in range(0, self.cells_per_lvl, chunk):
+                x = self.grid_coords[i:i + chunk].float() / (res - 1)
+                xw = self.aabbs[lvl, :3] + x * (self.aabbs[lvl, 3:] - self.aabbs[lvl, :3])           # [M,3]
+                xc = [((rt[:, j, 0:1] * xw[None, :, 0] + rt[:, j, 1:2] * xw[None, :, 1]) + rt[:, j, 2:3] * xw[None, :, 2])
+                      + w2c_t[:, j:j + 1] for j in range(3)]                                            # 3 x [C,M]
+                uvd = [(kk[:, j, 0:1] * xc[0] + kk[:, j, 1:2] * xc[1]) + kk[:, j, 2:3] * xc[2] for j in range(3)]
+                u, v = uvd[0] / uvd[2], uvd[1] / uvd[2]
+                in_image = (uvd[2] >= 0) & (u >= 0) & (u < width) & (v >= 0) & (v < height)
+                covered = ((uvd[2] >= near_plane) & in_image).any(0)
+                too_near = ((uvd[2] < near_plane) & in_image).any(0)
+                valid = covered & ~too_near
+                base = lvl * self.cells_per_lvl + i
+                self.occs[base:base + valid.numel()] = torch.where(valid, 0.0, -1.0)
+
+    @torch.no_grad()
     def update_every_n_steps(self, step, occ_eval_fn, occ_thre=1e-2, ema_decay=0.95, warmup_steps=256, n=16,
                              rng: Optional[HostRng] = None):
         if step % n == 0 and self.training:
