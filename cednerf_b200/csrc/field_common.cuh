@@ -35,7 +35,14 @@ __device__ __forceinline__ void run_chain(const CednerfMlpDesc& d, const uint8_t
       for (int k = 0; k < K / 16; ++k) umma(tmem_grp, ad + 2 * k, bd + 2 * k, id, k > 0);
       umma_commit(bar);
     }
-    mbar_wait(bar, phase);
+    // one warp of the group polls the mbarrier; the other three block on the group's named barrier, which costs no
+    // issue slots (four polling warps per tile were 14 % of the kernel's executed instructions)
+    if ((gtid >> 5) == 0) {
+      mbar_wait(bar, phase);
+      tc_fence_after();
+      tc_fence_before();
+    }
+    group_sync(group);
     phase ^= 1;
     tc_fence_after();
     if (l < L - 1) {
@@ -95,6 +102,14 @@ __device__ __noinline__ uint32_t wrapped_corner(uint32_t base, int k, uint32_t r
   return h >= size ? h % size : h;
 }
 
+// table[idx] with the address formed by ONE 64-bit multiply-add (the compiler otherwise folds the level offset into
+// every corner's index and spends five instructions per address on 64-bit carries)
+__device__ __forceinline__ __half2 gather_h2(const __half2* base, uint32_t idx) {
+  uint64_t addr;
+  asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(addr) : "r"(idx), "l"(base));
+  return __ldg(reinterpret_cast<const __half2*>(addr));
+}
+
 // the 8*LG gathers of levels l_first .. l_first+LG-1 (fractions kept for the weights)
 template <int LG>
 __device__ __forceinline__ void hash_issue(const float* xn, const __half* __restrict__ table, const CednerfGridLevels& lv,
@@ -105,7 +120,8 @@ __device__ __forceinline__ void hash_issue(const float* xn, const __half* __rest
     const Cell c = locate(xn, lv.scale[l]);
     frac[a][0] = c.f[0], frac[a][1] = c.f[1], frac[a][2] = c.f[2];
     const uint32_t res = lv.res[l], size = lv.size[l];
-    const __half2* tl = reinterpret_cast<const __half2*>(table) + lv.offset[l];
+    const __half2* tl;  // this level's table, as one opaque 64-bit value
+    asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(tl) : "r"(lv.offset[l]), "l"(table));
     if (lv.hashed[l]) {  // power-of-two table: (x ^ y P1 ^ z P2) & mask == (x & mask) ^ (y P1 & mask) ^ (z P2 & mask)
       const uint32_t mask = size - 1u;
       const uint32_t y0 = c.g[1] * 2654435761u, z0 = c.g[2] * 805459861u;
@@ -113,7 +129,7 @@ __device__ __forceinline__ void hash_issue(const float* xn, const __half* __rest
       const uint32_t hy[2] = {y0 & mask, (y0 + 2654435761u) & mask};
       const uint32_t hz[2] = {z0 & mask, (z0 + 805459861u) & mask};
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[a][k] = __ldg(tl + (hx[k & 1] ^ hy[(k >> 1) & 1] ^ hz[k >> 2]));
+      for (int k = 0; k < 8; ++k) v[a][k] = gather_h2(tl, hx[k & 1] ^ hy[(k >> 1) & 1] ^ hz[k >> 2]);
     } else {
       const uint32_t r2 = res * res;
       const uint32_t base = c.g[0] + c.g[1] * res + c.g[2] * r2;

@@ -553,7 +553,12 @@ __global__ void __launch_bounds__(BWD_GROUPS * MLP_TILE, 1) field_bwd_kernel(Tra
         if (l > 1) load_tile_async(ibuf[cur ^ 1], hidden + ((int64_t)(l - 2) * n + row0) * 64, 64, rows_valid, gtid, MLP_TILE);
         else make_input<NET>(a, sl, ibuf[cur ^ 1], gtid, s, ok);
       }
-      mbar_wait(bar, phase);
+      if ((gtid >> 5) == 0) {  // one polling warp per group, the others block on the named barrier
+        mbar_wait(bar, phase);
+        tc_fence_after();
+        tc_fence_before();
+      }
+      group_sync(group);
       phase ^= 1;
       tc_fence_after();
       if (l > 0) {
