@@ -23,7 +23,8 @@ __device__ __forceinline__ void group_sync(int group) { asm volatile("bar.sync %
 // The last layer's accumulator is left in TMEM columns [0, N_last) of this group's TMEM slice.
 __device__ __forceinline__ void run_chain(const CednerfMlpDesc& d, const uint8_t* wimg, uint8_t* abuf, uint32_t tmem_grp,
                                           uint32_t tmem_warp, uint64_t* bar, uint32_t& phase, int gtid, int group,
-                                          __half* save = nullptr, int64_t save_layer_stride = 0, int64_t save_row = -1) {
+                                          __half* save = nullptr, int64_t save_layer_stride = 0, int64_t save_row0 = 0,
+                                          int save_rows = 0, uint8_t* save_in = nullptr) {
   const int L = d.n_layers;
   for (int l = 0; l < L; ++l) {
     const int K = d.dim_in[l], N = d.dim_out[l];
@@ -34,6 +35,26 @@ __device__ __forceinline__ void run_chain(const CednerfMlpDesc& d, const uint8_t
       const uint32_t id = make_idesc(128, N, 0, 0);
       for (int k = 0; k < K / 16; ++k) umma(tmem_grp, ad + 2 * k, bd + 2 * k, id, k > 0);
       umma_commit(bar);
+    }
+    if (save_in && l == 0) {  // the network's input tile ([rows, K] fp16), copied out the same cooperative way
+      const int cpr = K >> 3;
+      uint4* dst = reinterpret_cast<uint4*>(save_in + save_row0 * K * 2);
+      for (int q = gtid; q < MLP_TILE * cpr; q += MLP_TILE) {
+        const int r = q / cpr, c = q - r * cpr;
+        if (r < save_rows) dst[q] = *reinterpret_cast<const uint4*>(abuf + swz(r, c));
+      }
+    }
+    if (save && l > 0) {
+      // post-ReLU activations of the previous layer, kept for the backward pass: the tile this layer's MMA is reading
+      // is copied out cooperatively while it runs - consecutive threads write consecutive 16-byte chunks of the
+      // row-major [rows, 64] fp16 matrix (512 contiguous bytes per warp instruction; one 128-byte row per thread made
+      // every store instruction touch 32 half-filled sectors).  Nobody overwrites the tile before the barrier below.
+      uint4* dst = reinterpret_cast<uint4*>(save + (l - 1) * save_layer_stride + save_row0 * 64);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int q = i * MLP_TILE + gtid, r = q >> 3, c = q & 7;
+        if (r < save_rows) dst[q] = *reinterpret_cast<const uint4*>(abuf + swz(r, c));
+      }
     }
     // one warp of the group polls the mbarrier; the other three block on the group's named barrier, which costs no
     // issue slots (four polling warps per tile were 14 % of the kernel's executed instructions)
@@ -56,11 +77,6 @@ __device__ __forceinline__ void run_chain(const CednerfMlpDesc& d, const uint8_t
         for (int j = 0; j < 8; ++j) p[j] = pack_relu_h2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
         *reinterpret_cast<uint4*>(abuf + swz(gtid, 2 * cb)) = make_uint4(p[0], p[1], p[2], p[3]);
         *reinterpret_cast<uint4*>(abuf + swz(gtid, 2 * cb + 1)) = make_uint4(p[4], p[5], p[6], p[7]);
-        if (save && save_row >= 0) {  // post-ReLU activations kept for the backward pass (one 128-byte row per thread)
-          uint4* dst = reinterpret_cast<uint4*>(save + l * save_layer_stride + save_row * 64 + cb * 16);
-          dst[0] = make_uint4(p[0], p[1], p[2], p[3]);
-          dst[1] = make_uint4(p[4], p[5], p[6], p[7]);
-        }
       }
       fence_proxy_async();
       tc_fence_before();

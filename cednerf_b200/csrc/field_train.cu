@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(768, 1) field_train_fwd_kernel(TrainArgs a) {
   for (int64_t tile = blockIdx.x + (int64_t)gridDim.x * group; tile < n_tiles; tile += (int64_t)gridDim.x * n_groups) {
     const int64_t s = tile * MLP_TILE + gtid;
     const bool ok = s < n;
-    const int64_t srow = ok ? s : -1;
+    const int rows_valid = (int)((n - tile * MLP_TILE) < MLP_TILE ? (n - tile * MLP_TILE) : MLP_TILE);
     float x[3] = {0.f, 0.f, 0.f}, tv = 0.f;
     int64_t ray = 0;
     if (ok) packed_sample(a.ridx, a.t0, a.t1, a.rays_o, a.rays_d, a.t, a.t_stride, s, x, tv, ray);
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(768, 1) field_train_fwd_kernel(TrainArgs a) {
     tc_fence_before();
     group_sync(group);
     run_chain(d.f1, w1, abuf, tmem_base, tmem_warp, bar, phase, gtid, group, reinterpret_cast<__half*>(a.saved + sl.h1),
-              n * 64, srow);
+              n * 64, tile * MLP_TILE, rows_valid);
     float xn[3], mv[3], mvnorm;
     bool selector;
     {
@@ -208,16 +208,13 @@ __global__ void __launch_bounds__(768, 1) field_train_fwd_kernel(TrainArgs a) {
         w = L + 5;
       }
       for (; 2 * w < k2; ++w) put_word(w, one2);
-      if (ok) {  // keep this thread's operand row for the backward pass (weight gradient of the first density layer)
-        uint4* dst = reinterpret_cast<uint4*>(a.saved + sl.in2 + s * k2 * 2);
-        for (int c = 0; c * 8 < k2; ++c) dst[c] = *reinterpret_cast<const uint4*>(abuf + swz(gtid, c));
-      }
     }
     fence_proxy_async();
     tc_fence_before();
     group_sync(group);
+    // (the density net's input rows are kept too: weight gradient of its first layer, huber target of the predictor)
     run_chain(d.f2, w2, abuf, tmem_base, tmem_warp, bar, phase, gtid, group, reinterpret_cast<__half*>(a.saved + sl.h2),
-              n * 64, srow);
+              n * 64, tile * MLP_TILE, rows_valid, a.saved + sl.in2);
     {
       uint32_t o2[16];
       tmem_ld16(tmem_warp, o2);
@@ -242,7 +239,7 @@ __global__ void __launch_bounds__(768, 1) field_train_fwd_kernel(TrainArgs a) {
     tc_fence_before();
     group_sync(group);
     run_chain(d.f3, w3, abuf, tmem_base, tmem_warp, bar, phase, gtid, group, reinterpret_cast<__half*>(a.saved + sl.h3),
-              n * 64, srow);
+              n * 64, tile * MLP_TILE, rows_valid);
     {
       uint32_t r[16];
       tmem_ld16(tmem_warp, r);
@@ -259,7 +256,7 @@ __global__ void __launch_bounds__(768, 1) field_train_fwd_kernel(TrainArgs a) {
       tc_fence_before();
       group_sync(group);
       run_chain(d.f4, w4, abuf, tmem_base, tmem_warp, bar, phase, gtid, group, reinterpret_cast<__half*>(a.saved + sl.h4),
-                n * 64, srow);
+                n * 64, tile * MLP_TILE, rows_valid);
 #pragma unroll
       for (int cb = 0; cb < 2; ++cb) {
         uint32_t r[16];
