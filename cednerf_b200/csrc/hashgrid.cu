@@ -238,16 +238,30 @@ hashgrid_bwd_table_kernel(const float* __restrict__ x, int x_stride, int64_t n, 
     // scan depth follows the longest run in the warp: 0 steps at fine levels (every lane its own run), 5 at the coarsest
     const int max_len = __reduce_max_sync(0xffffffffu, lane - run_start + 1);
     // corners come in x-pairs (k, k+1): when the two table entries form an aligned 16-byte pair (dense levels: even
-    // index; hashed levels: even x, because the x term of the hash is x itself) one 16-byte reduction carries both
+    // index; hashed levels: even x, because the x term of the hash is x itself) one 16-byte reduction carries both.
+    // Weights and indices with shared sub-expressions (cell_weights; hashed: per-axis terms masked once, one xor per
+    // corner; dense: base + offsets unless a corner wraps) - same values as corner_weight / corner_index.
+    float w8[8];
+    cell_weights(c.f, w8);
+    uint32_t hy[2], hz[2], x0, x1;
+    bool plain;  // indices are (x0 | x1) combined with hy / hz by xor (hashed) or by addition (dense, no wrap)
+    if (hashed) {
+      const uint32_t mask = size - 1u;
+      const uint32_t y0 = c.g[1] * 2654435761u, z0 = c.g[2] * 805459861u;
+      x0 = c.g[0] & mask, x1 = (c.g[0] + 1u) & mask;
+      hy[0] = y0 & mask, hy[1] = (y0 + 2654435761u) & mask;
+      hz[0] = z0 & mask, hz[1] = (z0 + 805459861u) & mask;
+      plain = true;
+    } else {
+      const uint32_t r2 = res * res;
+      x0 = c.g[0] + c.g[1] * res + c.g[2] * r2, x1 = x0 + 1u;
+      hy[0] = 0u, hy[1] = res, hz[0] = 0u, hz[1] = r2;
+      plain = x0 < size - (1u + res + r2);
+    }
 #pragma unroll
     for (int kp = 0; kp < 4; ++kp) {
       float v[4];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const float w = corner_weight(c, 2 * kp + h);
-        v[2 * h] = w * d0;
-        v[2 * h + 1] = w * d1;
-      }
+      v[0] = w8[2 * kp] * d0, v[1] = w8[2 * kp] * d1, v[2] = w8[2 * kp + 1] * d0, v[3] = w8[2 * kp + 1] * d1;
       for (int o = 1; o < max_len; o <<= 1) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -256,9 +270,18 @@ hashgrid_bwd_table_kernel(const float* __restrict__ x, int x_stride, int64_t n, 
         }
       }
       if (tail) {
-        const uint32_t gy = c.g[1] + (kp & 1), gz = c.g[2] + (kp >> 1);
-        const uint32_t i0 = corner_index(c.g[0], gy, gz, res, size, hashed);
-        const uint32_t i1 = corner_index(c.g[0] + 1, gy, gz, res, size, hashed);
+        uint32_t i0, i1;
+        if (hashed) {
+          const uint32_t yz = hy[kp & 1] ^ hz[kp >> 1];
+          i0 = x0 ^ yz, i1 = x1 ^ yz;
+        } else if (plain) {
+          const uint32_t yz = hy[kp & 1] + hz[kp >> 1];
+          i0 = x0 + yz, i1 = x1 + yz;
+        } else {
+          const uint32_t gy = c.g[1] + (kp & 1), gz = c.g[2] + (kp >> 1);
+          i0 = corner_index(c.g[0], gy, gz, res, size, false);
+          i1 = corner_index(c.g[0] + 1, gy, gz, res, size, false);
+        }
         if (!CACHED && (i0 ^ i1) == 1u && ((off & 1u) == 0u)) {
           const bool even = (i0 & 1u) == 0u;
           const float4 val = even ? make_float4(v[0], v[1], v[2], v[3]) : make_float4(v[2], v[3], v[0], v[1]);
@@ -281,13 +304,15 @@ hashgrid_bwd_table_kernel(const float* __restrict__ x, int x_stride, int64_t n, 
   }
 }
 
-// dense levels -> cached pass (long chunks), hashed levels -> direct pass (one block of 256 samples per CTA)
+// small dense levels -> cached pass (long chunks), the others -> direct pass (one block of 256 samples per CTA)
 template <typename GradT, bool LEVEL_MAJOR>
 int launch_table_gradient(const float* x, int x_stride, int64_t n, const CednerfGridLevels& lv, const GradT* dy, int dy_stride,
                           float* g_table, cudaStream_t st) {
   LevelList cached{}, direct{};
   for (int l = 0; l < lv.n_levels; ++l) {
-    LevelList& dst = lv.hashed[l] ? direct : cached;
+    // the cache pays where a level has few entries (heavy per-address contention in L2); from 2^20 entries on - hashed
+    // levels and the finest dense one - the direct reductions already run at the L2 reduction rate (measured per level)
+    LevelList& dst = (lv.hashed[l] || lv.size[l] >= (1u << 20)) ? direct : cached;
     dst.id[dst.n++] = l;
   }
   int launches = 0;
