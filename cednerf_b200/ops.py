@@ -398,6 +398,7 @@ class RenderWeightFunction(torch.autograd.Function):
              ptr(w), ptr(tr), ptr(al), None, None, None, None, 0, 0.0, stream())
         ctx.save_for_backward(t0, t1, tr, al, offsets)
         ctx.n_rays = n_rays
+        ctx.set_materialize_grads(False)
         return w, tr, al
 
     @staticmethod
@@ -421,10 +422,13 @@ class AccumulateFunction(torch.autograd.Function):
         call("cednerf_accumulate_fwd", ptr(w), ptr(v), c, ptr(offsets), w.numel(), n_rays, ptr(out), 0, stream())
         ctx.save_for_backward(w, v if v is not None else w, ray_indices)
         ctx.has_v, ctx.c = v is not None, c
+        ctx.set_materialize_grads(False)
         return out
 
     @staticmethod
     def backward(ctx, g):
+        if g is None:
+            return None, None, None, None, None
         w, v, ridx = ctx.saved_tensors
         v = v if ctx.has_v else None
         g = _f32c(g)
@@ -475,6 +479,7 @@ class CompositeFunction(torch.autograd.Function):
              n_rays, ptr(w), ptr(tr), ptr(al), ptr(colors), ptr(opac), ptr(depth), ptr(draw), 0, eps, stream())
         ctx.save_for_backward(t0, t1, rgb, tr, al, offsets, opac, draw, bk if bk is not None else t0)
         ctx.has_bk, ctx.stride, ctx.n_rays, ctx.eps = bk is not None, stride, n_rays, eps
+        ctx.set_materialize_grads(False)  # unused outputs (weights / trans / alphas ...) arrive as None, not as zero fills
         return colors, opac, depth, w, tr, al
 
     @staticmethod
@@ -604,6 +609,7 @@ class FieldTrainFunction(torch.autograd.Function):
         ctx.desc, ctx.t_stride, ctx.has4 = desc, int(t_stride), images[3] is not None and want_latent
         ctx.shapes = (p1.shape, p2.shape, p3.shape, None if p4 is None else p4.shape, table.shape)
         ctx.mark_non_differentiable(selector, move)
+        ctx.set_materialize_grads(False)
         if latent is None:
             latent = torch.zeros(0, device=dev)
         return sigma, rgb, latent, selector, move
@@ -615,8 +621,17 @@ class FieldTrainFunction(torch.autograd.Function):
         lib = _lib.load()
         n, dev = t0.numel(), t0.device
         s1, s2, s3, s4, st = ctx.shapes
-        g1, g2, g3 = (torch.zeros(s, dtype=F32, device=dev) for s in (s1, s2, s3))
-        g4 = torch.zeros(s4, dtype=F32, device=dev) if (ctx.has4 and s4 is not None) else None
+        # the MLP weight gradients share one zero-filled buffer (one fill launch instead of four)
+        want4 = ctx.has4 and s4 is not None
+        sizes = [math.prod(s) for s in (s1, s2, s3)] + ([math.prod(s4)] if want4 else [])
+        padded = [(k + 3) // 4 * 4 for k in sizes]  # 16-byte aligned slices
+        pool = torch.zeros(sum(padded), dtype=F32, device=dev)
+        views, o = [], 0
+        for k, kp, shp in zip(sizes, padded, (s1, s2, s3) + ((s4,) if want4 else ())):
+            views.append(pool[o:o + k].view(shp))
+            o += kp
+        g1, g2, g3 = views[:3]
+        g4 = views[3] if want4 else None
         gt = torch.zeros(st, dtype=F32, device=dev)
         d_sigma = torch.zeros(n, device=dev) if d_sigma is None else _f32c(d_sigma)
         d_rgb = torch.zeros(n, 3, device=dev) if d_rgb is None else _f32c(d_rgb)
