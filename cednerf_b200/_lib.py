@@ -71,7 +71,7 @@ _SIGNATURES = {
     "cednerf_mlp_pack_weights": "pMpp",
     "cednerf_mlp_fwd": "ppMlppp",
     "cednerf_mlp_bwd": "ppppMlpippp",
-    "cednerf_field_fwd": "ppppppppilppppFppp",
+    "cednerf_field_fwd": "ppppppppilppppFpppp",
     "cednerf_field_train_fwd": "ppppppilpppppFppppppp",
     "cednerf_field_train_bwd": "ppppppilpppppFpppppppppppppip",
     "cednerf_ray_offsets": "pllpp",

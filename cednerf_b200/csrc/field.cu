@@ -27,6 +27,7 @@ struct FieldFwdArgs {
   const float* t;       // timestamps: [n_rays] when ridx != null else [n]; stride 0 = one value for all
   int t_stride;
   int64_t n;
+  const int64_t* n_dev;  // nullable: the live sample count on the device (n is then the capacity of the buffers)
   const uint8_t* img1;
   const uint8_t* img2;
   const uint8_t* img3;
@@ -74,14 +75,19 @@ __global__ void __launch_bounds__(896, 1) field_fwd_kernel(FieldFwdArgs a) {
   const uint32_t tmem_base = tmem_base_s + 64u * (uint32_t)group;
   const uint32_t tmem_warp = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   uint32_t phase = 0;
-  const int64_t n_tiles = (a.n + MLP_TILE - 1) / MLP_TILE;
+  int64_t n_live = a.n;
+  if (a.n_dev) {
+    const int64_t nd = *a.n_dev;
+    n_live = nd < a.n ? nd : a.n;
+  }
+  const int64_t n_tiles = (n_live + MLP_TILE - 1) / MLP_TILE;
   const float ms = d.moving_step;
   const int L = d.levels.n_levels;
   const uint32_t one2 = 0x3C003C00u;  // half2(1, 1): tcnn's input padding value
 
   for (int64_t tile = blockIdx.x + (int64_t)gridDim.x * group; tile < n_tiles; tile += (int64_t)gridDim.x * n_groups) {
     const int64_t s = tile * MLP_TILE + gtid;
-    const bool ok = s < a.n;
+    const bool ok = s < n_live;
     // ---- the sample: position, time, direction (cednerf/utils.py:74-104) -------------------------------------
     float x[3] = {0.f, 0.f, 0.f}, tv = 0.f;
     if (ok) {
@@ -245,12 +251,15 @@ int check_field(const CednerfFieldDesc* d, bool want_rgb) {
 // sigma (and rgb) of n samples.  Samples are either packed ray samples (ray_indices, t_starts, t_ends, rays_o,
 // rays_d; timestamps indexed by ray) or explicit points (x, dirs; timestamps indexed by point); t_stride 0 = one
 // timestamp for all (the reference's eval path, cednerf/utils.py:187-191).  rgb == NULL: density only (the sigma_fn
-// pre-pass of OccGridEstimator.sampling and occ_eval_fn).
+// pre-pass of OccGridEstimator.sampling and occ_eval_fn).  n_device (nullable): the number of live samples is read from
+// device memory (min(n, *n_device)); n is then only the capacity of the buffers - the marching rounds of
+// render_image_test use it to skip the host read of each round's sample total.
 CEDNERF_EXPORT int cednerf_field_fwd(const int64_t* ray_indices, const float* t_starts, const float* t_ends,
                                      const float* rays_o, const float* rays_d, const float* x, const float* dirs,
                                      const float* timestamps, int t_stride, int64_t n, const void* image_deform,
                                      const void* image_density, const void* image_colour, const void* table_f16,
-                                     const CednerfFieldDesc* desc, float* sigma, float* rgb, void* stream) {
+                                     const CednerfFieldDesc* desc, float* sigma, float* rgb, const int64_t* n_device,
+                                     void* stream) {
   CEDNERF_REQUIRE(check_field(desc, rgb != nullptr), "bad field descriptor");
   CEDNERF_REQUIRE(n >= 0 && sigma && timestamps, "bad arguments");
   CEDNERF_REQUIRE((ray_indices && t_starts && t_ends && rays_o && rays_d) || (!ray_indices && x), "need packed samples or points");
@@ -271,7 +280,7 @@ CEDNERF_EXPORT int cednerf_field_fwd(const int64_t* ray_indices, const float* t_
     configured = true;
   }
   CEDNERF_REQUIRE(smem <= 224 * 1024, "networks too large for the fused kernel");
-  FieldFwdArgs a{ray_indices, t_starts, t_ends, rays_o, rays_d, x, dirs, timestamps, t_stride, n,
+  FieldFwdArgs a{ray_indices, t_starts, t_ends, rays_o, rays_d, x, dirs, timestamps, t_stride, n, n_device,
                  (const uint8_t*)image_deform, (const uint8_t*)image_density, (const uint8_t*)image_colour,
                  (const __half*)table_f16, sigma, rgb, *desc};
   const int64_t tiles = (n + MLP_TILE - 1) / MLP_TILE;

@@ -104,11 +104,11 @@ class DNGPradianceField(torch.nn.Module):
         return self._fdesc
 
     @torch.no_grad()
-    def fused_query(self, n, packed=None, points=None, timestamps=None, t_stride=1, sigma_only=True):
+    def fused_query(self, n, packed=None, points=None, timestamps=None, t_stride=1, sigma_only=True, n_dev=None):
         """-> (sigma [n], rgb [n,3] | None) in one kernel; see ops.field_fwd."""
         images = (self.xyz_wrap.network.weight_image(), self.mlp_base.weight_image(), self.mlp_head.weight_image())
         return ops.field_fwd(self._field_desc(), images, self.hash_encoder.table_f16(), n, sigma_only, packed, points,
-                             timestamps, t_stride)
+                             timestamps, t_stride, n_dev)
 
     def fused_train_supported(self) -> bool:
         return (self.fused_supported() and not self.use_weight_predict

@@ -546,9 +546,10 @@ def time_embed(t: torch.Tensor, move_norm: Optional[torch.Tensor] = None) -> tor
 # fused field query (inference: density pre-pass of the sampler, occupancy updates, eval rendering)
 # ------------------------------------------------------------------------------------------------
 def field_fwd(desc: FieldDesc, images, table_f16, n: int, sigma_only: bool, packed=None, points=None,
-              timestamps=None, t_stride: int = 1):
+              timestamps=None, t_stride: int = 1, n_dev: Optional[torch.Tensor] = None):
     """packed = (ray_indices, t_starts, t_ends, rays_o, rays_d) or points = (x, dirs-or-None).
-    -> (sigma [n], rgb [n,3] or None)."""
+    -> (sigma [n], rgb [n,3] or None).  n_dev (int64 [1] on the device): only the first min(n, n_dev) entries are live
+    (computed and written); n is then the capacity of the buffers and no host read of the count is needed."""
     _lib.check_device()
     dev = table_f16.device
     sigma = torch.empty(n, device=dev)
@@ -565,7 +566,7 @@ def field_fwd(desc: FieldDesc, images, table_f16, n: int, sigma_only: bool, pack
         ds = None if dirs is None else _f32c(dirs)
         args = (None, None, None, None, None, ptr(xs), ptr(ds))
     call("cednerf_field_fwd", *args, ptr(ts), int(t_stride), n, ptr(images[0]), ptr(images[1]), ptr(images[2]),
-         ptr(table_f16), ctypes.byref(desc), ptr(sigma), ptr(rgb), stream())
+         ptr(table_f16), ctypes.byref(desc), ptr(sigma), ptr(rgb), ptr(n_dev), stream())
     return sigma, rgb
 
 

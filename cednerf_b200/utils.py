@@ -110,6 +110,11 @@ def render_image_test(max_samples, radiance_field, estimator, rays, near_plane=0
     bits = nerfacc.grid.occupancy_bits(estimator.binaries)
     res = int(estimator.binaries.shape[1])
     done = total = 0
+    # With the fused field kernel a round needs ONE host read (the reference's `alive.sum()`): the round's sample total
+    # stays on the device - outputs are sized for the bound n_alive * k and the kernels read the live count themselves.
+    fuse = (getattr(radiance_field, "fused_supported", lambda: False)() and not radiance_field.training
+            and timestamps is not None and timestamps.numel() == 1 and render_step_size > 0)
+    total_dev = torch.zeros(1, dtype=torch.int64, device=dev)
     while done < max_samples:
         n_alive = int(alive.sum())                     # the reference's host read (utils.py:231)
         if n_alive == 0:
@@ -122,17 +127,27 @@ def render_image_test(max_samples, radiance_field, estimator, rays, near_plane=0
                              render_step_size, cone_angle, k, alive, t_sorted, t_indices, hits)
         _, n_sm, term = mi.count(record_runs=True)
         starts, _, n_tot = ops.exclusive_scan(n_sm, want_packed=False)
-        n_round = int(n_tot.item())
-        if n_round:
-            if mi.runs is not None:
-                ridx, t0, t1 = mi.fill_packed_from_runs(starts, n_round)
-            else:
-                ridx, t0, t1, _ = mi.fill_packed(starts, n_round)
-            rgbs, sres = rgb_sigma_fn(t0, t1, ridx)
-            ops.composite_round_(t0, t1, sres["density"].squeeze(-1), rgbs, torch.cat([starts, n_tot]), rgb, opacity, depth)
+        if fuse and mi.runs is not None:
+            cap = n_alive * k
+            ridx, t0, t1 = mi.fill_packed_from_runs(starts, cap)
+            sigma, rgbs = radiance_field.fused_query(cap, packed=(ridx, t0, t1, rays.origins, rays.viewdirs),
+                                                     timestamps=timestamps, t_stride=0, sigma_only=False, n_dev=n_tot)
+            ops.composite_round_(t0, t1, sigma, rgbs, torch.cat([starts, n_tot]), rgb, opacity, depth)
+            total_dev += n_tot
+        else:
+            n_round = int(n_tot.item())
+            if n_round:
+                if mi.runs is not None:
+                    ridx, t0, t1 = mi.fill_packed_from_runs(starts, n_round)
+                else:
+                    ridx, t0, t1, _ = mi.fill_packed(starts, n_round)
+                rgbs, sres = rgb_sigma_fn(t0, t1, ridx)
+                ops.composite_round_(t0, t1, sres["density"].squeeze(-1), rgbs, torch.cat([starts, n_tot]), rgb, opacity,
+                                     depth)
+            total += n_round
         near = term
         alive = (opacity.view(-1) <= 1 - early_stop_eps) & (n_sm == k)
-        total += n_round
+    total += int(total_dev.item())
     rgb = rgb + render_bkgd * (1.0 - opacity)
     depth = depth / opacity.clamp_min(torch.finfo(torch.float32).eps)
     return rgb.view(*shape[:-1], -1), opacity.view(*shape[:-1], -1), depth.view(*shape[:-1], -1), total

@@ -163,7 +163,8 @@ typedef struct CednerfFieldDesc {
 int cednerf_field_fwd(const int64_t* ray_indices, const float* t_starts, const float* t_ends, const float* rays_o,
                       const float* rays_d, const float* x, const float* dirs, const float* timestamps, int t_stride,
                       int64_t n, const void* image_deform, const void* image_density, const void* image_colour,
-                      const void* table_f16, const CednerfFieldDesc* desc, float* sigma, float* rgb, void* stream);
+                      const void* table_f16, const CednerfFieldDesc* desc, float* sigma, float* rgb,
+                      const int64_t* n_device /*nullable: live sample count on the device, n = capacity*/, void* stream);
 
 /* DNGPradianceField.forward in training (cednerf/model.py:468-488, return_interal=True) on packed ray samples, and its
  * backward.  `saved` (cednerf_field_saved_bytes) carries the activations; the backward accumulates into the fp32
