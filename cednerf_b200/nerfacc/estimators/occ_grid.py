@@ -29,6 +29,11 @@ class OccGridEstimator(torch.nn.Module):
         self.register_buffer("grid_coords", coords, persistent=False)
         self.register_buffer("grid_indices", torch.arange(self.cells_per_lvl), persistent=False)
         self._occ_mean_key, self._occ_mean = None, 0.0
+        self._may_have_invisible, self._occs_seen = False, None  # occs = -1 cells exist (mark_invisible_cells, checkpoints)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._occs_seen = None  # contents replaced in place: look again at the next update
+        return super()._load_from_state_dict(*args, **kwargs)
 
     @property
     def device(self):
@@ -99,6 +104,7 @@ class OccGridEstimator(torch.nn.Module):
         ops.call("cednerf_occ_mark_invisible", ops.ptr(K), K.shape[0], ops.ptr(c2w), c2w.shape[0], c2w.shape[1],
                  ops.ptr(self.aabbs), self.levels, int(self.resolution[0]), int(width), int(height), float(near_plane),
                  ops.ptr(self.occs), ops.stream())
+        self._may_have_invisible = True
         self.occs.add_(0)  # bump the version: `occs.mean()` is cached per version for `.sampling`
 
     @torch.no_grad()
@@ -115,30 +121,47 @@ class OccGridEstimator(torch.nn.Module):
         dev, cpl = self.device, self.cells_per_lvl
         randint = (lambda hi, k: torch.randint(hi, (k,), device=dev)) if rng is None else rng.randint
         rand = (lambda *s: torch.rand(*s, device=dev)) if rng is None else rng.rand
+        # `all_valid`: no cell has been marked invisible (occs = -1 comes only from mark_invisible_cells or a loaded
+        # checkpoint), so "cells with occs >= 0" is every cell and none of the compactions below - each one a host
+        # read - is needed
+        if self._occs_seen != self.occs.data_ptr():  # buffer replaced (assignment, .to(), load): look once (one host read)
+            self._may_have_invisible = bool((self.occs < 0).any())
+            self._occs_seen = self.occs.data_ptr()
+        all_valid = not self._may_have_invisible
         lvl_indices = []
         if step < warmup_steps:
             for l in range(self.levels):
-                lvl_indices.append(self.grid_indices[self.occs[l * cpl + self.grid_indices] >= 0])
+                lvl_indices.append(None if all_valid else self.grid_indices[self.occs[l * cpl + self.grid_indices] >= 0])
         else:
             k = cpl // 4
             for l in range(self.levels):
                 uni = randint(cpl, k).to(dev)
-                uni = uni[self.occs[l * cpl + uni] >= 0]
+                if not all_valid:
+                    uni = uni[self.occs[l * cpl + uni] >= 0]
                 occ_idx = torch.nonzero(self.binaries[l].flatten())[:, 0]
                 if k < len(occ_idx):
                     occ_idx = occ_idx[randint(len(occ_idx), k).to(dev)]
                 lvl_indices.append(torch.cat([uni, occ_idx]))
         for l, idx in enumerate(lvl_indices):
-            x = (self.grid_coords[idx].float() + rand(len(idx), 3).to(dev)) / self.resolution.float()
+            coords = self.grid_coords if idx is None else self.grid_coords[idx]
+            x = (coords.float() + rand(coords.shape[0], 3).to(dev)) / self.resolution.float()
             x = self.aabbs[l, :3] + x * (self.aabbs[l, 3:] - self.aabbs[l, :3])
             occ = occ_eval_fn(x).squeeze(-1).float()
+            if idx is None:  # every cell of the level exactly once: an element-wise maximum, no scatter
+                lvl = self.occs[l * cpl:(l + 1) * cpl]
+                torch.maximum(lvl * ema_decay, occ, out=lvl)
+                continue
             cell = l * cpl + idx
             # nerfacc writes occs[cell] = max(occs[cell]*decay, occ) with an index_put whose winner among duplicate
             # cells (uniform draws that repeat or coincide with occupied cells) is undefined on CUDA; here the
             # largest candidate wins (scatter-amax), which is one of those outcomes and is deterministic.
             self.occs.scatter_reduce_(0, cell, torch.maximum(self.occs[cell] * ema_decay, occ), "amax",
                                       include_self=False)
-        thre = torch.clamp(self.occs[self.occs >= 0].mean(), max=occ_thre).reshape(1).contiguous()
+        if all_valid:
+            thre = torch.clamp(self.occs.mean(), max=occ_thre).reshape(1).contiguous()
+        else:
+            valid = self.occs >= 0
+            thre = torch.clamp((self.occs * valid).sum() / valid.sum(), max=occ_thre).reshape(1).contiguous()
         bits = torch.empty(self.occs.numel() // 32, dtype=torch.int32, device=dev)
         ops.occ_threshold_pack(self.occs, thre, self.binaries, bits)
         set_occupancy_bits(self.binaries, bits)
