@@ -263,10 +263,25 @@ def run_ours(args):
     n_host = 4
     host = [workload.draw_batch(cfg, args.rays, gen, pin=True) for _ in range(n_host)]
     resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
-    # allocator warm-up batch: the visible-sample count moves by a few % from step to step; one untimed step on 1.25 x
-    # the rays leaves cached blocks large enough that no timed step has to cudaMalloc (a training run reaches the same
-    # state after its first few hundred iterations)
-    oversized = {k: v.to(dev) for k, v in workload.draw_batch(cfg, int(args.rays * 1.25), gen).items()}
+    # allocator warm-up batches: the visible-sample count moves by a few % from step to step and the configuration sits
+    # right at 2^20 samples, a size-class boundary of the caching allocator.  Untimed forward+backward passes (no
+    # optimiser step: parameters and optimiser state stay untouched) on 1.06 x and 1.12 x the rays, run after the warm-up
+    # steps, leave free blocks of the next size classes in the cache, so the timed step in which the count crosses the
+    # boundary does not have to grow the pool (one such step took 58-110 ms).  A training run reaches the same state
+    # after its first few hundred iterations.
+    oversized = [{k: v.to(dev) for k, v in workload.draw_batch(cfg, int(args.rays * f), gen).items()} for f in (1.06, 1.12)]
+
+    def touch_size_classes():
+        for b in oversized:
+            rays_b = cb.Rays(b["origins"], b["viewdirs"])
+            rgb, acc, _, n_s, extra = cb.render_image(field, est, rays_b, render_bkgd=b["color_bkgd"],
+                                                      timestamps=b["timestamps"], jitter=b["jitter"], **rk)
+            loss = torch.nn.functional.mse_loss(rgb, b["pixels"]) + aux_losses(rgb, acc, b["pixels"], extra, cfg.flags)
+            opt.zero_grad()
+            scaler.scale(loss).backward()
+            if reducer is not None:
+                reducer.wait()
+            opt.zero_grad()
 
     def step_resident(i):
         return train_step(cb, field, est, opt, scaler, resident[i % n_host], cfg, rk, reducer, state.sched, occ)
@@ -282,11 +297,11 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def timed(fn, k):
-        train_step(cb, field, est, opt, scaler, oversized, cfg, rk, reducer)
         state.restore()          # iteration 0 again (untimed), then the warm-up steps allocate the optimiser state
         occ.step = 0
         for i in range(max(args.warmup, 3)):
             fn(i)
+        touch_size_classes()
         barrier()
         occ.updates = 0
         l0 = _lib.launch_count()
