@@ -55,7 +55,8 @@ _SIGNATURES = {
     "cednerf_occ_pack_bits": "plpp",
     "cednerf_occ_threshold_pack": "plpppp",
     "cednerf_occ_mark_invisible": "pipiipiiiifpp",
-    "cednerf_march": "ipplppiippffffippppppppppppppppppppppip",
+    "cednerf_march": "ipplppiippffffippppppppppppppppppppppipp",
+    "cednerf_ray_coherence_keys": "plpp",
     "cednerf_march_fill_runs": "lppppiffppppp",
     "cednerf_exclusive_scan": "plppppp",
     "cednerf_hashgrid_fwd": "pilpGpip",

@@ -59,6 +59,7 @@ struct MarchArgs {
   int32_t* run_n;    // [n, run_cap]
   int32_t* n_runs;   // [n]  (may exceed run_cap: the ray then takes the full-march fill)
   int run_cap;
+  const int32_t* order;  // nullable: thread i marches ray order[i] (rays sorted for coherence); outputs stay indexed by ray
 };
 
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
@@ -134,8 +135,9 @@ __global__ void sort_boundaries_kernel(const float* __restrict__ t_mins, const f
 
 template <bool FILL>
 __global__ void __launch_bounds__(128) march_kernel(MarchArgs a) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= a.n_rays) return;
+  const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= a.n_rays) return;
+  const int64_t r = a.order ? (int64_t)a.order[slot] : slot;
   const float near = a.near ? a.near[r] : a.near_const;
   const float far = a.far ? a.far[r] : a.far_const;
   if (a.mask && !a.mask[r]) {
@@ -595,6 +597,42 @@ CEDNERF_EXPORT int cednerf_occ_mark_invisible(const float* K, int n_K, const flo
   return cednerf_check_launch("cednerf_occ_mark_invisible");
 }
 
+namespace {
+
+// 16-bit Morton code of the ray direction (octahedral map, 8 bits per axis): rays with neighbouring codes cross the
+// nested grids along neighbouring paths.  Sorting a batch of random training rays by it before the count pass raises the
+// marcher's SIMT efficiency (it is an instruction-bound kernel whose lanes otherwise sit in unrelated cells).
+__global__ void ray_coherence_keys_kernel(const float* __restrict__ rays_d, int64_t n, int32_t* __restrict__ keys) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const float x = rays_d[3 * r], y = rays_d[3 * r + 1], z = rays_d[3 * r + 2];
+  const float inv = 1.0f / fmaxf(fabsf(x) + fabsf(y) + fabsf(z), 1e-20f);
+  float u = x * inv, v = y * inv;
+  if (z < 0.0f) {
+    const float fu = (1.0f - fabsf(v)) * (u >= 0.0f ? 1.0f : -1.0f), fv = (1.0f - fabsf(u)) * (v >= 0.0f ? 1.0f : -1.0f);
+    u = fu, v = fv;
+  }
+  uint32_t qu = (uint32_t)fminf(fmaxf((u * 0.5f + 0.5f) * 255.0f, 0.0f), 255.0f);
+  uint32_t qv = (uint32_t)fminf(fmaxf((v * 0.5f + 0.5f) * 255.0f, 0.0f), 255.0f);
+  auto spread = [](uint32_t b) {
+    b = (b | (b << 4)) & 0x0f0fu;
+    b = (b | (b << 2)) & 0x3333u;
+    b = (b | (b << 1)) & 0x5555u;
+    return b;
+  };
+  keys[r] = (int32_t)(spread(qu) | (spread(qv) << 1));
+}
+
+}  // namespace
+
+// keys[r] = coherence key of ray r (sort by it, pass the permutation to cednerf_march as ray_order)
+CEDNERF_EXPORT int cednerf_ray_coherence_keys(const float* rays_d, int64_t n_rays, int32_t* keys, void* stream) {
+  CEDNERF_REQUIRE(n_rays >= 0 && rays_d && keys, "bad arguments");
+  if (n_rays == 0) return 0;
+  ray_coherence_keys_kernel<<<cednerf_blocks(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(rays_d, n_rays, keys);
+  return cednerf_check_launch("cednerf_ray_coherence_keys");
+}
+
 // March one pass.  fill == 0: count only (n_intervals / n_samples / termination).  fill == 1: write the
 // outputs at the offsets given by iv_starts / sm_starts.  near/far: per-ray arrays or null (constants).
 CEDNERF_EXPORT int cednerf_march(int fill, const float* rays_o, const float* rays_d, int64_t n_rays,
@@ -606,7 +644,7 @@ CEDNERF_EXPORT int cednerf_march(int fill, const float* rays_o, const float* ray
                                  uint8_t* iv_right, int64_t* iv_ray, float* sm_vals, int64_t* sm_ray,
                                  uint8_t* sm_valid, float* t_starts, float* t_ends, int64_t* ray_indices,
                                  int32_t* n_intervals, int32_t* n_samples, float* termination, float* run_t,
-                                 int32_t* run_n, int32_t* n_runs, int run_cap, void* stream) {
+                                 int32_t* run_n, int32_t* n_runs, int run_cap, const int32_t* ray_order, void* stream) {
   CEDNERF_REQUIRE(!run_t || (!fill && run_n && n_runs && run_cap > 0 && step_size > 0.0f),
                   "run recording: count pass, positive step size");
   CEDNERF_REQUIRE(n_rays >= 0 && n_levels >= 1 && n_levels <= MARCH_MAX_LEVELS && resolution >= 1,
@@ -620,7 +658,7 @@ CEDNERF_EXPORT int cednerf_march(int fill, const float* rays_o, const float* ray
   MarchArgs a{rays_o, rays_d, n_rays, occ_bits, aabbs, n_levels, resolution, near_planes, far_planes, near_const,
               far_const, step_size, cone_angle, steps_limit, rays_mask, t_sorted, t_indices, hits, iv_starts,
               sm_starts, iv_vals, iv_left, iv_right, iv_ray, sm_vals, sm_ray, sm_valid, t_starts, t_ends, ray_indices,
-              n_intervals, n_samples, termination, run_t, run_n, n_runs, run_cap};
+              n_intervals, n_samples, termination, run_t, run_n, n_runs, run_cap, ray_order};
   const unsigned grid = cednerf_blocks(n_rays, 128);
   if (fill) march_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
   else march_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(a);

@@ -64,6 +64,8 @@ class OccGridEstimator(torch.nn.Module):
                 near = near + u * render_step_size
         mi = ops.MarchInputs(rays_o, rays_d, occupancy_bits(self.binaries), self.aabbs, int(self.resolution[0]),
                              near, far, float(near_plane), float(far_plane), render_step_size, cone_angle)
+        if stratified and n >= 65536:  # a large batch of (random) training rays
+            mi.sort_for_coherence()
         _, n_sm, _ = mi.count(record_runs=True)
         starts, packed, total = ops.exclusive_scan(n_sm)
         if mi.runs is not None:

@@ -92,6 +92,15 @@ class MarchInputs:
         self.t_sorted = None if t_sorted is None else _f32c(t_sorted)
         self.t_indices = None if t_indices is None else t_indices.detach().to(I64).contiguous()
         self.hits = None if hits is None else hits.detach().to(torch.bool).contiguous()
+        self.order = None  # int32 permutation for the count pass (sort_for_coherence)
+
+    def sort_for_coherence(self):
+        """Random training rays: march them in the order of a direction key so that the lanes of a warp walk
+        neighbouring paths (the count pass is instruction-bound and half its lanes idle otherwise).  Outputs stay
+        indexed by ray, so nothing downstream sees the permutation."""
+        keys = torch.empty(self.n, dtype=I32, device=self.o.device)
+        call("cednerf_ray_coherence_keys", ptr(self.d), self.n, ptr(keys), stream())
+        self.order = torch.sort(keys)[1].to(I32)
 
     def _common(self, fill):
         return (fill, ptr(self.o), ptr(self.d), self.n, ptr(self.bits), ptr(self.aabbs), self.nl, self.res,
@@ -112,7 +121,7 @@ class MarchInputs:
         rt, rn, nr = self.runs if self.runs is not None else (None, None, None)
         call("cednerf_march", *self._common(0), None, None, None, None, None, None, None, None, None, None, None,
              None, ptr(n_iv), ptr(n_sm), ptr(term), ptr(rt), ptr(rn), ptr(nr), self.RUN_CAP if rt is not None else 0,
-             stream())
+             ptr(self.order), stream())
         return n_iv, n_sm, term
 
     def fill_packed_from_runs(self, sm_starts, total):
@@ -128,7 +137,7 @@ class MarchInputs:
         # overflow is 0 for rays the caller masked out (their run count is 0), so it can stand in as the ray mask
         user_mask, self.mask = self.mask, overflow
         call("cednerf_march", *self._common(1), None, ptr(sm_starts), None, None, None, None, None, None, None,
-             ptr(t0), ptr(t1), ptr(ridx), None, None, None, None, None, None, 0, stream())
+             ptr(t0), ptr(t1), ptr(ridx), None, None, None, None, None, None, 0, None, stream())
         self.mask = user_mask
         return ridx, t0, t1
 
@@ -139,7 +148,7 @@ class MarchInputs:
         ridx = torch.empty(total, dtype=I64, device=dev)
         term = torch.empty(self.n, device=dev)
         call("cednerf_march", *self._common(1), None, ptr(sm_starts), None, None, None, None, None, None, None,
-             ptr(t0), ptr(t1), ptr(ridx), None, None, ptr(term), None, None, None, 0, stream())
+             ptr(t0), ptr(t1), ptr(ridx), None, None, ptr(term), None, None, None, 0, None, stream())
         return ridx, t0, t1, term
 
     def fill_nerfacc(self, iv_starts, sm_starts, n_iv_total, n_sm_total):
@@ -156,7 +165,7 @@ class MarchInputs:
         term = torch.empty(self.n, device=dev)
         call("cednerf_march", *self._common(1), ptr(iv_starts), ptr(sm_starts), ptr(iv_vals), ptr(iv_left),
              ptr(iv_right), ptr(iv_ray), ptr(sm_vals), ptr(sm_ray), ptr(sm_valid), None, None, None, ptr(n_iv),
-             ptr(n_sm), ptr(term), None, None, None, 0, stream())
+             ptr(n_sm), ptr(term), None, None, None, 0, None, stream())
         return (iv_vals, iv_left, iv_right, iv_ray), (sm_vals, sm_ray, sm_valid), n_iv, n_sm, term
 
 

@@ -62,6 +62,7 @@ int cednerf_occ_mark_invisible(const float* K, int n_K, const float* c2w, int n_
  * t_sorted / t_indices / hits (nullable, all or none): computed in-kernel when absent.
  * Output groups (each nullable): nerfacc intervals (iv_*), nerfacc samples (sm_*), packed
  * (t_starts, t_ends, ray_indices). */
+int cednerf_ray_coherence_keys(const float* rays_d, int64_t n_rays, int32_t* keys, void* stream);
 int cednerf_march(int fill, const float* rays_o, const float* rays_d, int64_t n_rays, const uint32_t* occ_bits,
                   const float* aabbs, int n_levels, int resolution, const float* near_planes, const float* far_planes,
                   float near_const, float far_const, float step_size, float cone_angle, int steps_limit,
@@ -70,7 +71,9 @@ int cednerf_march(int fill, const float* rays_o, const float* rays_d, int64_t n_
                   uint8_t* iv_right, int64_t* iv_ray, float* sm_vals, int64_t* sm_ray, uint8_t* sm_valid,
                   float* t_starts, float* t_ends, int64_t* ray_indices, int32_t* n_intervals, int32_t* n_samples,
                   float* termination, float* run_t /*nullable: [n,run_cap], count pass only*/,
-                  int32_t* run_n /*[n,run_cap]*/, int32_t* n_runs /*[n]*/, int run_cap, void* stream);
+                  int32_t* run_n /*[n,run_cap]*/, int32_t* n_runs /*[n]*/, int run_cap,
+                  const int32_t* ray_order /*nullable: thread i marches ray ray_order[i]; outputs stay indexed by ray*/,
+                  void* stream);
 /* Packed fill that replays the runs a count pass recorded (first left edge + length of every stretch of back-to-back
  * samples): no second grid traversal.  overflow[r] = 1 where a ray had more than run_cap runs; fill those rays with
  * cednerf_march(fill = 1, rays_mask = overflow). */
