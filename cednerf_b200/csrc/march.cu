@@ -599,7 +599,7 @@ CEDNERF_EXPORT int cednerf_occ_mark_invisible(const float* K, int n_K, const flo
 
 namespace {
 
-// 16-bit Morton code of the ray direction (octahedral map, 8 bits per axis): rays with neighbouring codes cross the
+// 20-bit Morton code of the ray direction (octahedral map, 10 bits per axis): rays with neighbouring codes cross the
 // nested grids along neighbouring paths.  Sorting a batch of random training rays by it before the count pass raises the
 // marcher's SIMT efficiency (it is an instruction-bound kernel whose lanes otherwise sit in unrelated cells).
 __global__ void ray_coherence_keys_kernel(const float* __restrict__ rays_d, int64_t n, int32_t* __restrict__ keys) {
@@ -612,12 +612,13 @@ __global__ void ray_coherence_keys_kernel(const float* __restrict__ rays_d, int6
     const float fu = (1.0f - fabsf(v)) * (u >= 0.0f ? 1.0f : -1.0f), fv = (1.0f - fabsf(u)) * (v >= 0.0f ? 1.0f : -1.0f);
     u = fu, v = fv;
   }
-  uint32_t qu = (uint32_t)fminf(fmaxf((u * 0.5f + 0.5f) * 255.0f, 0.0f), 255.0f);
-  uint32_t qv = (uint32_t)fminf(fmaxf((v * 0.5f + 0.5f) * 255.0f, 0.0f), 255.0f);
-  auto spread = [](uint32_t b) {
-    b = (b | (b << 4)) & 0x0f0fu;
-    b = (b | (b << 2)) & 0x3333u;
-    b = (b | (b << 1)) & 0x5555u;
+  uint32_t qu = (uint32_t)fminf(fmaxf((u * 0.5f + 0.5f) * 1023.0f, 0.0f), 1023.0f);
+  uint32_t qv = (uint32_t)fminf(fmaxf((v * 0.5f + 0.5f) * 1023.0f, 0.0f), 1023.0f);
+  auto spread = [](uint32_t b) {  // 10 bits -> every other bit of 20
+    b = (b | (b << 8)) & 0x00ff00ffu;
+    b = (b | (b << 4)) & 0x0f0f0f0fu;
+    b = (b | (b << 2)) & 0x33333333u;
+    b = (b | (b << 1)) & 0x55555555u;
     return b;
   };
   keys[r] = (int32_t)(spread(qu) | (spread(qv) << 1));
