@@ -335,6 +335,56 @@ accumulate_wide_bwd_kernel(const float* __restrict__ w, const float* __restrict_
   }
 }
 
+// C == 32 (the latent-loss reduction): eight lanes per row with 16-byte accesses, four rays / samples per warp - a
+// quarter of the warp instructions of the lane-per-channel kernels above for the same bytes
+__global__ void __launch_bounds__(256)
+accumulate_c32_fwd_kernel(const float* __restrict__ w, const float4* __restrict__ v, const int64_t* __restrict__ offsets,
+                          int64_t n_rays, float4* __restrict__ out, int inplace) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t ray = t >> 3;
+  const int c = (int)(t & 7);
+  if (ray >= n_rays) return;
+  const int64_t s0 = offsets[ray], s1 = offsets[ray + 1];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t i = s0; i < s1; ++i) {
+    const float wi = w[i];
+    const float4 x = v[i * 8 + c];
+    acc.x += wi * x.x, acc.y += wi * x.y, acc.z += wi * x.z, acc.w += wi * x.w;
+  }
+  if (inplace) {
+    const float4 o = out[ray * 8 + c];
+    acc.x += o.x, acc.y += o.y, acc.z += o.z, acc.w += o.w;
+  }
+  out[ray * 8 + c] = acc;
+}
+
+__global__ void __launch_bounds__(256)
+accumulate_c32_bwd_kernel(const float* __restrict__ w, const float4* __restrict__ v, const int64_t* __restrict__ ridx,
+                          int64_t S, const float4* __restrict__ g_out, float* __restrict__ g_w, float4* __restrict__ g_v) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = t >> 3;
+  const int c = (int)(t & 7);
+  const bool ok = i < S;
+  float part = 0.f;
+  if (ok) {
+    const float4 go = g_out[ridx[i] * 8 + c];
+    if (g_v) {
+      const float wi = w[i];
+      g_v[i * 8 + c] = make_float4(wi * go.x, wi * go.y, wi * go.z, wi * go.w);
+    }
+    if (g_w) {
+      const float4 x = v[i * 8 + c];
+      part = go.x * x.x + go.y * x.y + go.z * x.z + go.w * x.w;
+    }
+  }
+  if (g_w) {  // sum over the eight lanes of the row
+    part += __shfl_xor_sync(0xffffffffu, part, 4);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    if (ok && c == 0) g_w[i] = part;
+  }
+}
+
 int pick_group(int64_t S, int64_t n_rays) {
   const double mean = n_rays > 0 ? (double)S / (double)n_rays : 0.0;
   if (mean <= 6.0) return 4;
@@ -412,6 +462,11 @@ CEDNERF_EXPORT int cednerf_accumulate_fwd(const float* weights, const float* val
   CEDNERF_REQUIRE(n_rays >= 0 && n_samples >= 0 && n_channels >= 1, "bad sizes");
   if (n_rays == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (values && n_channels == 32 && (((uintptr_t)values | (uintptr_t)outputs) & 15) == 0) {
+    accumulate_c32_fwd_kernel<<<cednerf_blocks(n_rays * 8, 256), 256, 0, st>>>(
+        weights, reinterpret_cast<const float4*>(values), offsets, n_rays, reinterpret_cast<float4*>(outputs), inplace);
+    return cednerf_check_launch("cednerf_accumulate_fwd");
+  }
   if (values && n_channels >= 8 && n_channels <= 32) {
     accumulate_wide_fwd_kernel<<<cednerf_blocks(n_rays * 32, 256), 256, 0, st>>>(weights, values, n_channels, offsets,
                                                                                  n_rays, outputs, inplace);
@@ -428,6 +483,13 @@ CEDNERF_EXPORT int cednerf_accumulate_bwd(const float* weights, const float* val
   CEDNERF_REQUIRE(n_samples >= 0 && n_channels >= 1, "bad sizes");
   if (n_samples == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (values && n_channels == 32 &&
+      (((uintptr_t)values | (uintptr_t)g_outputs | (uintptr_t)g_values) & 15) == 0) {
+    accumulate_c32_bwd_kernel<<<cednerf_blocks(n_samples * 8, 256), 256, 0, st>>>(
+        weights, reinterpret_cast<const float4*>(values), ray_indices, n_samples,
+        reinterpret_cast<const float4*>(g_outputs), g_weights, reinterpret_cast<float4*>(g_values));
+    return cednerf_check_launch("cednerf_accumulate_bwd");
+  }
   if (values && n_channels >= 8 && n_channels <= 32) {
     accumulate_wide_bwd_kernel<<<cednerf_blocks(n_samples * 32, 256), 256, 0, st>>>(
         weights, values, n_channels, ray_indices, n_samples, g_outputs, g_weights, g_values);
