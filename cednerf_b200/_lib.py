@@ -78,7 +78,8 @@ _SIGNATURES = {
     "cednerf_ray_offsets": "pllpp",
     "cednerf_composite_fwd": "pppppppillpppppppifp",
     "cednerf_composite_bwd": "pppppppillppppppppppfp",
-    "cednerf_visibility_mask": "ppppllffpp",
+    "cednerf_visibility_mask": "ppppllffppp",
+    "cednerf_compact_samples": "pppppllpppp",
     "cednerf_accumulate_fwd": "ppipllpip",
     "cednerf_accumulate_bwd": "ppiplpppp",
     "cednerf_nonfinite_check": "App",

@@ -248,13 +248,14 @@ template <int G>
 __global__ void __launch_bounds__(256)
 visibility_kernel(const float* __restrict__ t0, const float* __restrict__ t1, const float* __restrict__ sigma,
                   const int64_t* __restrict__ offsets, int64_t n_rays, float early_stop_eps, float alpha_thre,
-                  uint8_t* __restrict__ keep) {
+                  uint8_t* __restrict__ keep, int32_t* __restrict__ kept_counts) {
   const int gl = threadIdx.x % G;
   const unsigned gm = group_mask<G>();
   const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
   if (ray >= n_rays) return;
   const int64_t s0 = offsets[ray], s1 = offsets[ray + 1];
   float carry = 0.f;
+  int kept = 0;
   for (int64_t base = s0; base < s1; base += G) {
     const int64_t i = base + gl;
     const bool ok = i < s1;
@@ -263,7 +264,39 @@ visibility_kernel(const float* __restrict__ t0, const float* __restrict__ t1, co
     const float T = expf(-(carry + (incl - sd)));
     const float al = 1.f - expf(-sd);
     carry += __shfl_sync(gm, incl, G - 1, G);
-    if (ok) keep[i] = (T >= early_stop_eps) && (alpha_thre <= 0.f || al >= alpha_thre);
+    const bool k = ok && (T >= early_stop_eps) && (alpha_thre <= 0.f || al >= alpha_thre);
+    if (ok) keep[i] = k;
+    if (kept_counts) kept += __popc(__ballot_sync(gm, k) & gm);
+  }
+  if (kept_counts && gl == 0) kept_counts[ray] = kept;
+}
+
+// Compaction of the visible samples (what OccGridEstimator.sampling returns): every ray's kept samples move, in order,
+// to out_starts[ray] + rank.  One group of G lanes per ray; the rank inside a chunk is a popcount of the group's ballot.
+template <int G>
+__global__ void __launch_bounds__(256)
+compact_samples_kernel(const uint8_t* __restrict__ keep, const int64_t* __restrict__ offsets,
+                       const int64_t* __restrict__ out_starts, const float* __restrict__ t0, const float* __restrict__ t1,
+                       int64_t n_rays, int64_t* __restrict__ ridx_out, float* __restrict__ t0_out,
+                       float* __restrict__ t1_out) {
+  const int gl = threadIdx.x % G;
+  const unsigned gm = group_mask<G>();
+  const int shift = (threadIdx.x & 31) / G * G;
+  const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+  if (ray >= n_rays) return;
+  const int64_t s0 = offsets[ray], s1 = offsets[ray + 1];
+  int64_t dst = out_starts[ray];
+  for (int64_t base = s0; base < s1; base += G) {
+    const int64_t i = base + gl;
+    const bool k = i < s1 && keep[i] != 0;
+    const unsigned bits = (__ballot_sync(gm, k) & gm) >> shift;
+    if (k) {
+      const int64_t o = dst + __popc(bits & ((1u << gl) - 1u));
+      ridx_out[o] = ray;
+      t0_out[o] = t0[i];
+      t1_out[o] = t1[i];
+    }
+    dst += __popc(bits);
   }
 }
 
@@ -447,13 +480,28 @@ CEDNERF_EXPORT int cednerf_composite_bwd(const float* t_starts, const float* t_e
 
 CEDNERF_EXPORT int cednerf_visibility_mask(const float* t_starts, const float* t_ends, const float* sigmas,
                                            const int64_t* offsets, int64_t n_samples, int64_t n_rays,
-                                           float early_stop_eps, float alpha_thre, uint8_t* keep, void* stream) {
+                                           float early_stop_eps, float alpha_thre, uint8_t* keep,
+                                           int32_t* kept_counts, void* stream) {
   CEDNERF_REQUIRE(n_rays >= 0 && n_samples >= 0, "bad sizes");
-  if (n_rays == 0 || n_samples == 0) return 0;
+  if (n_rays == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   DISPATCH_G(pick_group(n_samples, n_rays), visibility_kernel, t_starts, t_ends, sigmas, offsets, n_rays,
-             early_stop_eps, alpha_thre, keep);
+             early_stop_eps, alpha_thre, keep, kept_counts);
   return cednerf_check_launch("cednerf_visibility_mask");
+}
+
+// keep [S] + offsets [n_rays+1] of the marched samples, out_starts [n_rays] = exclusive scan of the per-ray kept counts
+// (cednerf_visibility_mask's kept_counts through cednerf_exclusive_scan) -> the kept (ray_indices, t_starts, t_ends).
+CEDNERF_EXPORT int cednerf_compact_samples(const uint8_t* keep, const int64_t* offsets, const int64_t* out_starts,
+                                           const float* t_starts, const float* t_ends, int64_t n_samples, int64_t n_rays,
+                                           int64_t* ray_indices_out, float* t_starts_out, float* t_ends_out,
+                                           void* stream) {
+  CEDNERF_REQUIRE(n_rays >= 0 && n_samples >= 0 && keep && offsets && out_starts, "bad arguments");
+  if (n_rays == 0 || n_samples == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_G(pick_group(n_samples, n_rays), compact_samples_kernel, keep, offsets, out_starts, t_starts, t_ends, n_rays,
+             ray_indices_out, t_starts_out, t_ends_out);
+  return cednerf_check_launch("cednerf_compact_samples");
 }
 
 CEDNERF_EXPORT int cednerf_accumulate_fwd(const float* weights, const float* values, int n_channels,

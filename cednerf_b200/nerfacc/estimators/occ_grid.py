@@ -88,10 +88,8 @@ class OccGridEstimator(torch.nn.Module):
             if t0.numel():
                 sigmas = sigma_fn(t0, t1, ridx)
                 assert sigmas.shape == t0.shape, f"sigmas must have shape {tuple(t0.shape)}"
-                keep = ops.visibility_mask(t0, t1, sigmas, ops.offsets_from_packed(packed), rays_o.shape[0],
-                                           early_stop_eps, alpha_thre)
-                sel = torch.nonzero(keep).squeeze(-1)  # one compaction (one host read), three gathers
-                ridx, t0, t1 = ridx[sel], t0[sel], t1[sel]
+                ridx, t0, t1 = ops.visible_samples(t0, t1, sigmas, ops.offsets_from_packed(packed), rays_o.shape[0],
+                                                   early_stop_eps, alpha_thre)
         return ridx, t0, t1
 
     @torch.no_grad()

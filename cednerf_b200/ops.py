@@ -386,12 +386,30 @@ def offsets_from_packed(packed_info: torch.Tensor) -> torch.Tensor:
     return torch.cat([starts, (starts[-1:] + cnts[-1:])]).contiguous()
 
 
-def visibility_mask(t_starts, t_ends, sigmas, offsets, n_rays, early_stop_eps, alpha_thre) -> torch.Tensor:
+def visibility_mask(t_starts, t_ends, sigmas, offsets, n_rays, early_stop_eps, alpha_thre, want_counts=False):
+    """-> keep bool [S] (and, with want_counts, the per-ray number of kept samples int32 [n_rays])."""
     t0, t1, sg = _f32c(t_starts), _f32c(t_ends), _f32c(sigmas)
     keep = torch.empty(t0.numel(), dtype=torch.bool, device=t0.device)
+    counts = torch.empty(n_rays, dtype=I32, device=t0.device) if want_counts else None
     call("cednerf_visibility_mask", ptr(t0), ptr(t1), ptr(sg), ptr(offsets), t0.numel(), n_rays,
-         float(early_stop_eps), float(alpha_thre), ptr(keep), stream())
-    return keep
+         float(early_stop_eps), float(alpha_thre), ptr(keep), ptr(counts), stream())
+    return (keep, counts) if want_counts else keep
+
+
+def visible_samples(t_starts, t_ends, sigmas, offsets, n_rays, early_stop_eps, alpha_thre):
+    """render_visibility_from_density + the compaction of OccGridEstimator.sampling in three launches (mask + per-ray
+    counts, scan, ordered scatter) and one host read (the kept total) -> (ray_indices, t_starts, t_ends)."""
+    t0, t1 = _f32c(t_starts), _f32c(t_ends)
+    keep, counts = visibility_mask(t0, t1, sigmas, offsets, n_rays, early_stop_eps, alpha_thre, want_counts=True)
+    starts, _, total = exclusive_scan(counts, want_packed=False)
+    n_kept = int(total.item())
+    dev = t0.device
+    ridx = torch.empty(n_kept, dtype=I64, device=dev)
+    o0, o1 = torch.empty(n_kept, device=dev), torch.empty(n_kept, device=dev)
+    if n_kept:
+        call("cednerf_compact_samples", ptr(keep), ptr(offsets), ptr(starts), ptr(t0), ptr(t1), t0.numel(), n_rays,
+             ptr(ridx), ptr(o0), ptr(o1), stream())
+    return ridx, o0, o1
 
 
 class RenderWeightFunction(torch.autograd.Function):

@@ -214,7 +214,12 @@ int cednerf_composite_bwd(const float* t_starts, const float* t_ends, const floa
 /* nerfacc.render_visibility_from_density — inside OccGridEstimator.sampling (cednerf/utils.py:115-125) */
 int cednerf_visibility_mask(const float* t_starts, const float* t_ends, const float* sigmas, const int64_t* offsets,
                             int64_t n_samples, int64_t n_rays, float early_stop_eps, float alpha_thre, uint8_t* keep,
-                            void* stream);
+                            int32_t* kept_counts /*nullable: per-ray number of kept samples*/, void* stream);
+/* the compaction that follows it in .sampling: kept samples of every ray, in order, to out_starts[ray] + rank
+ * (out_starts = exclusive scan of kept_counts) */
+int cednerf_compact_samples(const uint8_t* keep, const int64_t* offsets, const int64_t* out_starts, const float* t_starts,
+                            const float* t_ends, int64_t n_samples, int64_t n_rays, int64_t* ray_indices_out,
+                            float* t_starts_out, float* t_ends_out, void* stream);
 /* nerfacc.accumulate_along_rays / accumulate_along_rays_ — cednerf/render.py:158-169, cednerf/utils.py:282-299 */
 int cednerf_accumulate_fwd(const float* weights, const float* values /*nullable*/, int n_channels,
                            const int64_t* offsets, int64_t n_samples, int64_t n_rays, float* outputs, int inplace,
