@@ -4,10 +4,13 @@
     python bench.py --gpus N --steps K --warmup W             # this repo's CUDA path (one rank per GPU under torchrun)
     python bench.py --impl reference --gpus N --steps K ...   # the CPU restatement of the reference path (oracle/)
 
-One step = the body of the reference's training loop for this path (train_real.py:330-420 without the data loader
-and without the every-16-steps occupancy update): stratified occupancy-grid sampling with the
-no-grad density pre-pass and visibility filtering, the field forward on the surviving samples, compositing, the
-MSE + auxiliary losses of the canonical DyNeRF flags (-te -ta -df -f -wr -ae), backward, GradScaler (2^10) and Adam.
+One step = the body of the reference's training loop for this path (train_real.py:330-420 without the data loader):
+estimator.update_every_n_steps (works every 16th step; on a twin estimator, see OccupancyUpdate), stratified
+occupancy-grid sampling with the no-grad density pre-pass and visibility filtering, the field forward on the surviving
+samples, compositing, the MSE + auxiliary losses of the canonical DyNeRF flags (-te -ta -df -f -wr -ae), backward,
+GradScaler (2^10) and fused Adam, at the reference schedule's first-iteration learning rate (see TrainState).  The
+reference arm runs the same step on the CPU restatement (oracle/) on a bounded ray sample, without the occupancy
+update (8.4 M CPU field queries per update would only flatter the ratio).
 Rank 0 prints ONE JSON line (see the keys below).  Synthetic data: seeded rays / pixels / occupancy, random-init
 weights with a density boost (cednerf_b200/workload.py)."""
 from __future__ import annotations
