@@ -134,7 +134,11 @@ def train_step(impl, field, est, opt, scaler, batch, cfg, rk, reducer=None, sche
                                                           timestamps=batch["timestamps"], jitter=batch["jitter"], **rk)
     if n_samples == 0:
         return None, 0
-    loss = torch.nn.functional.mse_loss(rgb, batch["pixels"]) + aux_losses(rgb, acc, batch["pixels"], extra, cfg.flags)
+    if hasattr(impl, "losses"):  # this repo: the same loss as one fused forward / backward launch
+        loss = impl.losses.training_loss(rgb, acc, batch["pixels"], extra, acc_entropy_loss=True, weight_rgbper=True,
+                                         use_feat_predict=bool(cfg.flags.get("use_feat_predict")))
+    else:
+        loss = torch.nn.functional.mse_loss(rgb, batch["pixels"]) + aux_losses(rgb, acc, batch["pixels"], extra, cfg.flags)
     opt.zero_grad()
     if scaler is not None:
         scaler.scale(loss).backward()
@@ -357,7 +361,7 @@ def run_ours(args):
 
         state.restore()
         step_resident(0)
-        for m in (_lib, cb.ops, cb.optim):
+        for m in (_lib, cb.ops, cb.optim, cb.losses):
             m.call = recording_call
         barrier()
         t0 = time.perf_counter()
@@ -365,7 +369,7 @@ def run_ours(args):
             step_resident(i)
         torch.cuda.synchronize()
         prof_ms = (time.perf_counter() - t0) * 1e3 / args.profile_steps
-        for m in (_lib, cb.ops, cb.optim):
+        for m in (_lib, cb.ops, cb.optim, cb.losses):
             m.call = real_call
     if rank == 0 and args.profile_steps > 0:
         agg = {}
@@ -443,11 +447,11 @@ def run_ours(args):
                 e_.record()
                 rec_r.append((name, s_, e_))
 
-            for m in (_lib, cb.ops, cb.optim):
+            for m in (_lib, cb.ops, cb.optim, cb.losses):
                 m.call = rec_call
             render_one(0)
             torch.cuda.synchronize()
-            for m in (_lib, cb.ops, cb.optim):
+            for m in (_lib, cb.ops, cb.optim, cb.losses):
                 m.call = real_call
             agg_r = {}
             for name, s_, e_ in rec_r:

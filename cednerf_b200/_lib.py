@@ -83,6 +83,8 @@ _SIGNATURES = {
     "cednerf_accumulate_fwd": "ppipllpip",
     "cednerf_accumulate_bwd": "ppiplpppp",
     "cednerf_nonfinite_check": "App",
+    "cednerf_training_loss_fwd": "ppplppplpiffppp",
+    "cednerf_training_loss_bwd": "pppplpppliffppppp",
     "cednerf_adam_step": "Apippfffip",
 }
 _CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_int64, "f": ctypes.c_float,

@@ -1,0 +1,73 @@
+"""Loss of the reference's training loop for its canonical flags (train_real.py:369-409), SURVEY.md §8f N4:
+
+    loss = F.mse_loss(rgb, pixels)
+         + 1e-3 * entropy(clamp(1 - acc, 1e-6, 1 - 1e-6)).mean()                                   (-ae)
+         + 1e-3 * ((rgbs - pixels[ray_indices])**2).sum(-1) @ weights.detach() / n_rays             (-wr)
+         + latent_losses.mean()                                                                     (-f)
+
+as one forward and one backward launch (`csrc/losses.cu`) instead of ~50 element-wise / reduction launches and autograd
+nodes.  `training_loss(rgb, acc, pixels, extras, ...)` takes what `render_image` returns."""
+from __future__ import annotations
+
+import torch
+
+from ._lib import call, ptr, stream
+from .ops import _f32c
+
+F32, F64, I64 = torch.float32, torch.float64, torch.int64
+
+
+class TrainingLossFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rgb, acc, pixels, rgbs, weights, ray_indices, latent, w_entropy, w_rgbper):
+        rgb, pixels = _f32c(rgb), _f32c(pixels)
+        n_rays, dev = rgb.shape[0], rgb.device
+        acc_c = None if acc is None else _f32c(acc).view(-1)
+        rgbs_c = None if rgbs is None else _f32c(rgbs)
+        w_c = None if rgbs is None else _f32c(weights)
+        ridx = None if rgbs is None else ray_indices.detach().to(I64).contiguous()
+        lat = None if latent is None else _f32c(latent)
+        n_s = 0 if rgbs_c is None else rgbs_c.shape[0]
+        n_lat = 0 if lat is None else lat.shape[-1]
+        sums = torch.empty(4, dtype=F64, device=dev)
+        loss = torch.empty(1, dtype=F32, device=dev)
+        call("cednerf_training_loss_fwd", ptr(rgb), ptr(acc_c), ptr(pixels), n_rays, ptr(rgbs_c), ptr(w_c), ptr(ridx), n_s,
+             ptr(lat), n_lat, float(w_entropy), float(w_rgbper), ptr(sums), ptr(loss), stream())
+        keep = [t if t is not None else rgb for t in (acc_c, rgbs_c, w_c, ridx)]
+        ctx.save_for_backward(rgb, pixels, *keep)
+        ctx.flags = (acc_c is not None, rgbs_c is not None, n_lat, n_s, float(w_entropy), float(w_rgbper))
+        ctx.shapes = (None if acc is None else acc.shape, None if latent is None else latent.shape)
+        ctx.set_materialize_grads(False)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        if g is None:
+            return (None,) * 9
+        rgb, pixels, acc_c, rgbs_c, w_c, ridx = ctx.saved_tensors
+        has_acc, has_rgbs, n_lat, n_s, w_entropy, w_rgbper = ctx.flags
+        n_rays, dev = rgb.shape[0], rgb.device
+        need = ctx.needs_input_grad
+        g = g.detach().to(F32).reshape(1).contiguous()
+        d_rgb = torch.empty_like(rgb) if need[0] else None
+        d_acc = torch.empty(n_rays, device=dev) if (has_acc and need[1]) else None
+        d_rgbs = torch.empty_like(rgbs_c) if (has_rgbs and need[3]) else None
+        d_lat = torch.empty(n_rays, n_lat, device=dev) if (n_lat and need[6]) else None
+        call("cednerf_training_loss_bwd", ptr(g), ptr(rgb), ptr(acc_c) if has_acc else None, ptr(pixels), n_rays,
+             ptr(rgbs_c) if has_rgbs else None, ptr(w_c) if has_rgbs else None, ptr(ridx) if has_rgbs else None, n_s,
+             n_lat, w_entropy, w_rgbper, ptr(d_rgb), ptr(d_acc), ptr(d_rgbs), ptr(d_lat), stream())
+        acc_shape, lat_shape = ctx.shapes
+        return (d_rgb, None if d_acc is None else d_acc.view(acc_shape), None, d_rgbs, None, None,
+                None if d_lat is None else d_lat.view(lat_shape), None, None)
+
+
+def training_loss(rgb, acc, pixels, extras, acc_entropy_loss: bool = True, weight_rgbper: bool = True,
+                  use_feat_predict: bool = True) -> torch.Tensor:
+    """`extras` is the list `render_image` returns (one dict per ray chunk; training renders the batch as one chunk)."""
+    if len(extras) != 1:
+        raise ValueError("training_loss fuses the one-chunk case of a training batch (render_image in training mode)")
+    ex = extras[0]
+    latent = ex.get("latent_losses") if use_feat_predict else None
+    return TrainingLossFunction.apply(rgb, acc if acc_entropy_loss else None, pixels,
+                                      ex["rgbs"] if weight_rgbper else None, ex["weights"].detach(), ex["ray_indices"],
+                                      latent, 1e-3, 1e-3)

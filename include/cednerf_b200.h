@@ -255,6 +255,20 @@ int cednerf_adam_step(const CednerfAdamTensors* tensors, float* step, int advanc
                       const float* found_inf /*nullable*/, float beta1, float beta2, float eps, int adam_w_mode,
                       void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Training loss of the reference loop for the canonical flags (train_real.py:369-409): F.mse_loss(rgb, pixels)
+ * + w_entropy * acc-entropy (-ae, 1e-3) + w_rgbper * weighted per-sample colour loss (-wr, 1e-3) + latent_losses.mean()
+ * (-f).  acc / rgbs / latent nullable (term absent).  sums: 4 doubles of workspace; loss: 1 float. */
+int cednerf_training_loss_fwd(const float* rgb, const float* acc, const float* pixels, int64_t n_rays, const float* rgbs,
+                              const float* weights, const int64_t* ray_indices, int64_t n_samples, const float* latent,
+                              int n_latent, float w_entropy, float w_rgbper, double* sums, float* loss, void* stream);
+/* its gradients times g_loss[0] (device scalar); any of d_rgb [R,3], d_acc [R], d_rgbs [S,3], d_latent [R,n_latent] null */
+int cednerf_training_loss_bwd(const float* g_loss, const float* rgb, const float* acc, const float* pixels, int64_t n_rays,
+                              const float* rgbs, const float* weights, const int64_t* ray_indices, int64_t n_samples,
+                              int n_latent, float w_entropy, float w_rgbper, float* d_rgb, float* d_acc, float* d_rgbs,
+                              float* d_latent, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
