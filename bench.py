@@ -276,7 +276,10 @@ def run_ours(args):
     # steps, leave free blocks of the next size classes in the cache, so the timed step in which the count crosses the
     # boundary does not have to grow the pool (one such step took 58-110 ms).  A training run reaches the same state
     # after its first few hundred iterations.
-    oversized = [{k: v.to(dev) for k, v in workload.draw_batch(cfg, int(args.rays * f), gen).items()} for f in (1.06, 1.12)]
+    # (the count grows by ~0.25 % per step at this learning rate: cover the whole run in 6 % increments)
+    n_classes = max(2, int((0.003 * (args.steps + max(args.warmup, 3)) + 0.06) / 0.06) + 1)
+    oversized = [{k: v.to(dev) for k, v in workload.draw_batch(cfg, int(args.rays * (1.0 + 0.06 * (j + 1))), gen).items()}
+                 for j in range(min(n_classes, 12))]
 
     def touch_size_classes():
         for b in oversized:
