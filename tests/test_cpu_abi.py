@@ -110,6 +110,20 @@ def test_no_cpu_fallback():
         cb.tcnn.Network(32, 16, {"otype": "FullyFusedMLP", "n_neurons": 64, "n_hidden_layers": 1})(torch.zeros(8, 32))
     with pytest.raises(RuntimeError):
         cb.ops.time_embed(torch.zeros(3, 1))
+    # optimiser and loss of the training loop: same rule
+    p = torch.nn.Parameter(torch.zeros(16))
+    p.grad = torch.ones(16)
+    with pytest.raises(RuntimeError):
+        cb.optim.FusedAdam([p], lr=1e-2, eps=1e-15).step()
+    with pytest.raises(RuntimeError):
+        cb.optim.FusedAdam([p], amsgrad=True)
+    ex = {"rgbs": torch.zeros(5, 3), "weights": torch.zeros(5), "ray_indices": torch.zeros(5, dtype=torch.long),
+          "latent_losses": torch.zeros(4, 32)}
+    with pytest.raises(RuntimeError):
+        cb.losses.training_loss(torch.zeros(4, 3), torch.zeros(4, 1), torch.zeros(4, 3), [ex])
+    est = cb.OccGridEstimator([-1, -1, -1, 1, 1, 1], resolution=16, levels=1)
+    with pytest.raises(RuntimeError):
+        est.mark_invisible_cells(torch.eye(3)[None], torch.eye(4)[None], 8, 8, 0.1)
 
 
 def test_product_never_imports_the_oracle():
