@@ -7,8 +7,9 @@
 // sampler and rendering(): torch.cat / slicing / casts, tcnn Frequency / SH / HashGrid / 4 x FullyFusedMLP forward and
 // backward, huber_loss, tanh, exp, sigmoid and their autograd nodes.
 //
-// Backward order (autograd's): colour net -> density net -> feature predictor -> hash grid
-// (table gradient + dL/dx) -> deformation net.  Gradient dtype flow is tcnn's: gradients that cross a
+// Backward order: colour net -> density net (its epilogue also subtracts the feature predictor's output gradient from
+// the hash-feature gradient: the features are that net's huber target) -> hash-table gradient -> feature predictor ->
+// dL/dx of the encoding -> deformation net.  Everything after the table gradient can run under its all-reduce.  Gradient dtype flow is tcnn's: gradients that cross a
 // module boundary are fp16, hidden gradients are fp16, weight / table gradients and dL/dx are fp32.
 #include "field_common.cuh"
 
@@ -309,6 +310,32 @@ __device__ __forceinline__ const CednerfMlpDesc& net_desc(const CednerfFieldDesc
   else return d.f4;
 }
 
+// Output gradient of the feature predictor for 16 of its 32 columns (chunk pair cb of sample s), as 8 packed half2 words:
+// dL/dpred = d_latent * huber'(pred - hash_feat) * selector, huber'(x) = clamp(x, -1, 1)  (model.py:435-438).  The hash
+// features are the huber target too, so the same words are subtracted from the density net's input gradient.
+__device__ __forceinline__ void predictor_dout(const TrainArgs& a, const SavedLayout& sl, int64_t s, int cb, uint32_t* dw) {
+  const int k2 = a.d.f2.dim_in[0];
+  const uint4* ps = reinterpret_cast<const uint4*>(a.saved + sl.o4 + s * 64) + 2 * cb;
+  const uint4* fs = reinterpret_cast<const uint4*>(a.saved + sl.in2 + s * k2 * 2) + 2 * cb;
+  const bool sel = a.selector[s] != 0;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const uint4 p = ps[c], f = fs[c];
+    const uint32_t pw[4] = {p.x, p.y, p.z, p.w}, fw[4] = {f.x, f.y, f.z, f.w};
+    const float4 l0 = *reinterpret_cast<const float4*>(a.d_latent + s * 32 + (2 * cb + c) * 8);
+    const float4 l1 = *reinterpret_cast<const float4*>(a.d_latent + s * 32 + (2 * cb + c) * 8 + 4);
+    const float lg[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 pv = __half22float2(*reinterpret_cast<const __half2*>(&pw[j]));
+      const float2 fv = __half22float2(*reinterpret_cast<const __half2*>(&fw[j]));
+      const float d0 = sel ? lg[2 * j] * fminf(fmaxf(pv.x - fv.x, -1.f), 1.f) : 0.f;
+      const float d1 = sel ? lg[2 * j + 1] * fminf(fmaxf(pv.y - fv.y, -1.f), 1.f) : 0.f;
+      dw[4 * c + j] = pack_h2(d0, d1);
+    }
+  }
+}
+
 template <int NET>
 __device__ __forceinline__ void make_dout(const TrainArgs& a, const SavedLayout& sl, const BwdWorkLayout& wl, uint8_t* tile,
                                           int row, int64_t s, bool ok) {
@@ -338,36 +365,8 @@ __device__ __forceinline__ void make_dout(const TrainArgs& a, const SavedLayout&
       w[0] = pack_h2(gs, hi);
     } else if constexpr (NET == 4) {
       n_chunks = 4;
-      const int k2 = d.f2.dim_in[0];
-      const uint4* ps = reinterpret_cast<const uint4*>(a.saved + sl.o4 + s * 64);
-      const uint4* fs = reinterpret_cast<const uint4*>(a.saved + sl.in2 + s * k2 * 2);
-      uint4* gs = reinterpret_cast<uint4*>(a.work + wl.d_in2 + s * k2 * 2);
-      const bool sel = a.selector[s] != 0;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint4 p = ps[c], f = fs[c];
-        uint4 g = gs[c];
-        const uint32_t pw[4] = {p.x, p.y, p.z, p.w}, fw[4] = {f.x, f.y, f.z, f.w};
-        uint32_t gw[4] = {g.x, g.y, g.z, g.w};
-        const float4 l0 = *reinterpret_cast<const float4*>(a.d_latent + s * 32 + c * 8);
-        const float4 l1 = *reinterpret_cast<const float4*>(a.d_latent + s * 32 + c * 8 + 4);
-        const float lg[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 pv = __half22float2(*reinterpret_cast<const __half2*>(&pw[j]));
-          const float2 fv = __half22float2(*reinterpret_cast<const __half2*>(&fw[j]));
-          // huber'(x) = clamp(x, -1, 1); the loss is masked by the selector (model.py:435-438)
-          const float d0 = sel ? lg[2 * j] * fminf(fmaxf(pv.x - fv.x, -1.f), 1.f) : 0.f;
-          const float d1 = sel ? lg[2 * j + 1] * fminf(fmaxf(pv.y - fv.y, -1.f), 1.f) : 0.f;
-          const uint32_t dw = pack_h2(d0, d1);
-          w[4 * c + j] = dw;
-          // the hash features are the huber target too: dL/dfeat -= dL/dpred (added to the density net's input gradient)
-          __half2 acc = __hsub2(*reinterpret_cast<const __half2*>(&gw[j]), *reinterpret_cast<const __half2*>(&dw));
-          gw[j] = *reinterpret_cast<uint32_t*>(&acc);
-          reinterpret_cast<uint32_t*>(a.work + wl.dy_lm)[(int64_t)(4 * c + j) * a.n + s] = gw[j];
-        }
-        gs[c] = make_uint4(gw[0], gw[1], gw[2], gw[3]);
-      }
+      predictor_dout(a, sl, s, 0, w);
+      predictor_dout(a, sl, s, 1, w + 8);
     } else {  // NET == 1: through aabb normalisation, x + move, move = o[:3]*MS + tanh(o[3:])*MS
       const float* gx = reinterpret_cast<const float*>(a.work + wl.g_xn) + 3 * s;
       float g[3] = {gx[0], gx[1], gx[2]};
@@ -608,13 +607,27 @@ __global__ void __launch_bounds__(BWD_GROUPS * MLP_TILE, 1) field_bwd_kernel(Tra
               uint32_t p[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) p[j] = pack_h2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-              reinterpret_cast<uint4*>(out)[2 * cb] = make_uint4(p[0], p[1], p[2], p[3]);
-              reinterpret_cast<uint4*>(out)[2 * cb + 1] = make_uint4(p[4], p[5], p[6], p[7]);
-              if constexpr (NET == 2) {  // level-major copy of the hash-feature part for the table-gradient kernel
+              if constexpr (NET == 2) {
+                // the hash features are also the huber target of the feature predictor: its output gradient is
+                // subtracted here, so the table gradient does not have to wait for the predictor's backward kernel
+                if (a.d.f4.n_layers > 0 && a.d_latent && cb < 2) {
+                  uint32_t dw[8];
+                  predictor_dout(a, sl, s, cb, dw);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    const __half2 q = __hsub2(*reinterpret_cast<const __half2*>(&p[j]), *reinterpret_cast<const __half2*>(&dw[j]));
+                    p[j] = *reinterpret_cast<const uint32_t*>(&q);
+                  }
+                }
+                // level-major hash-feature gradient for the table-gradient and dL/dx kernels (nothing else reads the
+                // density net's input gradient)
                 uint32_t* lm = reinterpret_cast<uint32_t*>(a.work + wl.dy_lm);
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                   if (8 * cb + j < a.d.levels.n_levels) lm[(int64_t)(8 * cb + j) * n + s] = p[j];
+              } else {
+                reinterpret_cast<uint4*>(out)[2 * cb] = make_uint4(p[0], p[1], p[2], p[3]);
+                reinterpret_cast<uint4*>(out)[2 * cb + 1] = make_uint4(p[4], p[5], p[6], p[7]);
               }
             }
           }
@@ -849,14 +862,14 @@ CEDNERF_EXPORT int cednerf_field_train_bwd(const int64_t* ray_indices, const flo
     if ((rc = launch_bwd<3>(a, st))) return rc;
     if ((rc = launch_bwd<2>(a, st))) return rc;
     launches += 2;
-    if (has4) {
-      if ((rc = launch_bwd<4>(a, st))) return rc;
-      ++launches;
-    }
     rc = cednerf_hashgrid_bwd_table_lm(xn, 3, n, &desc->levels, (const uint8_t*)work + wl.dy_lm, g_table, stream);
     if (rc) return rc;
     // g_table is complete here: with phase == 1 the caller can start its all-reduce while phase 2 runs
     if (phase == 1) return cednerf_check_launch("cednerf_field_train_bwd", launches);
+  }
+  if (has4) {  // the predictor's own backward (its weight gradients and dL/dx_norm through its Frequency input)
+    if ((rc = launch_bwd<4>(a, st))) return rc;
+    ++launches;
   }
   hashgrid_bwd_input_lm_kernel<<<cednerf_blocks(n, 256), 256, 0, st>>>(
       xn, n, (const __half*)table_f16, desc->levels, reinterpret_cast<const __half2*>((const uint8_t*)work + wl.dy_lm), g_xn);

@@ -189,8 +189,8 @@ int cednerf_field_train_bwd(const int64_t* ray_indices, const float* t_starts, c
                             const float* d_sigma, const float* d_rgb, const float* d_latent, void* work,
                             float* d_params_deform, float* d_params_density, float* d_params_colour,
                             float* d_params_predict, float* g_table, int phase, void* stream);
-/* phase: 0 = the whole backward; 1 = colour, density and predictor nets + table gradient (g_table is complete on return:
- * a data-parallel caller starts its all-reduce here); 2 = the rest (dL/dx of the encoding, deformation net). */
+/* phase: 0 = the whole backward; 1 = colour and density nets + table gradient (g_table is complete on return: a
+ * data-parallel caller starts its all-reduce here); 2 = the rest (predictor net, dL/dx of the encoding, deformation net). */
 
 /* ---- K4: compositing ------------------------------------------------------------------------------- */
 /* offsets[r] = first sample of ray r (ray_indices sorted); offsets[n_rays] = n_samples */
