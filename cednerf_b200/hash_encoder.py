@@ -29,6 +29,7 @@ class _Base(torch.nn.Module):
                              persistent=False)
         self.begin_fast_hash_level = next((i for i, v in enumerate(self.level_info) if v[4]), int(levels))
         self._f16 = ops._F16Cache()
+        self.hash_table._cednerf_f16 = self._f16  # optim.FusedAdam writes the fp16 copy inside its update pass
 
     def table_f16(self):
         return self._f16.get(self.hash_table, ops.cast_f16)

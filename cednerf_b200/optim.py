@@ -30,6 +30,10 @@ class FusedAdam(torch.optim.Optimizer):
         self.adam_w_mode, self.set_grad_none = bool(adam_w_mode), set_grad_none
         self._step_t = None
 
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._step_t = None  # re-derived from the loaded "step" entries at the next step()
+
     def zero_grad(self, set_to_none=None):
         super().zero_grad(self.set_grad_none if set_to_none is None else set_to_none)
 
@@ -86,12 +90,16 @@ class FusedAdam(torch.optim.Optimizer):
             return loss
         dev = items[0][0].device
         if self._step_t is None:
-            self._step_t = torch.zeros(1, dtype=torch.float32, device=dev)
+            # one shared device counter (every parameter steps together); after load_state_dict it resumes from the
+            # loaded per-parameter "step" entries, which all hold the same value
+            loaded = [st["step"] for st in self.state.values() if "step" in st]
+            start = float(torch.as_tensor(loaded[0]).reshape(-1)[0]) if loaded else 0.0
+            self._step_t = torch.full((1,), start, dtype=torch.float32, device=dev)
         for p, _ in items:
             st = self.state[p]
             if "exp_avg" not in st:
-                st["step"] = self._step_t  # one shared device counter: every parameter steps together
                 st["exp_avg"], st["exp_avg_sq"] = torch.zeros_like(p), torch.zeros_like(p)
+            st["step"] = self._step_t
             cache = getattr(p, "_cednerf_f16", None)  # hash table: fp16 working copy owned by the encoder
             if cache is not None:  # the update pass (re)writes every element of it, also when the step is skipped
                 if cache.val is None or cache.val.numel() != p.numel() or cache.val.device != p.device:

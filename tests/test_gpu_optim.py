@@ -95,3 +95,32 @@ def test_fused_adam_without_scaler_and_weight_decay_modes():
             ropt.step()
             opt.step()
         torch.testing.assert_close(p.detach().cpu(), q.detach(), rtol=2e-5, atol=1e-7)
+
+
+def test_fused_adam_resumes_from_a_state_dict():
+    """Checkpoint / resume (train_real.py:433-441 saves the optimiser state): 3 steps, state_dict -> new optimiser, 2 more
+    steps == 5 uninterrupted steps (bias corrections continue from the loaded step count)."""
+    import cednerf_b200 as cb
+
+    g = torch.Generator().manual_seed(9)
+    p0 = (torch.rand(9000, generator=g) - 0.5)
+    grads = [torch.randn(9000, generator=g) * 0.1 for _ in range(5)]
+
+    def run(opt, p, gs):
+        for x in gs:
+            p.grad = x.to(DEV)
+            opt.step()
+
+    a = torch.nn.Parameter(p0.clone().to(DEV))
+    opt_a = cb.optim.FusedAdam([a], lr=3e-3, eps=1e-15)
+    run(opt_a, a, grads)
+    b = torch.nn.Parameter(p0.clone().to(DEV))
+    opt_b = cb.optim.FusedAdam([b], lr=3e-3, eps=1e-15)
+    run(opt_b, b, grads[:3])
+    sd = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in opt_b.state_dict().items()}
+    c = torch.nn.Parameter(b.detach().clone())
+    opt_c = cb.optim.FusedAdam([c], lr=3e-3, eps=1e-15)
+    opt_c.load_state_dict(sd)
+    run(opt_c, c, grads[3:])
+    assert torch.equal(c.detach(), a.detach())
+    assert float(opt_c.state[c]["step"].item()) == 5.0
