@@ -12,7 +12,7 @@ from __future__ import annotations
 import torch
 
 from ._lib import call, ptr, stream
-from .ops import _f32c
+from .ops import _f32c, _sempty
 
 F32, F64, I64 = torch.float32, torch.float64, torch.int64
 
@@ -51,7 +51,7 @@ class TrainingLossFunction(torch.autograd.Function):
         g = g.detach().to(F32).reshape(1).contiguous()
         d_rgb = torch.empty_like(rgb) if need[0] else None
         d_acc = torch.empty(n_rays, device=dev) if (has_acc and need[1]) else None
-        d_rgbs = torch.empty_like(rgbs_c) if (has_rgbs and need[3]) else None
+        d_rgbs = _sempty(rgbs_c.shape[0], 3, device=dev) if (has_rgbs and need[3]) else None
         d_lat = torch.empty(n_rays, n_lat, device=dev) if (n_lat and need[6]) else None
         call("cednerf_training_loss_bwd", ptr(g), ptr(rgb), ptr(acc_c) if has_acc else None, ptr(pixels), n_rays,
              ptr(rgbs_c) if has_rgbs else None, ptr(w_c) if has_rgbs else None, ptr(ridx) if has_rgbs else None, n_s,

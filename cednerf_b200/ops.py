@@ -127,9 +127,9 @@ class MarchInputs:
     def fill_packed_from_runs(self, sm_starts, total):
         """Packed fill replaying the recorded runs; rays with more than RUN_CAP runs take the full-march fill."""
         dev = self.o.device
-        t0 = torch.empty(total, device=dev)
-        t1 = torch.empty(total, device=dev)
-        ridx = torch.empty(total, dtype=I64, device=dev)
+        t0 = _sempty(total, device=dev)
+        t1 = _sempty(total, device=dev)
+        ridx = _sempty(total, dtype=I64, device=dev)
         overflow = torch.empty(self.n, dtype=torch.bool, device=dev)
         rt, rn, nr = self.runs
         call("cednerf_march_fill_runs", self.n, ptr(sm_starts), ptr(rt), ptr(rn), ptr(nr), self.RUN_CAP, self.step,
@@ -143,9 +143,9 @@ class MarchInputs:
 
     def fill_packed(self, sm_starts, total):
         dev = self.o.device
-        t0 = torch.empty(total, device=dev)
-        t1 = torch.empty(total, device=dev)
-        ridx = torch.empty(total, dtype=I64, device=dev)
+        t0 = _sempty(total, device=dev)
+        t1 = _sempty(total, device=dev)
+        ridx = _sempty(total, dtype=I64, device=dev)
         term = torch.empty(self.n, device=dev)
         call("cednerf_march", *self._common(1), None, ptr(sm_starts), None, None, None, None, None, None, None,
              ptr(t0), ptr(t1), ptr(ridx), None, None, ptr(term), None, None, None, 0, None, stream())
@@ -205,6 +205,36 @@ def cast_f16(src: torch.Tensor) -> torch.Tensor:
 
 def _cap(n: int) -> int:
     return (int(n) + 32767) // 32768 * 32768
+
+
+# Sample-sized buffers: the number of marched / visible samples changes a little with every batch, and a caching
+# allocator serves a request that is a few KB larger than last time with fresh cudaMallocs (bursts of 10-100 ms when a
+# size class boundary is crossed).  `_sempty` therefore allocates at a sticky capacity - the smallest remembered one in
+# [n, 1.3 n], else a new one 10 % above n - and returns the leading n rows: in the steady state of a training loop every
+# request repeats the size of the previous step exactly.
+_capacities: List[int] = []
+
+
+def _sticky_capacity(n: int) -> int:
+    n = int(n)
+    if n < 65536:
+        return n
+    best = 0
+    for c in _capacities:
+        if n <= c <= n * 13 // 10 and (best == 0 or c < best):
+            best = c
+    if best == 0:
+        best = (n * 11 // 10 + 65535) // 65536 * 65536
+        _capacities.append(best)
+        if len(_capacities) > 64:
+            del _capacities[0]
+    return best
+
+
+def _sempty(n: int, *tail, dtype=None, device=None) -> torch.Tensor:
+    cap = _sticky_capacity(n)
+    t = torch.empty((cap,) + tuple(tail), dtype=dtype, device=device)
+    return t if cap == n else t[:n]
 
 
 _param_epoch = 0
@@ -389,7 +419,7 @@ def offsets_from_packed(packed_info: torch.Tensor) -> torch.Tensor:
 def visibility_mask(t_starts, t_ends, sigmas, offsets, n_rays, early_stop_eps, alpha_thre, want_counts=False):
     """-> keep bool [S] (and, with want_counts, the per-ray number of kept samples int32 [n_rays])."""
     t0, t1, sg = _f32c(t_starts), _f32c(t_ends), _f32c(sigmas)
-    keep = torch.empty(t0.numel(), dtype=torch.bool, device=t0.device)
+    keep = _sempty(t0.numel(), dtype=torch.bool, device=t0.device)
     counts = torch.empty(n_rays, dtype=I32, device=t0.device) if want_counts else None
     call("cednerf_visibility_mask", ptr(t0), ptr(t1), ptr(sg), ptr(offsets), t0.numel(), n_rays,
          float(early_stop_eps), float(alpha_thre), ptr(keep), ptr(counts), stream())
@@ -404,8 +434,8 @@ def visible_samples(t_starts, t_ends, sigmas, offsets, n_rays, early_stop_eps, a
     starts, _, total = exclusive_scan(counts, want_packed=False)
     n_kept = int(total.item())
     dev = t0.device
-    ridx = torch.empty(n_kept, dtype=I64, device=dev)
-    o0, o1 = torch.empty(n_kept, device=dev), torch.empty(n_kept, device=dev)
+    ridx = _sempty(n_kept, dtype=I64, device=dev)
+    o0, o1 = _sempty(n_kept, device=dev), _sempty(n_kept, device=dev)
     if n_kept:
         call("cednerf_compact_samples", ptr(keep), ptr(offsets), ptr(starts), ptr(t0), ptr(t1), t0.numel(), n_rays,
              ptr(ridx), ptr(o0), ptr(o1), stream())
@@ -420,7 +450,7 @@ class RenderWeightFunction(torch.autograd.Function):
         t0, t1, sg = _f32c(t_starts), _f32c(t_ends), _f32c(sigmas)
         pf = None if prefix_trans is None else _f32c(prefix_trans)
         s = t0.numel()
-        w, tr, al = (torch.empty(s, device=t0.device) for _ in range(3))
+        w, tr, al = (_sempty(s, device=t0.device) for _ in range(3))
         call("cednerf_composite_fwd", ptr(t0), ptr(t1), ptr(sg), None, ptr(pf), ptr(offsets), None, 0, s, n_rays,
              ptr(w), ptr(tr), ptr(al), None, None, None, None, 0, 0.0, stream())
         ctx.save_for_backward(t0, t1, tr, al, offsets)
@@ -432,7 +462,7 @@ class RenderWeightFunction(torch.autograd.Function):
     def backward(ctx, gw, gt, ga):
         t0, t1, tr, al, offsets = ctx.saved_tensors
         s = t0.numel()
-        gs = torch.empty(s, device=t0.device)
+        gs = _sempty(s, device=t0.device)
         gw, gt, ga = (None if g is None else _f32c(g) for g in (gw, gt, ga))
         call("cednerf_composite_bwd", ptr(t0), ptr(t1), None, ptr(tr), ptr(al), ptr(offsets), None, 0, s, ctx.n_rays,
              None, None, None, None, None, ptr(gw), ptr(gt), ptr(ga), ptr(gs), None, 0.0, stream())
@@ -459,8 +489,8 @@ class AccumulateFunction(torch.autograd.Function):
         w, v, ridx = ctx.saved_tensors
         v = v if ctx.has_v else None
         g = _f32c(g)
-        gw = torch.empty_like(w) if ctx.needs_input_grad[0] else None
-        gv = torch.empty_like(v) if (ctx.has_v and ctx.needs_input_grad[1]) else None
+        gw = _sempty(w.numel(), device=w.device) if ctx.needs_input_grad[0] else None
+        gv = _sempty(v.shape[0], v.shape[1], device=v.device) if (ctx.has_v and ctx.needs_input_grad[1]) else None
         if gw is not None or gv is not None:
             call("cednerf_accumulate_bwd", ptr(w), ptr(v), ctx.c, ptr(ridx), w.numel(), ptr(g), ptr(gw), ptr(gv),
                  stream())
@@ -498,7 +528,7 @@ class CompositeFunction(torch.autograd.Function):
         if bkgd is not None:
             bk = _f32c(bkgd)
             stride = 3 if bk.numel() == 3 * n_rays and bk.dim() == 2 and n_rays > 1 else 0
-        w, tr, al = (torch.empty(s, device=dev) for _ in range(3))
+        w, tr, al = (_sempty(s, device=dev) for _ in range(3))
         colors = torch.empty(n_rays, 3, device=dev)
         opac, depth, draw = (torch.empty(n_rays, 1, device=dev) for _ in range(3))
         eps = float(torch.finfo(torch.float32).eps)
@@ -514,8 +544,8 @@ class CompositeFunction(torch.autograd.Function):
         t0, t1, rgb, tr, al, offsets, opac, draw, bk = ctx.saved_tensors
         bk = bk if ctx.has_bk else None
         s = t0.numel()
-        gs = torch.empty(s, device=t0.device)
-        grgb = torch.empty(s, 3, device=t0.device) if ctx.needs_input_grad[3] else None
+        gs = _sempty(s, device=t0.device)
+        grgb = _sempty(s, 3, device=t0.device) if ctx.needs_input_grad[3] else None
         gc, go, gd, gw, gt, ga = (None if g is None else _f32c(g) for g in (gc, go, gd, gw, gt, ga))
         call("cednerf_composite_bwd", ptr(t0), ptr(t1), ptr(rgb), ptr(tr), ptr(al), ptr(offsets), ptr(bk), ctx.stride,
              s, ctx.n_rays, ptr(opac), ptr(draw), ptr(gc), ptr(go), ptr(gd), ptr(gw), ptr(gt), ptr(ga), ptr(gs),
@@ -579,8 +609,8 @@ def field_fwd(desc: FieldDesc, images, table_f16, n: int, sigma_only: bool, pack
     (computed and written); n is then the capacity of the buffers and no host read of the count is needed."""
     _lib.check_device()
     dev = table_f16.device
-    sigma = torch.empty(n, device=dev)
-    rgb = None if sigma_only else torch.empty(n, 3, device=dev)
+    sigma = _sempty(n, device=dev)
+    rgb = None if sigma_only else _sempty(n, 3, device=dev)
     ts = _f32c(timestamps).view(-1)
     if packed is not None:
         ridx, t0, t1, o, d = packed
@@ -621,14 +651,14 @@ class FieldTrainFunction(torch.autograd.Function):
         ridx = ridx.detach().to(I64).contiguous()
         t0, t1, rays_o, rays_d = _f32c(t0), _f32c(t1), _f32c(rays_o), _f32c(rays_d)
         ts = _f32c(ts).view(-1)
-        sigma = torch.empty(n, device=dev)
-        rgb = torch.empty(n, 3, device=dev)
-        latent = torch.empty(n, 32, device=dev) if want_latent else None
-        selector = torch.empty(n, dtype=torch.bool, device=dev)
-        move = torch.empty(n, 3, device=dev)
+        sigma = _sempty(n, device=dev)
+        rgb = _sempty(n, 3, device=dev)
+        latent = _sempty(n, 32, device=dev) if want_latent else None
+        selector = _sempty(n, dtype=torch.bool, device=dev)
+        move = _sempty(n, 3, device=dev)
         # capacity in steps of 32 Ki samples: the visible-sample count changes a little every step, and a 1 GB buffer that
         # grows by a few KB would make the caching allocator cudaMalloc (and sometimes free + retry) in the hot loop
-        saved = torch.empty(max(int(lib.cednerf_field_saved_bytes(ctypes.byref(desc), _cap(n))), 16), dtype=U8, device=dev)
+        saved = torch.empty(max(int(lib.cednerf_field_saved_bytes(ctypes.byref(desc), _sticky_capacity(n))), 16), dtype=U8, device=dev)
         call("cednerf_field_train_fwd", ptr(ridx), ptr(t0), ptr(t1), ptr(rays_o), ptr(rays_d), ptr(ts), int(t_stride), n,
              ptr(images[0]), ptr(images[1]), ptr(images[2]), ptr(images[3]), ptr(table_f16), ctypes.byref(desc),
              ptr(sigma), ptr(rgb), ptr(latent), ptr(selector), ptr(move), ptr(saved), stream())
@@ -666,7 +696,7 @@ class FieldTrainFunction(torch.autograd.Function):
         dl = None
         if ctx.has4 and d_latent is not None and d_latent.numel():
             dl = _f32c(d_latent)
-        work = torch.empty(max(int(lib.cednerf_field_bwd_workspace_bytes(ctypes.byref(ctx.desc), _cap(n))), 16), dtype=U8,
+        work = torch.empty(max(int(lib.cednerf_field_bwd_workspace_bytes(ctypes.byref(ctx.desc), _sticky_capacity(n))), 16), dtype=U8,
                            device=dev)
         hook = _table_grad_hook
         for phase in ((1, 2) if hook is not None else (0,)):
