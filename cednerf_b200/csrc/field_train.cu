@@ -382,8 +382,9 @@ __device__ __forceinline__ void make_dout(const TrainArgs& a, const SavedLayout&
           for (int k = 0; k < 4; ++k) {
             const float2 gv = __half22float2(*reinterpret_cast<const __half2*>(&qw[k]));
             const float sc = (float)(1 << k);
-            const float ph = xs[dim] * sc;
-            acc += (gv.x * cospif(ph) + gv.y * cospif(ph + 0.5f)) * sc * 3.14159265358979323846f;
+            float sn, cs;  // d/dx sin(pi ph) = pi 2^k cos(pi ph); d/dx sin(pi (ph + 1/2)) = -pi 2^k sin(pi ph)
+            sincospi_fast(xs[dim] * sc, sn, cs);
+            acc += (gv.x * cs - gv.y * sn) * sc * 3.14159265358979323846f;
           }
           g[dim] += acc;
         }
@@ -570,9 +571,10 @@ __global__ void __launch_bounds__(BWD_GROUPS * MLP_TILE, 1) field_bwd_kernel(Tra
           uint32_t p[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float lo = (mw[j] & 0x7FFFu) && !(mw[j] & 0x8000u) ? __uint_as_float(r[2 * j]) : 0.f;
-            const float hi = (mw[j] & 0x7FFF0000u) && !(mw[j] & 0x80000000u) ? __uint_as_float(r[2 * j + 1]) : 0.f;
-            p[j] = pack_h2(lo, hi);
+            // ReLU mask from the saved post-ReLU activations: one packed compare (0xffff per half that is > 0) and
+            // one AND on the packed gradient - exact zeroing, three instructions per pair of elements
+            const unsigned keep = __hgt2_mask(*reinterpret_cast<const __half2*>(&mw[j]), __float2half2_rn(0.f));
+            p[j] = pack_h2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])) & keep;
           }
           // in place: every MMA that read this tile has completed, and a thread only touches its own row
           *reinterpret_cast<uint4*>(gbuf + swz(gtid, 2 * cb)) = make_uint4(p[0], p[1], p[2], p[3]);

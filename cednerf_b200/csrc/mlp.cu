@@ -222,9 +222,10 @@ __global__ void __launch_bounds__(MLP_TILE) mlp_bwd_kernel(MlpBwdArgs a) {
           uint32_t p[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float lo = (mw[j] & 0x7FFFu) && !(mw[j] & 0x8000u) ? __uint_as_float(r[2 * j]) : 0.f;
-            const float hi = (mw[j] & 0x7FFF0000u) && !(mw[j] & 0x80000000u) ? __uint_as_float(r[2 * j + 1]) : 0.f;
-            p[j] = pack_h2(lo, hi);
+            // ReLU mask from the saved post-ReLU activations: one packed compare (0xffff per half that is > 0) and
+            // one AND on the packed gradient - exact zeroing, three instructions per pair of elements
+            const unsigned keep = __hgt2_mask(*reinterpret_cast<const __half2*>(&mw[j]), __float2half2_rn(0.f));
+            p[j] = pack_h2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])) & keep;
           }
           *reinterpret_cast<uint4*>(nxt + swz(tid, 2 * cb)) = make_uint4(p[0], p[1], p[2], p[3]);
           *reinterpret_cast<uint4*>(nxt + swz(tid, 2 * cb + 1)) = make_uint4(p[4], p[5], p[6], p[7]);
