@@ -124,3 +124,27 @@ def test_fused_adam_resumes_from_a_state_dict():
     run(opt_c, c, grads[3:])
     assert torch.equal(c.detach(), a.detach())
     assert float(opt_c.state[c]["step"].item()) == 5.0
+
+
+def test_fused_adam_more_than_eight_tensors_and_per_group_lr():
+    """More parameter tensors than one launch descriptor holds (8): the step counter must advance once, and every group
+    keeps its own learning rate."""
+    import cednerf_b200 as cb
+
+    g = torch.Generator().manual_seed(21)
+    sizes = [33, 4096 * 3, 7, 5000, 64, 4097, 1, 900, 12288, 77, 4096]
+    p0s = [torch.rand(n, generator=g) - 0.5 for n in sizes]
+    grads = [[torch.randn(n, generator=g) * 0.05 for n in sizes] for _ in range(3)]
+    ref = [torch.nn.Parameter(p.clone()) for p in p0s]
+    ours = [torch.nn.Parameter(p.clone().to(DEV)) for p in p0s]
+    groups = lambda ps: [{"params": ps[:5], "lr": 1e-2}, {"params": ps[5:], "lr": 3e-4}]  # noqa: E731
+    ropt = torch.optim.Adam(groups(ref), eps=1e-15)
+    opt = cb.optim.FusedAdam(groups(ours), eps=1e-15)
+    for gs in grads:
+        for q, p, x in zip(ref, ours, gs):
+            q.grad, p.grad = x.clone(), x.to(DEV)
+        ropt.step()
+        opt.step()
+    assert float(opt.state[ours[0]]["step"].item()) == 3.0
+    for q, p in zip(ref, ours):
+        torch.testing.assert_close(p.detach().cpu(), q.detach(), rtol=2e-5, atol=1e-7)
