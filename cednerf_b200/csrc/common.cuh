@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #define CEDNERF_EXPORT extern "C" __attribute__((visibility("default")))
 
 // Negative library codes (positive values are cudaError_t).
@@ -32,15 +34,41 @@ static inline int cednerf_check_launch(const char* what, int n_launches = 1) {
     }                                                   \
   } while (0)
 
-static inline int cednerf_num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
+// Per-device one-shot state.  Function attributes (the opt-in to > 48 KB of dynamic shared memory) and the SM count
+// belong to a device, and entry points may be called from several host threads: a bit per device in an atomic word;
+// losing a race only repeats an idempotent cudaFuncSetAttribute / attribute query.
+#define CEDNERF_MAX_DEVICES 64
+struct CednerfOncePerDevice {
+  std::atomic<unsigned long long> done{0};
+};
+
+template <typename Kernel>
+static inline int cednerf_opt_in_smem(Kernel kernel, int bytes, CednerfOncePerDevice& once, const char* what) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & (CEDNERF_MAX_DEVICES - 1));
+  if (once.done.load(std::memory_order_acquire) & bit) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    cednerf_set_error("%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
   }
-  return sms;
+  once.done.fetch_or(bit, std::memory_order_release);
+  return 0;
+}
+
+static inline int cednerf_num_sms() {
+  static std::atomic<int> sms[CEDNERF_MAX_DEVICES];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::atomic<int>& slot = sms[dev & (CEDNERF_MAX_DEVICES - 1)];
+  int n = slot.load(std::memory_order_relaxed);
+  if (n == 0) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+    slot.store(n, std::memory_order_relaxed);
+  }
+  return n;
 }
 
 static inline unsigned cednerf_blocks(int64_t n, int threads) {

@@ -270,15 +270,8 @@ CEDNERF_EXPORT int cednerf_field_fwd(const int64_t* ray_indices, const float* t_
   const int n_groups = 7;
   const int smem = desc->f1.image_bytes + desc->f2.image_bytes + (rgb ? desc->f3.image_bytes : 0) +
                    n_groups * MLP_TILE_BYTES + 2048;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(field_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-    if (e != cudaSuccess) {
-      cednerf_set_error("cednerf_field_fwd: %s", cudaGetErrorString(e));
-      return (int)e;
-    }
-    configured = true;
-  }
+  static CednerfOncePerDevice configured;
+  if (int e = cednerf_opt_in_smem(field_fwd_kernel, 224 * 1024, configured, "cednerf_field_fwd")) return e;
   CEDNERF_REQUIRE(smem <= 224 * 1024, "networks too large for the fused kernel");
   FieldFwdArgs a{ray_indices, t_starts, t_ends, rays_o, rays_d, x, dirs, timestamps, t_stride, n, n_device,
                  (const uint8_t*)image_deform, (const uint8_t*)image_density, (const uint8_t*)image_colour,

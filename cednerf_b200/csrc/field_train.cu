@@ -741,15 +741,8 @@ int check_train_desc(const CednerfFieldDesc* d) {
 
 template <int NET>
 int launch_bwd(TrainArgs a, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(field_bwd_kernel<NET>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM_MAX);
-    if (e != cudaSuccess) {
-      cednerf_set_error("cednerf_field_train_bwd: %s", cudaGetErrorString(e));
-      return (int)e;
-    }
-    configured = true;
-  }
+  static CednerfOncePerDevice configured;
+  if (int e = cednerf_opt_in_smem(field_bwd_kernel<NET>, BWD_SMEM_MAX, configured, "cednerf_field_train_bwd")) return e;
   const CednerfMlpDesc& d = NET == 1 ? a.d.f1 : (NET == 2 ? a.d.f2 : (NET == 3 ? a.d.f3 : a.d.f4));
   int groups = BWD_GROUPS;  // as many tiles in flight as shared memory (weights + 48 KB per group) and TMEM allow
   const int fixed = ((d.image_bytes + 1023) & ~1023) + 2048;
@@ -797,15 +790,8 @@ CEDNERF_EXPORT int cednerf_field_train_fwd(const int64_t* ray_indices, const flo
   const int smem = desc->f1.image_bytes + desc->f2.image_bytes + desc->f3.image_bytes +
                    (desc->f4.n_layers > 0 ? desc->f4.image_bytes : 0) + n_groups * MLP_TILE_BYTES + 2048;
   CEDNERF_REQUIRE(smem <= 224 * 1024, "networks too large for the fused kernel");
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(field_train_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-    if (e != cudaSuccess) {
-      cednerf_set_error("cednerf_field_train_fwd: %s", cudaGetErrorString(e));
-      return (int)e;
-    }
-    configured = true;
-  }
+  static CednerfOncePerDevice configured;
+  if (int e = cednerf_opt_in_smem(field_train_fwd_kernel, 224 * 1024, configured, "cednerf_field_train_fwd")) return e;
   TrainArgs a{};
   a.ridx = ray_indices, a.t0 = t_starts, a.t1 = t_ends, a.rays_o = rays_o, a.rays_d = rays_d, a.t = timestamps;
   a.t_stride = t_stride, a.n = n;

@@ -348,8 +348,11 @@ __global__ void cast_f32_to_f16_kernel(const float4* __restrict__ src, uint2* __
 
 int check_levels(const CednerfGridLevels* lv) {
   if (!lv || lv->n_levels < 1 || lv->n_levels > CEDNERF_MAX_LEVELS) return 0;
-  for (int l = 0; l < lv->n_levels; ++l)
+  for (int l = 0; l < lv->n_levels; ++l) {
     if (lv->size[l] == 0) return 0;
+    // hashed levels are reduced with `& (size - 1)` in every kernel (forward, table gradient, fused field kernels)
+    if (lv->hashed[l] && (lv->size[l] & (lv->size[l] - 1u)) != 0u) return 0;
+  }
   return 1;
 }
 

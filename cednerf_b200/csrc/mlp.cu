@@ -341,15 +341,8 @@ CEDNERF_EXPORT int cednerf_mlp_fwd(const void* x_f16, const void* weight_image, 
   CEDNERF_REQUIRE(check_desc(desc), "bad MLP descriptor");
   CEDNERF_REQUIRE(n >= 0, "bad size");
   if (n == 0) return 0;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
-    if (e != cudaSuccess) {
-      cednerf_set_error("cednerf_mlp_fwd: %s", cudaGetErrorString(e));
-      return (int)e;
-    }
-    configured = true;
-  }
+  static CednerfOncePerDevice configured;
+  if (int e = cednerf_opt_in_smem(mlp_fwd_kernel, FWD_SMEM, configured, "cednerf_mlp_fwd")) return e;
   MlpFwdArgs a{(const __half*)x_f16, (const uint8_t*)weight_image, (__half*)out_f16, (__half*)hidden_f16, n, *desc};
   const int64_t tiles = (n + MLP_TILE - 1) / MLP_TILE;
   const int64_t max_ctas = (int64_t)cednerf_num_sms() * 3;
@@ -363,15 +356,8 @@ CEDNERF_EXPORT int cednerf_mlp_bwd(const void* x_f16, const void* hidden_f16, co
   CEDNERF_REQUIRE(check_desc(desc), "bad MLP descriptor");
   CEDNERF_REQUIRE(n >= 0 && (desc->n_layers == 1 || hidden_f16), "bad arguments");
   if (n == 0) return 0;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
-    if (e != cudaSuccess) {
-      cednerf_set_error("cednerf_mlp_bwd: %s", cudaGetErrorString(e));
-      return (int)e;
-    }
-    configured = true;
-  }
+  static CednerfOncePerDevice configured;
+  if (int e = cednerf_opt_in_smem(mlp_bwd_kernel, BWD_SMEM, configured, "cednerf_mlp_bwd")) return e;
   uint32_t cols = 64u * (uint32_t)(desc->n_layers + 1), alloc = 64;
   while (alloc < cols) alloc <<= 1;
   MlpBwdArgs a{(const __half*)x_f16, (const __half*)hidden_f16, (const __half*)d_out_f16, (const uint8_t*)weight_image,

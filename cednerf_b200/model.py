@@ -66,7 +66,8 @@ class DNGPradianceField(torch.nn.Module):
             "log2_hashmap_size": log2_hashmap_size, "base_resolution": base_resolution, "per_level_scale": b}, seed + 2)
         base_in, self.geo_feat_dim_head = self.hash_encoder.n_output_dims, geo_feat_dim
         if use_time_embedding:
-            self.time_encoder = (SinusoidalEncoderWithExp if use_time_attenuation else SinusoidalEncoder)(1, 0, 4, True)
+            self.time_encoder = SinusoidalEncoder(1, 0, 4, True)               # both exist in the reference
+            self.time_encoder_feat = SinusoidalEncoderWithExp(1, 0, 4, True)   # (model.py:266-267) and in its checkpoints
             if time_inject_before_sigma:
                 base_in += 9
             else:
@@ -159,7 +160,7 @@ class DNGPradianceField(torch.nn.Module):
             with torch.no_grad():
                 if self.use_time_attenuation:
                     move = torch.linalg.norm(move.detach(), dim=-1)
-                    time_encode = self.time_encoder(t.view(-1, 1), move.view(-1, 1))
+                    time_encode = self.time_encoder_feat(t.view(-1, 1), move.view(-1, 1))
                 else:
                     time_encode = self.time_encoder(t.view(-1, 1))
             if self.time_inject_before_sigma:

@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import math
+import weakref
 from typing import Optional
 
 import torch
@@ -26,23 +27,36 @@ def ray_aabb_intersect(rays_o, rays_d, aabbs, near_plane: float = -math.inf, far
     return ops.ray_aabb_intersect(rays_o, rays_d, aabbs, near_plane, far_plane, miss_value)
 
 
+# Bit-packed copies of `binaries` tensors, keyed by the tensor OBJECT (id + weak reference) and validated by
+# (storage, version, shape): a second estimator whose buffer happens to land on the same allocator block with the same
+# version counter can never hit another tensor's entry, and entries die with their tensor.
 _BITS_CACHE = {}
 
 
+def _bits_key(binaries: torch.Tensor):
+    return (binaries.data_ptr(), binaries._version, tuple(binaries.shape))
+
+
+def _remember(binaries: torch.Tensor, bits: torch.Tensor) -> None:
+    ident = id(binaries)
+    _BITS_CACHE[ident] = (weakref.ref(binaries, lambda _r, i=ident: _BITS_CACHE.pop(i, None)), _bits_key(binaries), bits)
+
+
 def occupancy_bits(binaries: torch.Tensor) -> torch.Tensor:
-    """Bit-packed copy of `binaries`, cached on (storage, version) so repeated marches do not re-pack."""
-    key = (binaries.data_ptr(), binaries._version, tuple(binaries.shape))
-    hit = _BITS_CACHE.get("k")
-    if hit is not None and hit[0] == key:
-        return hit[1]
+    """Bit-packed copy of `binaries`, cached per tensor object and version so repeated marches do not re-pack."""
+    hit = _BITS_CACHE.get(id(binaries))
+    if hit is not None and hit[0]() is binaries and hit[1] == _bits_key(binaries):
+        return hit[2]
     bits = ops.pack_occupancy(binaries)
-    _BITS_CACHE["k"] = (key, bits)
+    _remember(binaries, bits)
     return bits
 
 
 def set_occupancy_bits(binaries: torch.Tensor, bits: torch.Tensor) -> None:
-    """Install a bit field produced together with `binaries` by a raw kernel write (no version bump)."""
-    _BITS_CACHE["k"] = ((binaries.data_ptr(), binaries._version, tuple(binaries.shape)), bits)
+    """Install a bit field produced together with `binaries` by a raw kernel write: the write went through a raw
+    pointer, so the tensor's version counter is bumped here (anything else keyed on it must see the change)."""
+    torch.autograd.graph.increment_version(binaries)
+    _remember(binaries, bits)
 
 
 @torch.no_grad()

@@ -189,6 +189,10 @@ def grid_levels(n_levels: int, base_resolution: float, log_per_level_scale: floa
         res = int(math.ceil(s)) + 1
         full = res ** 3
         size = min(int(max_params), (full + 7) // 8 * 8)
+        if full > size and size & (size - 1):
+            # every kernel reduces a hashed index with `& (size - 1)` (tcnn's and the reference's configurations are
+            # 2^log2_hashmap_size); a table of another size would need the reference's `% size` in all of them
+            raise ValueError(f"hashed level {l}: max_params must be a power of two, got {max_params}")
         g.scale[l] = float(np.float32(s))
         g.res[l], g.size[l], g.offset[l], g.hashed[l] = res, size, off, int(full > size)
         info.append((float(np.float32(s)), res, size, off, full > size))
@@ -614,9 +618,10 @@ def field_fwd(desc: FieldDesc, images, table_f16, n: int, sigma_only: bool, pack
     ts = _f32c(timestamps).view(-1)
     if packed is not None:
         ridx, t0, t1, o, d = packed
-        args = (ptr(ridx.detach().to(I64).contiguous()), ptr(_f32c(t0)), ptr(_f32c(t1)), ptr(_f32c(o)), ptr(_f32c(d)),
-                None, None)
-        keep = args  # the temporaries must outlive the launch (stream-ordered, same stream: safe to drop after)
+        # converted copies are bound to locals so that they outlive the launch (a temporary freed right after its ptr()
+        # would hand its block to the next conversion: two arguments aliasing one buffer)
+        ridx_c, t0_c, t1_c, o_c, d_c = ridx.detach().to(I64).contiguous(), _f32c(t0), _f32c(t1), _f32c(o), _f32c(d)
+        args = (ptr(ridx_c), ptr(t0_c), ptr(t1_c), ptr(o_c), ptr(d_c), None, None)
     else:
         x, dirs = points
         xs = _f32c(x)
@@ -624,6 +629,7 @@ def field_fwd(desc: FieldDesc, images, table_f16, n: int, sigma_only: bool, pack
         args = (None, None, None, None, None, ptr(xs), ptr(ds))
     call("cednerf_field_fwd", *args, ptr(ts), int(t_stride), n, ptr(images[0]), ptr(images[1]), ptr(images[2]),
          ptr(table_f16), ctypes.byref(desc), ptr(sigma), ptr(rgb), ptr(n_dev), stream())
+    del args  # (ridx_c ... d_c / xs, ds stay referenced by this frame until here: the launch is enqueued)
     return sigma, rgb
 
 

@@ -87,17 +87,29 @@ class Network(torch.nn.Module):
 
 
 class NetworkWithInputEncoding(torch.nn.Module):
+    """tinycudann.NetworkWithInputEncoding: ONE module with ONE flat `params` Parameter (encoding parameters, none for
+    Frequency, followed by the network's), so a reference checkpoint's `xyz_wrap.params` / `mlp_feat_prediction.params`
+    keys load with strict=True.  `encoding` and `network` are helpers that are deliberately NOT registered as
+    sub-modules (they would add `*.network.params` / `*.encoding.params` keys tcnn does not have); `network` borrows
+    this module's Parameter object, which `.to()` / `.cuda()` update in place."""
+
     def __init__(self, n_input_dims, n_output_dims, encoding_config, network_config, seed: int = 1337):
         super().__init__()
-        self.encoding = Encoding(n_input_dims, encoding_config, seed)
-        if self.encoding.params.numel():
+        encoding = Encoding(n_input_dims, encoding_config, seed)
+        if encoding.params.numel():
             raise NotImplementedError("only parameter-free input encodings (the reference uses Frequency)")
-        self.network = Network(self.encoding.n_output_dims, n_output_dims, network_config, seed)
+        network = Network(encoding.n_output_dims, n_output_dims, network_config, seed)
+        self.params = network.params  # registered here, once
+        del network._parameters["params"]
+        network.__dict__["params"] = self.params
+        self.__dict__["encoding"], self.__dict__["network"] = encoding, network
         self.n_input_dims, self.n_output_dims = n_input_dims, n_output_dims
 
-    @property
-    def params(self):
-        return self.network.params
+    def _apply(self, fn, recurse=True):
+        out = super()._apply(fn, recurse)
+        if self.network.__dict__["params"] is not self.params:  # parameter objects were replaced, not updated in place
+            self.network.__dict__["params"] = self.params
+        return out
 
     def forward(self, x):
         if self.encoding.cfg["otype"] == "Frequency":  # write the padded MLP operand directly

@@ -83,6 +83,11 @@ class DNGPradianceField(torch.nn.Module):
                                                   "base_resolution": base_resolution, "per_level_scale": b}, seed + 2)
         base_in, self.geo_feat_dim_head = self.hash_encoder.n_output_dims, geo_feat_dim
         if use_time_embedding:
+            # the reference's encoder modules carry these buffers into its checkpoints (cednerf/encoder.py:18-20, :55-60)
+            self.time_encoder, self.time_encoder_feat = torch.nn.Module(), torch.nn.Module()
+            self.time_encoder.register_buffer("scales", torch.tensor([2 ** i for i in range(4)]))
+            self.time_encoder_feat.register_buffer("scales", torch.tensor([2 ** i for i in range(4)]))
+            self.time_encoder_feat.register_buffer("scales_move", torch.tensor([i * 2 ** i for i in range(4)]))
             if time_inject_before_sigma:
                 base_in += 9
             else:

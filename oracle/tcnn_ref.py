@@ -230,16 +230,19 @@ class Network(torch.nn.Module):
 
 
 class NetworkWithInputEncoding(torch.nn.Module):
+    """One module, one flat `params` (tcnn's torch binding): checkpoint key `<name>.params`."""
+
     def __init__(self, n_input_dims, n_output_dims, encoding_config, network_config, seed: int = 1337):
         super().__init__()
-        self.encoding = Encoding(n_input_dims, encoding_config, seed)
-        assert self.encoding.params.numel() == 0, "oracle: only parameter-free input encodings"
-        self.network = Network(self.encoding.n_output_dims, n_output_dims, network_config, seed)
+        encoding = Encoding(n_input_dims, encoding_config, seed)
+        assert encoding.params.numel() == 0, "oracle: only parameter-free input encodings"
+        network = Network(encoding.n_output_dims, n_output_dims, network_config, seed)
+        self.params = network.params
+        del network._parameters["params"]
+        network.__dict__["params"] = self.params
+        self.__dict__["encoding"], self.__dict__["network"] = encoding, network  # helpers, not sub-modules
         self.n_input_dims, self.n_output_dims = n_input_dims, n_output_dims
 
-    @property
-    def params(self):
-        return self.network.params
-
     def forward(self, x):
+        self.network.__dict__["params"] = self.params
         return self.network(self.encoding(x))

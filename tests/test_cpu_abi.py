@@ -156,3 +156,30 @@ def test_module_surface_mirrors_reference_names():
     assert field.hash_encoder.params.numel() == 2 * 23928800
     assert field.mlp_base.n_input_dims == 41 and field.mlp_head.n_input_dims == 19
     assert field.xyz_wrap.n_output_dims == 6 and field.mlp_feat_prediction.n_output_dims == 32
+
+
+def test_state_dict_has_the_reference_checkpoint_key_set():
+    """A `model.pth` written by train_real.py:438 must load with strict=True: tcnn modules save ONE flat `params` each
+    (NetworkWithInputEncoding included), the two time encoders save their `scales` buffers (cednerf/encoder.py:18-20,
+    :55-60) and both exist whenever -te is on (cednerf/model.py:266-267)."""
+    import cednerf_b200 as cb
+
+    field = cb.DNGPradianceField([-1, -1, -1, 1, 1, 1], n_levels=4, log2_hashmap_size=10, dst_resolution=64,
+                                 use_feat_predict=True, use_weight_predict=True, use_time_embedding=True,
+                                 use_time_attenuation=True, use_div_offsets=True)
+    want = {"aabb", "xyz_wrap.params", "direction_encoding.params", "hash_encoder.params", "time_encoder.scales",
+            "time_encoder_feat.scales", "time_encoder_feat.scales_move", "mlp_base.params", "mlp_head.params",
+            "mlp_feat_prediction.params", "mlp_weight_prediction.params"}
+    sd = field.state_dict()
+    assert set(sd) == want
+    assert sd["time_encoder_feat.scales_move"].tolist() == [0, 2, 8, 24] and sd["time_encoder.scales"].tolist() == [1, 2, 4, 8]
+    # what an optimiser sees: each tensor once, the NetworkWithInputEncoding parameters included
+    names = [n for n, _ in field.named_parameters()]
+    assert len(names) == len(set(names)) == 7 and "xyz_wrap.params" in names
+    # round trip through a fresh module, strict
+    other = cb.DNGPradianceField([-1, -1, -1, 1, 1, 1], n_levels=4, log2_hashmap_size=10, dst_resolution=64,
+                                 use_feat_predict=True, use_weight_predict=True, use_time_embedding=True,
+                                 use_time_attenuation=True, use_div_offsets=True, seed=7)
+    other.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=True)
+    assert torch.equal(other.xyz_wrap.params, field.xyz_wrap.params)
+    assert other.xyz_wrap.network.params is other.xyz_wrap.params  # the helper borrows the registered Parameter

@@ -45,7 +45,8 @@ def gpu_scene(cb, golden):
 def gpu_field(cb, golden, name, extra=None):
     field = cb.DNGPradianceField(golden["scene.aabbs"][-1], **FIELD_KW, **FLAG_SETS[name], **(extra or {}))
     sd = {k[len(name) + 7:]: v for k, v in golden.items() if k.startswith(f"{name}.state.")}
-    missing = field.load_state_dict({k: v for k, v in sd.items() if not k.startswith("time_encoder")}, strict=False)
+    # the golden state dict has the reference's own key set (made by cednerf/model.py): nothing may be left over
+    missing = field.load_state_dict(sd, strict=False)
     assert not missing.unexpected_keys and all("prediction" in k for k in missing.missing_keys)
     return field.to(DEV)
 

@@ -26,7 +26,7 @@ def load_field(golden, name):
     est, _, _ = scene(golden)
     field = cr.DNGPradianceField(est.aabbs[-1], **FIELD_KW, **FLAG_SETS[name])
     sd = {k[len(name) + 7:]: v for k, v in golden.items() if k.startswith(f"{name}.state.")}
-    field.load_state_dict({k: v for k, v in sd.items() if not k.startswith("time_encoder")})
+    field.load_state_dict(sd)  # strict: the reference's exact key set
     return field
 
 
