@@ -48,6 +48,25 @@ class AdamTensors(ctypes.Structure):
                 ("chunk_begin", ctypes.c_int64 * (OPT_MAX_TENSORS + 1))]
 
 
+DP_MAX_RANKS = 8
+
+
+class DpCtrl(ctypes.Structure):
+    _fields_ = [("arrive", ctypes.c_uint32 * DP_MAX_RANKS), ("found_inf", ctypes.c_float), ("timed_out", ctypes.c_uint32)]
+
+
+class DpPeers(ctypes.Structure):
+    _fields_ = [("world", ctypes.c_int), ("rank", ctypes.c_int), ("ctrl", ctypes.c_void_p * DP_MAX_RANKS)]
+
+
+class DpAdam(ctypes.Structure):
+    _fields_ = [("world", ctypes.c_int), ("rank", ctypes.c_int), ("grad", ctypes.c_void_p * DP_MAX_RANKS),
+                ("n_out", ctypes.c_int), ("p32_out", ctypes.c_void_p * DP_MAX_RANKS),
+                ("p16_out", ctypes.c_void_p * DP_MAX_RANKS), ("m", ctypes.c_void_p), ("v", ctypes.c_void_p),
+                ("lo", ctypes.c_int64), ("hi", ctypes.c_int64), ("lr", ctypes.c_float), ("weight_decay", ctypes.c_float),
+                ("grad_div", ctypes.c_float)]
+
+
 # p = pointer, i = int, l = int64, f = float, A = AdamTensors*, G = GridLevels*, M = MlpDesc*, F = FieldDesc*
 _SIGNATURES = {
     "cednerf_ray_aabb_intersect": "pplpifffpppp",
@@ -86,10 +105,18 @@ _SIGNATURES = {
     "cednerf_training_loss_fwd": "ppplppplpiffppp",
     "cednerf_training_loss_bwd": "pppplpppliffppppp",
     "cednerf_adam_step": "Apippfffip",
+    "cednerf_peer_alloc": "lp",
+    "cednerf_peer_free": "p",
+    "cednerf_ipc_export": "pp",
+    "cednerf_ipc_open": "pp",
+    "cednerf_ipc_close": "p",
+    "cednerf_dp_barrier": "Puip",
+    "cednerf_dp_found_inf": "Pppp",
+    "cednerf_dp_adam": "Dpppfffip",
 }
 _CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_int64, "f": ctypes.c_float,
        "G": ctypes.POINTER(GridLevels), "M": ctypes.POINTER(MlpDesc), "F": ctypes.POINTER(FieldDesc),
-       "A": ctypes.POINTER(AdamTensors)}
+       "A": ctypes.POINTER(AdamTensors), "P": ctypes.POINTER(DpPeers), "D": ctypes.POINTER(DpAdam), "u": ctypes.c_uint32}
 
 _lib = None
 
@@ -106,6 +133,7 @@ def load() -> ctypes.CDLL:
     lib.cednerf_last_error.restype = ctypes.c_char_p
     lib.cednerf_scan_workspace_bytes.restype = ctypes.c_int64
     lib.cednerf_launch_count.restype = ctypes.c_int64
+    lib.cednerf_dp_ctrl_bytes.restype = ctypes.c_int64
     for name in ("cednerf_field_saved_bytes", "cednerf_field_bwd_workspace_bytes"):
         getattr(lib, name).restype = ctypes.c_int64
         getattr(lib, name).argtypes = [ctypes.POINTER(FieldDesc), ctypes.c_int64]
@@ -121,7 +149,7 @@ def load() -> ctypes.CDLL:
 def exported_symbols():
     return sorted(list(_SIGNATURES) + ["cednerf_last_error", "cednerf_abi_version", "cednerf_check_device",
                                        "cednerf_scan_workspace_bytes", "cednerf_launch_count", "cednerf_field_saved_bytes",
-                                       "cednerf_field_bwd_workspace_bytes"])
+                                       "cednerf_field_bwd_workspace_bytes", "cednerf_dp_ctrl_bytes"])
 
 
 def ptr(t: Optional[torch.Tensor]):

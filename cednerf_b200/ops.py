@@ -644,6 +644,17 @@ def set_table_grad_hook(fn):
     _table_grad_hook = fn
 
 
+_table_grad_alloc = None
+
+
+def set_table_grad_alloc(fn):
+    """fn(shape, device) -> zero-filled fp32 tensor (or None) that the fused training backward accumulates the hash-table
+    gradient into.  dp.DistributedFusedAdam hands out its peer-visible buffer here, so that the other ranks read this
+    rank's gradient where the kernel wrote it.  None removes the hook."""
+    global _table_grad_alloc
+    _table_grad_alloc = fn
+
+
 class FieldTrainFunction(torch.autograd.Function):
     """Training-mode DNGPradianceField.forward on packed ray samples: one forward launch, backward = one tensor-core
     launch per network + the hash-grid backward.  Returns (sigma [n], rgb [n,3], latent [n,32] | None, selector, move)."""
@@ -696,7 +707,9 @@ class FieldTrainFunction(torch.autograd.Function):
             o += kp
         g1, g2, g3 = views[:3]
         g4 = views[3] if want4 else None
-        gt = torch.zeros(st, dtype=F32, device=dev)
+        gt = _table_grad_alloc(st, dev) if _table_grad_alloc is not None else None
+        if gt is None:
+            gt = torch.zeros(st, dtype=F32, device=dev)
         d_sigma = torch.zeros(n, device=dev) if d_sigma is None else _f32c(d_sigma)
         d_rgb = torch.zeros(n, 3, device=dev) if d_rgb is None else _f32c(d_rgb)
         dl = None

@@ -257,6 +257,48 @@ int cednerf_adam_step(const CednerfAdamTensors* tensors, float* step, int advanc
 
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Data-parallel optimiser step over NVLink peer memory (no reference counterpart - the reference
+ * trains on cuda:0 only, train_real.py:81).  One process per GPU.  Gradient, fp32 master and fp16 working copy of the
+ * hash table live in cednerf_peer_alloc memory that the other ranks map with cednerf_ipc_open (the caller exchanges
+ * the 64-byte handles).  cednerf_dp_barrier -> cednerf_dp_found_inf -> cednerf_dp_adam -> cednerf_dp_barrier, all
+ * stream-ordered, replace gradient all-reduce + replicated Adam: every rank sums ITS range of all ranks' gradients
+ * over NVLink (reduce-scatter), applies unscale + Adam to that range and stores the new fp32 / fp16 values into all
+ * replicas (all-gather).  Up to 8 ranks. */
+#define CEDNERF_DP_MAX_RANKS 8
+typedef struct CednerfDpCtrl {   /* one per rank, in peer-visible memory, zero-initialised */
+  uint32_t arrive[CEDNERF_DP_MAX_RANKS];
+  float found_inf;               /* this rank's local non-finite flag (cednerf_nonfinite_check target) */
+  uint32_t timed_out;            /* != 0: a barrier gave up waiting for a peer */
+} CednerfDpCtrl;
+typedef struct CednerfDpPeers {
+  int world, rank;
+  CednerfDpCtrl* ctrl[CEDNERF_DP_MAX_RANKS];  /* every rank's control block as mapped in this process */
+} CednerfDpPeers;
+typedef struct CednerfDpAdam {
+  int world, rank;
+  const float* grad[CEDNERF_DP_MAX_RANKS];    /* every rank's gradient buffer (same layout), as mapped here */
+  int n_out;                                  /* replicas to update: world (broadcast) or 1 (local only) */
+  float* p32_out[CEDNERF_DP_MAX_RANKS];       /* fp32 parameter replicas; entry 0 is the local one (also the input) */
+  void* p16_out[CEDNERF_DP_MAX_RANKS];        /* fp16 working copies (nullable entries) */
+  float* m;                                   /* Adam moments of the owned range, indexed from lo */
+  float* v;
+  int64_t lo, hi;                             /* owned element range, lo % 4 == 0 */
+  float lr, weight_decay, grad_div;           /* summed gradient / grad_div (world: average) */
+} CednerfDpAdam;
+int cednerf_peer_alloc(int64_t bytes, void** ptr);            /* cudaMalloc + zero fill */
+int cednerf_peer_free(void* ptr);
+int cednerf_ipc_export(void* ptr, void* handle64);            /* cudaIpcGetMemHandle of a cednerf_peer_alloc pointer */
+int cednerf_ipc_open(const void* handle64, void** ptr);       /* map a peer's allocation on the current device */
+int cednerf_ipc_close(void* ptr);
+int64_t cednerf_dp_ctrl_bytes(void);
+/* epoch increases by one per barrier, identically on all ranks; after timeout_ms the wait gives up and sets timed_out */
+int cednerf_dp_barrier(const CednerfDpPeers* peers, uint32_t epoch, int timeout_ms, void* stream);
+/* *found_out (nullable) = OR of all ranks' found_inf; *step (nullable) += 1 unless set */
+int cednerf_dp_found_inf(const CednerfDpPeers* peers, float* found_out, float* step, void* stream);
+int cednerf_dp_adam(const CednerfDpAdam* args, const float* step, const float* grad_scale /*nullable*/,
+                    const float* found_inf /*nullable*/, float beta1, float beta2, float eps, int adam_w_mode, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Training loss of the reference loop for the canonical flags (train_real.py:369-409): F.mse_loss(rgb, pixels)
  * + w_entropy * acc-entropy (-ae, 1e-3) + w_rgbper * weighted per-sample colour loss (-wr, 1e-3) + latent_losses.mean()
  * (-f).  acc / rgbs / latent nullable (term absent).  sums: 4 doubles of workspace; loss: 1 float. */

@@ -45,6 +45,12 @@ def test_ctypes_signatures_match_header():
                 sig += "M"
             elif "CednerfAdamTensors" in a:
                 sig += "A"
+            elif "CednerfDpPeers" in a:
+                sig += "P"
+            elif "CednerfDpAdam" in a:
+                sig += "D"
+            elif a.startswith("uint32_t "):
+                sig += "u"
             elif "*" in a:
                 sig += "p"
             elif a.startswith("int64_t"):
@@ -65,6 +71,10 @@ def test_descriptor_structs_match_header_layout():
     assert ctypes.sizeof(_lib.MlpDesc) == 4 + 4 * 4 * 5 + 4
     # n_tensors (+ padding to 8), five pointer arrays, n[8], lr[8], weight_decay[8], chunk_begin[9]
     assert ctypes.sizeof(_lib.AdamTensors) == 8 + 5 * 8 * 8 + 8 * 8 + 2 * 4 * 8 + 9 * 8
+    assert ctypes.sizeof(_lib.DpCtrl) == 8 * 4 + 4 + 4 == _lib.load().cednerf_dp_ctrl_bytes()
+    assert ctypes.sizeof(_lib.DpPeers) == 8 + 8 * 8
+    # world, rank, grad[8], n_out (+ padding), p32_out[8], p16_out[8], m, v, lo, hi, lr, weight_decay, grad_div (+ padding)
+    assert ctypes.sizeof(_lib.DpAdam) == 8 + 64 + 8 + 64 + 64 + 16 + 16 + 16
     assert ctypes.sizeof(_lib.FieldDesc) == 6 * 4 + 4 + 3 * 4 + 4 * ctypes.sizeof(_lib.MlpDesc) + ctypes.sizeof(_lib.GridLevels)
 
 
