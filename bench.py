@@ -1,33 +1,43 @@
 #!/usr/bin/env python
-"""Benchmark of the per-ray rendering hot path: DyNeRF flame_salmon_1-shaped train step (BASELINE.json configs[1]).
+"""Benchmark of the per-ray rendering hot path on the configurations BASELINE.json names.
 
     python bench.py --gpus N --steps K --warmup W             # this repo's CUDA path (one rank per GPU under torchrun)
     python bench.py --impl reference --gpus N --steps K ...   # the CPU restatement of the reference path (oracle/)
+    python bench.py --config {dynerf,hypernerf,dnerf} ...     # which configuration is the headline (default dynerf)
 
-One step = the body of the reference's training loop for this path (train_real.py:330-420 without the data loader):
-estimator.update_every_n_steps (works every 16th step; on a twin estimator, see OccupancyUpdate), stratified
-occupancy-grid sampling with the no-grad density pre-pass and visibility filtering, the field forward on the surviving
-samples, compositing, the MSE + auxiliary losses of the canonical DyNeRF flags (-te -ta -df -f -wr -ae), backward,
-GradScaler (2^10) and fused Adam, at the reference schedule's first-iteration learning rate (see TrainState).  The
-reference arm runs the same step on the CPU restatement (oracle/) on a bounded ray sample, without the occupancy
-update (8.4 M CPU field queries per update would only flatter the ratio).
-Rank 0 prints ONE JSON line (see the keys below).  Synthetic data: seeded rays / pixels / occupancy, random-init
-weights with a density boost (cednerf_b200/workload.py)."""
+Headline (configs[1]): DyNeRF flame_salmon_1-shaped TRAIN STEP, 2^18 rays per GPU.  One step = the body of the
+reference's training loop for this path (train_real.py:330-420 without the data loader): estimator.update_every_n_steps
+(works every 16th step; on a twin estimator, see OccupancyUpdate), stratified occupancy-grid sampling with the no-grad
+density pre-pass and visibility filtering, the field forward on the surviving samples, compositing, the MSE + auxiliary
+losses of the canonical flags (-te -ta -df -f -wr -ae), backward, GradScaler (2^10) and fused Adam at the reference
+schedule's first-iteration learning rate (see TrainState).  With N > 1 every rank runs the step on its own 2^18 rays
+(weak scaling) and the optimiser step is dp.DistributedFusedAdam (fused reduce-scatter + Adam + all-gather over NVLink
+peer memory; `--dp nccl` selects the all-reduce path of round 1).
+
+Besides the headline the default run measures, and reports under `configs` / `render` at the END of the JSON line:
+  configs[3]  `render`            the 300-pose novel-view video of the DyNeRF-shaped scene (datasets/utils.py:67-112 spiral,
+                                  t = i/300), frames interleaved over the ranks, no collective (strong scaling);
+  configs[0]  `configs.dnerf`     D-NeRF-shaped 800x800 frames (t = 0.5) through render_image_test;
+  configs[2]  `configs.hypernerf` HyperNeRF-shaped train step (536x960 camera, one timestamp per batch);
+  configs[4]  `configs.dynerf_2p20` (N > 1 only) the DyNeRF train step with 2^20 rays split over the N ranks.
+The reference arm runs the headline configuration on the CPU restatement (oracle/) from the same initial weights, the
+same learning rate and the same loss scaling, on a bounded ray sample, without the occupancy update (8.4 M CPU field
+queries per update would only flatter the ratio).
+Rank 0 prints ONE JSON line.  Synthetic data: seeded rays / pixels / occupancy, random-init weights with a density
+boost (cednerf_b200/workload.py)."""
 from __future__ import annotations
 
 import argparse
+import importlib.util
 import json
 import os
 
 # Sample-sized buffers change size a little every step (the visible-sample count follows the field, and the named
 # configuration sits right at 2^20 samples - a size-class boundary of any power-of-two rounding).  The library allocates
 # them at sticky capacities (ops._sempty), so the caching allocator sees the same request sizes step after step; 1/8
-# power-of-two rounding keeps the few remaining torch-side temporaries in one class.  (Measured over 120 steps: no step
-# above 6.3 ms except the occupancy updates; expandable segments, used earlier in the round, map GB-sized growth in
-# 2 MB granules and cost one 27-280 ms step whenever a capacity had to grow.)
+# power-of-two rounding keeps the few remaining torch-side temporaries in one class.
 os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "roundup_power2_divisions:8")
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -45,13 +55,26 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--rays", type=int, default=2 ** 18, help="rays per rank per step")
+    ap.add_argument("--config", default="dynerf", choices=["dynerf", "hypernerf", "dnerf"])
+    ap.add_argument("--rays", type=int, default=2 ** 18, help="rays per rank per step (train configurations)")
     ap.add_argument("--cpu-rays", type=int, default=4096, help="rays per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=3, help="instrumented steps for the per-kernel breakdown")
-    ap.add_argument("--render-frames", type=int, default=2, help="full frames per rank for the render leg (0 = skip)")
+    ap.add_argument("--render-frames", type=int, default=300,
+                    help="frames of the video leg in total (subsampled from the 300-pose spiral; 0 = skip)")
+    ap.add_argument("--headline-only", action="store_true", help="skip the other configurations")
+    ap.add_argument("--dp", default="peer", choices=["peer", "nccl"], help="multi-GPU optimiser step")
     ap.add_argument("--torch-profile", default="", help="write a torch.profiler kernel table of one step to this file")
     return ap.parse_args()
+
+
+def load_workload():
+    """cednerf_b200/workload.py by path: it needs torch only, and the reference arm must not load the product."""
+    spec = importlib.util.spec_from_file_location("cednerf_workload", os.path.join(ROOT, "cednerf_b200", "workload.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["cednerf_workload"] = mod
+    spec.loader.exec_module(mod)
+    return mod
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -106,25 +129,26 @@ class TrainState:
 
 class OccupancyUpdate:
     """estimator.update_every_n_steps(step, occ_eval_fn, occ_thre) of the reference loop (train_real.py:324-336): every
-    16th iteration the field is queried at one jittered point per grid cell (all 4 x 128^3 cells during the first 256
+    16th iteration the field is queried at one jittered point per grid cell (all L x 128^3 cells during the first 256
     iterations) with random timestamps.  It runs on a TWIN of the estimator: the synthetic occupancy is what defines the
-    workload (a random field would otherwise mark everything occupied), so the marcher keeps reading the original."""
+    workload (a random field would otherwise mark everything occupied), so the marcher keeps reading the original.
+    All draws come from dp.SharedRng, seeded alike on every rank: the replicas stay identical without a collective."""
 
-    def __init__(self, impl, cfg, est, field, step_size):
+    def __init__(self, impl, cfg, est, field, step_size, rng):
         self.twin = impl.OccGridEstimator(list(cfg.roi_aabb), resolution=cfg.occ_res, levels=cfg.occ_levels)
         self.twin = self.twin.to(est.aabbs.device)
         self.twin.binaries, self.twin.occs = est.binaries.clone(), est.occs.clone()
         self.twin.train()
-        self.field, self.step_size, self.step, self.updates = field, step_size, 0, 0
+        self.field, self.step_size, self.step, self.updates, self.rng = field, step_size, 0, 0, rng
 
     def occ_eval_fn(self, x):
-        t = torch.rand(x.shape[0], 1, device=x.device)
+        t = self.rng.rand(x.shape[0], 1)
         return self.field.query_density(x, t)["density"] * self.step_size
 
     def __call__(self):
         if self.step % 16 == 0:
             self.updates += 1
-        self.twin.update_every_n_steps(step=self.step, occ_eval_fn=self.occ_eval_fn, occ_thre=1e-2)
+        self.twin.update_every_n_steps(step=self.step, occ_eval_fn=self.occ_eval_fn, occ_thre=1e-2, rng=self.rng)
         self.step += 1
 
 
@@ -148,7 +172,7 @@ def train_step(impl, field, est, opt, scaler, batch, cfg, rk, reducer=None, sche
             reducer.wait()
         scaler.step(opt)
         scaler.update()
-    else:
+    else:  # CPU arm: the GradScaler(2^10) protocol spelled out (scale, unscale, step)
         (loss * 1024.0).backward()
         for p in field.parameters():
             if p.grad is not None:
@@ -174,8 +198,7 @@ class ClockSampler:
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
         except Exception:  # noqa: BLE001 - NVML missing: report it, do not fail the benchmark
             return
-        names = {"hw_slowdown": pynvml.nvmlClocksEventReasonHwSlowdown if hasattr(pynvml, "nvmlClocksEventReasonHwSlowdown") else 0x8,
-                 "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
         self.run = True
 
         def loop():
@@ -219,6 +242,12 @@ def algorithmic_bytes(name, args):
     if name == "cednerf_field_fwd":
         n, L = args[9], args[14]._obj.levels.n_levels
         return n * (L * 8 * 4 + 16 + 4 + (12 if args[16] else 0))  # 512 B table + packed sample 16 B + sigma (+ rgb)
+    if name == "cednerf_field_train_fwd":                       # 512 B table + 16 B sample + sigma / rgb / selector / move
+        n, L = args[7], args[13]._obj.levels.n_levels
+        return n * (L * 8 * 4 + 16 + 4 + 12 + 1 + 12)
+    if name == "cednerf_field_train_bwd":                       # 1024 B table-gradient RMW + 512 B table re-read + d_sigma / d_rgb
+        n, L = args[7], args[13]._obj.levels.n_levels
+        return n * (L * 8 * 8 + L * 8 * 4 + 16 + 16)
     if name == "cednerf_mlp_fwd":
         d, n = args[2]._obj, args[3]
         hid = (d.n_layers - 1) * 128 if args[5] else 0
@@ -229,7 +258,9 @@ def algorithmic_bytes(name, args):
                     (d.dim_in[0] * (4 if args[7] else 2) if args[6] else 0))
     if name == "cednerf_march":
         n = args[3]
-        return n * 52                                           # 32 B/ray in + 20 B/ray out; per-sample writes added below
+        return n * 52                                           # 32 B/ray in + 20 B/ray out (per-sample writes: the fill)
+    if name == "cednerf_march_fill_runs":
+        return None
     if name == "cednerf_composite_fwd":
         return args[8] * 44 + args[9] * 20
     if name == "cednerf_composite_bwd":
@@ -237,50 +268,138 @@ def algorithmic_bytes(name, args):
     if name == "cednerf_adam_step":                             # 16 B read + 12 B written (+ 2 B fp16 copy) per parameter
         t = args[0]._obj
         return sum(t.n[k] * (30 if t.p16[k] else 28) for k in range(t.n_tensors))
+    if name == "cednerf_dp_adam":                               # N gradient reads + 12 B state in + 8 B state out + 6 N B replicas
+        a = args[0]._obj
+        return (a.hi - a.lo) * (4 * a.world + 20 + 6 * a.n_out)
     if name == "cednerf_nonfinite_check":
         t = args[0]._obj
         return sum(t.n[k] * 4 for k in range(t.n_tensors))
     return None
 
 
-def run_ours(args):
-    import torch.distributed as dist
+class Instrument:
+    """CUDA events around every entry point of the library (same stream), for per-kernel shares and rooflines."""
 
-    import cednerf_b200 as cb
-    from cednerf_b200 import _lib, dp, workload
+    def __init__(self, cb, _lib):
+        self.mods = (_lib, cb.ops, cb.optim, cb.losses)
+        self.real, self.rec = _lib.call, []
 
-    rank = int(os.environ.get("RANK", 0))
-    local_rank = int(os.environ.get("LOCAL_RANK", 0))
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py (impl=ours) needs a CUDA device: the product has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    cfg = workload.DYNERF
+    def __enter__(self):
+        def recording_call(name, *a):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            self.real(name, *a)
+            e.record()
+            self.rec.append((name, a, s, e))
+
+        for m in self.mods:
+            m.call = recording_call
+        return self
+
+    def __exit__(self, *exc):
+        for m in self.mods:
+            m.call = self.real
+
+    def aggregate(self):
+        agg = {}
+        for name, a, s, e in self.rec:
+            by = algorithmic_bytes(name, a)
+            d = agg.setdefault(name, {"ms": 0.0, "launches": 0, "bytes": 0, "has_bytes": by is not None})
+            d["ms"] += s.elapsed_time(e)
+            d["launches"] += 1
+            d["bytes"] += by or 0
+        return agg
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured"
+    except (OSError, ValueError, KeyError):
+        return 6650.0, "fallback"
+
+
+def roofline_of(agg, n_iter, total_ms):
+    """Dominant kernel (by time, among those with algorithmic bytes) against the HBM copy peak; plus the whole step."""
+    hbm_peak, src = peaks()
+    top = max((n for n in agg if agg[n]["has_bytes"]), key=lambda n: agg[n]["ms"])
+    d = agg[top]
+    achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+    traffic = None  # dram__bytes_read + dram__bytes_write per launch of that kernel, from the committed ncu capture
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get(top, {}).get("bytes_per_launch")
+    except (OSError, ValueError):
+        pass
+    step_bytes = sum(v["bytes"] for v in agg.values()) / n_iter
+    return {"kernel": top, "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
+            "frac": round(achieved / hbm_peak, 4), "traffic": traffic, "peak_source": src,
+            "avg_launch_ms": round(d["ms"] / d["launches"], 4), "bytes_per_launch": d["bytes"] // d["launches"],
+            "share_of_step": round(d["ms"] / n_iter / total_ms, 3),
+            "step_bytes": int(step_bytes), "step_frac": round(step_bytes / (total_ms * 1e-3) / 1e9 / hbm_peak, 4)}
+
+
+class Dist:
+    def __init__(self):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.rank = int(os.environ.get("RANK", 0))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", 0))
+        self.world = int(os.environ.get("WORLD_SIZE", 1))
+        if not torch.cuda.is_available():
+            raise RuntimeError("bench.py (impl=ours) needs a CUDA device: the product has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+
+# --------------------------------------------------------------------------------------------------------------
+# train-step leg
+# --------------------------------------------------------------------------------------------------------------
+def train_leg(D, cb, workload, cfg, args, n_rays, steps, warmup, full: bool):
+    """-> dict.  `full`: also the end-to-end (host batches) leg, the per-kernel breakdown and the clock samples."""
+    from cednerf_b200 import _lib, dp
+
+    dev, world, rank = D.dev, D.world, D.rank
     rk = workload.render_kwargs(cfg)
     est, field = workload.build_scene(cfg, dev, cb, seed=42)
     est.train(), field.train()
-    opt = cb.optim.FusedAdam(field.parameters(), lr=1e-2, eps=1e-15)  # apex.optimizers.FusedAdam, train_real.py:267-270
     scaler = cb.optim.GradScaler(2 ** 10)                              # torch.cuda.amp.GradScaler(2**10), train_real.py:252
-    reducer = dp.GradAllReducer(field.parameters(), world) if world > 1 else None
+    reducer, dp_mode = None, "single"
+    if world > 1 and args.dp == "peer":
+        opt = dp.DistributedFusedAdam(field.parameters(), lr=1e-2, eps=1e-15)
+        ok = torch.ones(1, device=dev)
+        try:
+            opt.setup()
+        except Exception as e:  # noqa: BLE001 - no peer access / IPC on this box: fall back, and say so
+            print(f"[bench] rank {rank}: peer-memory setup failed ({e}); using the NCCL all-reduce path", file=sys.stderr)
+            ok.zero_()
+        D.dist.all_reduce(ok, op=D.dist.ReduceOp.MIN)
+        dp_mode = "peer" if float(ok.item()) == 1.0 else "nccl"
+    if world > 1 and dp_mode != "peer":
+        dp_mode = "nccl"
+        opt = cb.optim.FusedAdam(field.parameters(), lr=1e-2, eps=1e-15)
+        reducer = dp.GradAllReducer(field.parameters(), world)
+    if world == 1:
+        opt = cb.optim.FusedAdam(field.parameters(), lr=1e-2, eps=1e-15)  # apex.optimizers.FusedAdam, train_real.py:267-270
     state = TrainState(field, opt)
-    occ = OccupancyUpdate(cb, cfg, est, field, rk["render_step_size"])
+    occ = OccupancyUpdate(cb, cfg, est, field, rk["render_step_size"], dp.SharedRng(4242, dev))
 
     gen = torch.Generator().manual_seed(1000 + rank)  # every rank draws its own slice of the global batch
     n_host = 4
-    host = [workload.draw_batch(cfg, args.rays, gen, pin=True) for _ in range(n_host)]
+    host = [workload.draw_batch(cfg, n_rays, gen, pin=True) for _ in range(n_host)]
     resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
-    # allocator warm-up batches: the visible-sample count moves by a few % from step to step and the configuration sits
-    # right at 2^20 samples, a size-class boundary of the caching allocator.  Untimed forward+backward passes (no
-    # optimiser step: parameters and optimiser state stay untouched) on 1.06 x and 1.12 x the rays, run after the warm-up
-    # steps, leave free blocks of the next size classes in the cache, so the timed step in which the count crosses the
-    # boundary does not have to grow the pool (one such step took 58-110 ms).  A training run reaches the same state
-    # after its first few hundred iterations.
-    # (the count grows by ~0.25 % per step at this learning rate: cover the whole run in 6 % increments)
-    n_classes = max(2, int((0.003 * (args.steps + max(args.warmup, 3)) + 0.06) / 0.06) + 1)
-    oversized = [{k: v.to(dev) for k, v in workload.draw_batch(cfg, int(args.rays * (1.0 + 0.06 * (j + 1))), gen).items()}
+    # allocator warm-up batches: the visible-sample count moves by a few % from step to step.  Untimed forward+backward
+    # passes (no optimiser step) on 1.06 x, 1.12 x ... the rays, run after the warm-up steps, leave free blocks of the
+    # next size classes in the cache, so the timed step in which the count crosses a boundary does not grow the pool.
+    n_classes = max(2, int((0.003 * (steps + max(warmup, 3)) + 0.06) / 0.06) + 1)
+    oversized = [{k: v.to(dev) for k, v in workload.draw_batch(cfg, int(n_rays * (1.0 + 0.06 * (j + 1))), gen).items()}
                  for j in range(min(n_classes, 12))]
 
     def touch_size_classes():
@@ -303,18 +422,13 @@ def run_ours(args):
         loss, n_s = train_step(cb, field, est, opt, scaler, b, cfg, rk, reducer, state.sched, occ)
         return (None if loss is None else float(loss.item())), n_s  # device -> host read of the step's result
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     def timed(fn, k):
         state.restore()          # iteration 0 again (untimed), then the warm-up steps allocate the optimiser state
         occ.step = 0
-        for i in range(max(args.warmup, 3)):
+        for i in range(max(warmup, 3)):
             fn(i)
         touch_size_classes()
-        barrier()
+        D.barrier()
         occ.updates = 0
         l0 = _lib.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -331,79 +445,38 @@ def run_ours(args):
                 continue
             n_tot += fn(i)[1]
         e1.record()
-        barrier()
+        D.barrier()
         ms = dp.max_over_ranks(e0.elapsed_time(e1) / k, dev)
         return ms, n_tot / k, (_lib.launch_count() - l0) // k
 
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
+    clocks = ClockSampler(D.local_rank) if (full and rank == 0) else None
+    if clocks:
         clocks.start()
-    ms, samples, launches = timed(step_resident, args.steps)
-    occ_updates = occ.updates
-    clk = clocks.stop() if rank == 0 else None
-    ms_e2e, _, _ = timed(step_e2e, args.steps)
-    samples_all = dp.sum_over_ranks(samples, dev)
-
-    # ---- per-entry-point breakdown and the roofline of the dominant kernel (CUDA events, same stream) -----------
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except (OSError, ValueError):
-        pass
-    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
-    roof, breakdown = None, {}
-    if args.profile_steps > 0:
-        # every rank runs the instrumented steps (they contain the gradient all-reduce); rank 0 keeps the records
-        rec = []
-        real_call = _lib.call
-
-        def recording_call(name, *a):
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            real_call(name, *a)
-            e.record()
-            rec.append((name, a, s, e))
-
+    ms, samples, launches = timed(step_resident, steps)
+    out = {"ms": ms, "samples": dp.sum_over_ranks(samples, dev), "launches": int(launches), "occ_updates": occ.updates,
+           "dp_mode": dp_mode, "rays": n_rays * world, "clocks": clocks.stop() if clocks else None,
+           "h2d": sum(v.numel() * v.element_size() for v in host[0].values())}
+    if full:
+        out["ms_e2e"] = timed(step_e2e, steps)[0]
+    if args.profile_steps > 0 and full:
+        # every rank runs the instrumented steps (they contain the cross-rank barriers); rank 0 keeps the records
         state.restore()
         step_resident(0)
-        for m in (_lib, cb.ops, cb.optim, cb.losses):
-            m.call = recording_call
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(args.profile_steps):
-            step_resident(i)
-        torch.cuda.synchronize()
-        prof_ms = (time.perf_counter() - t0) * 1e3 / args.profile_steps
-        for m in (_lib, cb.ops, cb.optim, cb.losses):
-            m.call = real_call
-    if rank == 0 and args.profile_steps > 0:
-        agg = {}
-        for name, a, s, e in rec:
-            t = s.elapsed_time(e)
-            by = algorithmic_bytes(name, a)
-            d = agg.setdefault(name, {"ms": 0.0, "launches": 0, "bytes": 0, "has_bytes": by is not None})
-            d["ms"] += t
-            d["launches"] += 1
-            d["bytes"] += by or 0
-        for name, d in agg.items():
-            breakdown[name] = {"ms_per_step": round(d["ms"] / args.profile_steps, 4),
-                               "launches_per_step": d["launches"] // args.profile_steps}
-        top = max((n for n in agg if agg[n]["has_bytes"]), key=lambda n: agg[n]["ms"])
-        d = agg[top]
-        achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9
-        traffic = None  # dram__bytes_read + dram__bytes_write per launch of that kernel, from the committed ncu capture
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get(top, {}).get("bytes_per_launch")
-        except (OSError, ValueError):
-            pass
-        roof = {"kernel": top, "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
-                "frac": round(achieved / hbm_peak, 4), "traffic": traffic, "peak_source": peak_src,
-                "avg_launch_ms": round(d["ms"] / d["launches"], 4), "bytes_per_launch": d["bytes"] // d["launches"],
-                "share_of_step": round(d["ms"] / args.profile_steps / prof_ms, 3)}
-        breakdown["_ours_total_ms"] = round(sum(v["ms"] for v in agg.values()) / args.profile_steps, 3)
-        breakdown["_instrumented_step_ms"] = round(prof_ms, 3)
-
-    if args.torch_profile:
+        with Instrument(cb, _lib) as ins:
+            D.barrier()
+            t0 = time.perf_counter()
+            for i in range(args.profile_steps):
+                step_resident(i)
+            torch.cuda.synchronize()
+            prof_ms = (time.perf_counter() - t0) * 1e3 / args.profile_steps
+        if rank == 0:
+            agg = ins.aggregate()
+            out["breakdown"] = {n: {"ms_per_step": round(d["ms"] / args.profile_steps, 4),
+                                    "launches_per_step": d["launches"] // args.profile_steps} for n, d in agg.items()}
+            out["breakdown"]["_ours_total_ms"] = round(sum(v["ms"] for v in agg.values()) / args.profile_steps, 3)
+            out["breakdown"]["_instrumented_step_ms"] = round(prof_ms, 3)
+            out["roofline"] = roofline_of(agg, args.profile_steps, prof_ms)
+    if args.torch_profile and full:
         from torch.profiler import ProfilerActivity, profile
 
         with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
@@ -412,91 +485,155 @@ def run_ours(args):
         if rank == 0:
             with open(args.torch_profile, "w") as f:
                 f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=70))
+    if dp_mode == "peer":
+        out["dp_timed_out"] = bool(opt.timed_out())
+        opt.close()
+    if reducer is not None:
+        reducer.remove()
+    return out
 
-    # ---- render leg (BASELINE.json configs[3]): full 1352 x 1014 frames through render_image_test, frames sharded over
-    # ranks with no collective; reported beside the train-step headline --------------------------------------------------
-    render = None
-    if args.render_frames > 0:
-        field.eval(), est.eval()
-        o, d = workload.frame_rays(cfg, 0)
-        frame = cb.Rays(o.to(dev).view(cfg.height, cfg.width, 3), d.to(dev).view(cfg.height, cfg.width, 3))
-        black = torch.zeros(3, device=dev)
-        frames = dp.shard_interleaved(args.render_frames * world, rank, world)   # weak scaling: render_frames per rank
 
-        def render_one(i):
-            t = torch.tensor([[frames[i % len(frames)] / 300.0]], device=dev)     # t = i / 300 (dnerf_3d_video_IS.py:366)
-            return cb.render_image_test(1024, field, est, frame, render_bkgd=black, timestamps=t, **rk)[3]
+# --------------------------------------------------------------------------------------------------------------
+# render leg: full frames through render_image_test, frames interleaved over the ranks, no collective
+# --------------------------------------------------------------------------------------------------------------
+def render_leg(D, cb, workload, cfg, args, poses, times, opengl, bkgd, profile: bool):
+    """poses [F,3,4], times [F]: the whole job; rank r renders frames r, r+W, ... (strong scaling)."""
+    from cednerf_b200 import _lib, dp
 
-        render_one(0)
-        barrier()
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        r0.record()
-        n_render = sum(render_one(i) for i in range(len(frames)))
-        r1.record()
-        barrier()
-        ms_r = dp.max_over_ranks(r0.elapsed_time(r1), dev)
-        n_render_all = dp.sum_over_ranks(n_render, dev)
-        rays_r = cfg.width * cfg.height * len(frames) * world
-        render = {"workload": f"{cfg.width}x{cfg.height} frames, render_image_test(max_samples=1024), "
-                              f"{len(frames)} frame(s)/GPU, frame-sharded, no collective",
-                  "rays_per_s": round(rays_r / (ms_r * 1e-3), 1), "samples_per_s": round(n_render_all / (ms_r * 1e-3), 1),
-                  "ms_per_frame": round(ms_r / len(frames), 3), "samples_per_ray": round(n_render_all / rays_r, 3)}
-        if rank == 0 and args.profile_steps > 0:   # per-entry-point share of one frame
-            rec_r = []
-            real_call = _lib.call
+    dev, world, rank = D.dev, D.world, D.rank
+    rk = workload.render_kwargs(cfg)
+    est, field = workload.build_scene(cfg, dev, cb, seed=42)
+    est.eval(), field.eval()
+    mine = dp.shard_interleaved(len(poses), rank, world)
+    bk = torch.tensor(bkgd, dtype=torch.float32, device=dev)
+    frames = [(poses[i].to(dev), torch.tensor([[float(times[i])]], device=dev)) for i in mine]
 
-            def rec_call(name, *a2):
-                s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s_.record()
-                real_call(name, *a2)
-                e_.record()
-                rec_r.append((name, s_, e_))
+    def render_one(k):
+        c2w, t = frames[k]   # pixel -> ray generation on the device, inside the timed region (gui.py:43-86 does it per frame)
+        o, d = workload.pose_rays(cfg, c2w, opengl)
+        rays = cb.Rays(o.view(cfg.height, cfg.width, 3), d.view(cfg.height, cfg.width, 3))
+        return cb.render_image_test(1024, field, est, rays, render_bkgd=bk, timestamps=t, **rk)[3]
 
-            for m in (_lib, cb.ops, cb.optim, cb.losses):
-                m.call = rec_call
+    for k in range(min(2, len(frames))):
+        render_one(k)
+    D.barrier()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = _lib.launch_count()
+    r0.record()
+    n_samples = sum(render_one(k) for k in range(len(frames)))
+    r1.record()
+    D.barrier()
+    ms = dp.max_over_ranks(r0.elapsed_time(r1), dev)
+    n_all = dp.sum_over_ranks(n_samples, dev)
+    rays = cfg.width * cfg.height * len(poses)
+    hbm_peak, _ = peaks()
+    out = {"workload": f"{cfg.name}: {len(poses)} {cfg.width}x{cfg.height} frames, render_image_test(1024), "
+                       f"frames interleaved over {world} GPU(s), no collective",
+           "frames": len(poses), "scaling": "strong", "rays_per_s": round(rays / (ms * 1e-3), 1),
+           "samples_per_s": round(n_all / (ms * 1e-3), 1), "ms_per_frame_per_gpu": round(ms / max(len(mine), 1), 3),
+           "samples_per_ray": round(n_all / rays, 3), "launches_per_frame": (_lib.launch_count() - l0) // max(len(mine), 1),
+           # fused render per sample: 512 B table + ~50 B (SURVEY.md 8d) against the HBM copy peak, whole job
+           "pipeline_frac": round(n_all * 562 / (ms * 1e-3) / 1e9 / (hbm_peak * world), 4)}
+    if profile and rank == 0 and frames:
+        with Instrument(cb, _lib) as ins:
             render_one(0)
             torch.cuda.synchronize()
-            for m in (_lib, cb.ops, cb.optim, cb.losses):
-                m.call = real_call
-            agg_r = {}
-            for name, s_, e_ in rec_r:
-                d_ = agg_r.setdefault(name, [0.0, 0])
-                d_[0] += s_.elapsed_time(e_)
-                d_[1] += 1
-            render["breakdown_ms_per_frame"] = {k: [round(v[0], 3), v[1]] for k, v in
-                                                sorted(agg_r.items(), key=lambda kv: -kv[1][0])}
-        field.train(), est.train()
+        agg = ins.aggregate()
+        out["breakdown_ms_per_frame"] = {k: [round(v["ms"], 3), v["launches"]] for k, v in
+                                         sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
+    return out
+
+
+def run_ours(args):
+    import cednerf_b200 as cb
+    from cednerf_b200 import workload
+
+    D = Dist()
+    rank, world = D.rank, D.world
+    cfgs = {"dynerf": workload.DYNERF, "hypernerf": workload.HYPERNERF, "dnerf": workload.DNERF}
+    cfg = cfgs[args.config]
+
+    def video_leg(profile):
+        n = max(1, args.render_frames)
+        idx = [k * 300 // n for k in range(n)] if n < 300 else list(range(300))
+        poses = workload.spiral_poses(workload.DYNERF, 300)
+        return render_leg(D, cb, workload, workload.DYNERF, args, poses[idx], [k / 300.0 for k in idx], False,
+                          (0.0, 0.0, 0.0), profile)
+
+    def dnerf_leg(n_frames, profile):
+        poses = torch.stack([workload.orbit_pose(4.0, 2 * 3.14159265 * k / n_frames) for k in range(n_frames)])
+        return render_leg(D, cb, workload, workload.DNERF, args, poses, [0.5] * n_frames, True, (1.0, 1.0, 1.0), profile)
+
+    line = {"higher_is_better": True, "vs_baseline": None, "data": "synthetic", "n_gpus": world,
+            "dtype": "f16 (MLP, tables) / f32 (marching, compositing, grads)"}
+    extra = {}
+    if args.config == "dnerf":   # configs[0]: one "step" = one 800x800 frame
+        n_frames = max(args.steps, 1) * world
+        for _ in range(1):
+            r = dnerf_leg(n_frames, args.profile_steps > 0)
+        line.update({"metric": "render_rays_per_s", "value": r["rays_per_s"], "unit": "rays/s", "steps": args.steps,
+                     "warmup": 2, "ms_per_step": r["ms_per_frame_per_gpu"], "scaling": "weak",
+                     "config": {"workload": r["workload"], "samples_per_ray": r["samples_per_ray"],
+                                "samples_per_s": r["samples_per_s"], "l2": "inputs (800x800 rays x frames) and the 96 MB table exceed L2"},
+                     "e2e": {"value": r["rays_per_s"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8,
+                             "note": "render_image_test reads one count per marching round back to the host"},
+                     "gpu_launches": r["launches_per_frame"], "clocks": None,
+                     "roofline": {"bound": "hbm", "frac": r["pipeline_frac"], "kernel": "render pipeline"}})
+        extra["render_breakdown"] = r.get("breakdown_ms_per_frame")
+    else:
+        t = train_leg(D, cb, workload, cfg, args, args.rays, args.steps, args.warmup, True)
+        rays_all = t["rays"]
+        line.update({
+            "metric": "train_step_rays_per_s", "value": round(rays_all / (t["ms"] * 1e-3), 1), "unit": "rays/s",
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(t["ms"], 4), "scaling": "weak",
+            "config": {"workload": f"{cfg.name} train step, {args.rays} rays/GPU/step, occgrid sampler "
+                                   f"(BASELINE.json configs[{1 if args.config == 'dynerf' else 2}])",
+                       "flags": "-te -ta -df -f -wr -ae; GradScaler 2^10 + fused Adam",
+                       "rays_per_gpu": args.rays, "samples_per_step": round(t["samples"], 1),
+                       "samples_per_ray": round(t["samples"] / rays_all, 3),
+                       "samples_per_s": round(t["samples"] / (t["ms"] * 1e-3), 1),
+                       "l2": "working set (96 MB fp16 table, 191 MB fp32 master, 383 MB Adam state) exceeds the 126 MB L2; 4 rotating batches",
+                       "occ_update": f"every step on a twin estimator; {t['occ_updates']} full update(s) in the timed steps",
+                       "parallelism": ("single" if world == 1 else
+                                       f"dp{world}, optimiser step: " + ("fused reduce-scatter+Adam+all-gather over NVLink peer memory"
+                                                                        if t["dp_mode"] == "peer" else "NCCL all-reduce + Adam"))},
+            "e2e": {"value": round(rays_all / (t["ms_e2e"] * 1e-3), 1), "unit": "rays/s", "ms_per_step": round(t["ms_e2e"], 4),
+                    "h2d_bytes_per_step": t["h2d"], "d2h_bytes_per_step": 4},
+            "gpu_launches": t["launches"], "clocks": t["clocks"], "roofline": t.get("roofline")})
+        if t.get("dp_timed_out"):
+            line["config"]["parallelism"] += " (A BARRIER TIMED OUT)"
+        extra["breakdown"] = t.get("breakdown")
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = run_reference_steps(args.cpu_rays, steps=3, warmup=1)
-
+        cpu = run_reference_steps(args.config, args.cpu_rays, steps=3, warmup=1)
+    line["cpu_baseline"] = cpu
+    line.update(extra)   # the long per-kernel tables go before the other configurations: the END of the line is what a
+                         # truncated log keeps
+    if not args.headline_only and args.config == "dynerf":
+        others = {}
+        if args.render_frames > 0:
+            line["render"] = video_leg(args.profile_steps > 0)
+            line["config"]["render"] = {k: line["render"][k] for k in ("frames", "rays_per_s", "samples_per_s",
+                                                                       "ms_per_frame_per_gpu", "pipeline_frac")}
+        r = dnerf_leg(8 * world, False)
+        others["dnerf"] = {k: r[k] for k in ("frames", "rays_per_s", "samples_per_s", "ms_per_frame_per_gpu",
+                                             "samples_per_ray", "pipeline_frac")}
+        h = train_leg(D, cb, workload, workload.HYPERNERF, args, args.rays, 10, 3, False)
+        others["hypernerf"] = {"rays_per_s": round(h["rays"] / (h["ms"] * 1e-3), 1), "ms_per_step": round(h["ms"], 4),
+                               "samples_per_s": round(h["samples"] / (h["ms"] * 1e-3), 1),
+                               "samples_per_ray": round(h["samples"] / h["rays"], 3), "rays_per_gpu": args.rays}
+        if world > 1:   # configs[4]: 2^20 rays per step split over the ranks
+            s = train_leg(D, cb, workload, workload.DYNERF, args, 2 ** 20 // world, 10, 3, False)
+            others["dynerf_2p20"] = {"rays_per_s": round(s["rays"] / (s["ms"] * 1e-3), 1), "ms_per_step": round(s["ms"], 4),
+                                     "rays_per_gpu": 2 ** 20 // world, "samples_per_s": round(s["samples"] / (s["ms"] * 1e-3), 1),
+                                     "dp": s["dp_mode"]}
+        line["configs"] = others
+        line["config"]["others"] = others
     if rank == 0:
-        rays_all = args.rays * world
-        h2d = sum(v.numel() * v.element_size() for v in host[0].values())
-        line = {
-            "metric": "train_step_rays_per_s", "value": round(rays_all / (ms * 1e-3), 1), "unit": "rays/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f16 (MLP, tables) / f32 (marching, compositing, grads)",
-            "data": "synthetic",
-            "config": {"workload": f"{cfg.name} train step, {args.rays} rays/GPU/step, occgrid sampler "
-                                   f"(BASELINE.json configs[1]); flags -te -ta -df -f -wr -ae; GradScaler 2^10 + fused Adam (cednerf_b200.optim)",
-                       "rays_per_gpu": args.rays, "samples_per_step": round(samples_all, 1),
-                       "samples_per_ray": round(samples_all / rays_all, 3),
-                       "samples_per_s": round(samples_all / (ms * 1e-3), 1),
-                       "l2": "working set (96 MB fp16 table + 191 MB fp32 master + 383 MB Adam state + per-step "
-                             "buffers) far exceeds the 126 MB L2; 4 rotating input batches",
-                       "occ_update": f"update_every_n_steps(n=16, warm-up: all 4 x 128^3 cells) called every step on a twin "
-                                     f"estimator; {occ_updates} update(s) fell into the {args.steps} timed steps",
-                       "parallelism": f"dp{world}" if world > 1 else "single"},
-            "e2e": {"value": round(rays_all / (ms_e2e * 1e-3), 1), "unit": "rays/s", "ms_per_step": round(ms_e2e, 4),
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "render": render,
-            "breakdown": breakdown,
-        }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        D.dist.destroy_process_group()
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -509,19 +646,42 @@ class _OracleImpl:
         from oracle import nerfacc_ref as nf
 
         self.OccGridEstimator, self.DNGPradianceField = nf.OccGridEstimator, cr.DNGPradianceField
-        self.Rays, self.render_image = cr.Rays, cr.render_image
+        self.Rays, self.render_image, self.render_image_test = cr.Rays, cr.render_image, cr.render_image_test
 
 
-def run_reference_steps(n_rays, steps, warmup):
-    from cednerf_b200 import workload
-
+def run_reference_steps(config, n_rays, steps, warmup):
+    """The headline configuration on the CPU restatement: same initial weights (workload.initial_state + density boost),
+    same learning rate (iteration 0 of the reference schedule), same loss scaling, a bounded sample of the rays."""
+    workload = load_workload()
     torch.set_num_threads(os.cpu_count() or 1)
     impl = _OracleImpl()
-    cfg = workload.DYNERF
+    cfg = {"dynerf": workload.DYNERF, "hypernerf": workload.HYPERNERF, "dnerf": workload.DNERF}[config]
     rk = workload.render_kwargs(cfg)
     est, field = workload.build_scene(cfg, "cpu", impl, seed=42)
+    if config == "dnerf":   # a square crop of the 800x800 frame holding ~n_rays pixels
+        est.eval(), field.eval()
+        side = max(8, int(n_rays ** 0.5))
+        o, d = workload.pose_rays(cfg, workload.orbit_pose(4.0, 0.0), True)
+        lo = (cfg.height - side) // 2
+        sel = (torch.arange(lo, lo + side)[:, None] * cfg.width + torch.arange(lo, lo + side)[None, :]).reshape(-1)
+        rays = impl.Rays(o[sel], d[sel])
+        times, samples = [], 0
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                n_s = impl.render_image_test(1024, field, est, rays, render_bkgd=torch.ones(3),
+                                             timestamps=torch.tensor([[0.5]]), **rk)[3]
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+                samples += n_s
+        sec = sum(times) / len(times)
+        return {"value": round(side * side / sec, 1), "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+                "sample": f"centre {side}x{side} crop of one 800x800 frame, {steps} timed renders "
+                          f"({round(samples / steps / side / side, 2)} samples/ray), oracle/ PyTorch-CPU + OpenMP C marcher",
+                "ms_per_step": round(sec * 1e3, 1), "samples_per_s": round(samples / steps / sec, 1)}
     est.train(), field.train()
     opt = torch.optim.Adam(field.parameters(), lr=1e-2, eps=1e-15)
+    make_scheduler(opt)   # lr -> 1e-4, as the GPU arm's TrainState
     gen = torch.Generator().manual_seed(1000)
     batches = [workload.draw_batch(cfg, n_rays, gen) for _ in range(2)]
     times, samples = [], 0
@@ -534,25 +694,26 @@ def run_reference_steps(n_rays, steps, warmup):
             samples += n_s
     sec = sum(times) / len(times)
     return {"value": round(n_rays / sec, 1), "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{n_rays} rays/step of the same workload, {steps} timed steps after {warmup} warm-up "
-                      f"({round(samples / steps / n_rays, 2)} samples/ray), oracle/ PyTorch-CPU + OpenMP C marcher",
-            "ms_per_step": round(sec * 1e3, 1), "samples_per_s": round(samples / steps / sec, 1)}
+            "sample": f"{n_rays} rays/step of the same workload and initial weights, {steps} timed steps after {warmup} "
+                      f"warm-up ({round(samples / steps / n_rays, 2)} samples/ray; no occupancy update), oracle/ "
+                      f"PyTorch-CPU + OpenMP C marcher",
+            "ms_per_step": round(sec * 1e3, 1), "samples_per_s": round(samples / steps / sec, 1),
+            "samples_per_ray": round(samples / steps / n_rays, 3)}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    from cednerf_b200 import workload
-
-    cfg = workload.DYNERF
-    cpu = run_reference_steps(args.cpu_rays, steps=max(1, min(args.steps, 3)), warmup=1)
-    line = {"impl": "reference", "metric": "train_step_rays_per_s", "value": cpu["value"], "unit": "rays/s",
-            "n_gpus": args.gpus, "steps": max(1, min(args.steps, 3)), "warmup": 1, "ms_per_step": cpu["ms_per_step"],
+    steps = max(1, min(args.steps, 3))
+    cpu = run_reference_steps(args.config, args.cpu_rays, steps=steps, warmup=1)
+    train = args.config != "dnerf"
+    line = {"impl": "reference", "metric": "train_step_rays_per_s" if train else "render_rays_per_s", "value": cpu["value"],
+            "unit": "rays/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": cpu["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (CPU), fp16-rounded MLP",
             "data": "synthetic",
-            "config": {"workload": f"{cfg.name} train step, bounded sample of {args.cpu_rays} rays/step on the host CPU "
-                                   f"(BASELINE.json configs[1]); flags -te -ta -df -f -wr -ae; Adam"},
+            "config": {"workload": f"{args.config}-shaped {'train step' if train else 'frame render'}, bounded sample of "
+                                   f"{args.cpu_rays} rays/step on the host CPU, same initial weights / lr / loss scale as the GPU arm"},
             "cpu_baseline": cpu,
             "e2e": {"value": cpu["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)

@@ -193,3 +193,28 @@ def test_state_dict_has_the_reference_checkpoint_key_set():
     other.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=True)
     assert torch.equal(other.xyz_wrap.params, field.xyz_wrap.params)
     assert other.xyz_wrap.network.params is other.xyz_wrap.params  # the helper borrows the registered Parameter
+
+
+def test_workload_initial_state_is_the_module_initialisation():
+    """bench.py's two arms start from workload.initial_state (pure torch): it must be bit-identical to what
+    DNGPradianceField's own constructors draw, key for key, and the pose generators must give unit directions."""
+    import cednerf_b200 as cb
+    from cednerf_b200 import workload as w
+
+    for cfg in (w.TINY, w.DNERF):
+        est = cb.OccGridEstimator(list(cfg.roi_aabb), resolution=cfg.occ_res, levels=cfg.occ_levels)
+        sd, st = cb.DNGPradianceField(est.aabbs[-1], **w.field_kwargs(cfg)).state_dict(), w.initial_state(cfg)
+        assert set(sd) == set(st)
+        for k in sd:
+            assert torch.equal(sd[k].float(), st[k].float()), (cfg.name, k)
+    poses = w.spiral_poses(w.DYNERF, 300)
+    assert poses.shape == (300, 3, 4) and len({tuple(p[:, 3].tolist()) for p in poses}) == 300  # 300 distinct positions
+    r = poses[:, :, :3]
+    assert torch.allclose(r @ r.transpose(1, 2), torch.eye(3).expand(300, 3, 3), atol=1e-5)       # rotations
+    o, d = w.pose_rays(w.TINY, poses[17])
+    assert o.shape == d.shape == (w.TINY.width * w.TINY.height, 3)
+    assert torch.allclose(d.norm(dim=-1), torch.ones(d.shape[0]), atol=1e-6) and bool((d[:, 2] > 0.5).all())
+    c = w.orbit_pose(4.0, 1.0)
+    o, d = w.pose_rays(w.DNERF, c, True)
+    centre = d[(w.DNERF.height // 2) * w.DNERF.width + w.DNERF.width // 2]
+    assert torch.allclose(centre, -c[:, 3] / 4.0, atol=2e-3)  # the centre pixel looks at the origin
