@@ -183,9 +183,15 @@ class DistributedFusedAdam(_FusedAdam):
     The table parameter is the one carrying an fp16 working copy (`_cednerf_f16`, set by tcnn.Encoding / HashEncoder);
     its storage, its fp16 copy and its gradient are (re)homed in peer-visible memory on the first step."""
 
-    def __init__(self, params, *args, group=None, average: bool = True, timeout_ms: int = 20000, **kwargs):
+    def __init__(self, params, *args, group=None, average: bool = True, timeout_ms: int = 20000,
+                 replicate_master: bool = False, **kwargs):
+        """replicate_master=False (default): only the fp16 working copy - what forward and backward read - is all-gathered
+        every step (2 B per element and peer instead of 6); a rank's fp32 master is then current for its OWNED range only,
+        and `sync_master()` (one-sided, no collective) brings the rest up to date before a checkpoint is written.
+        replicate_master=True stores the fp32 values into every replica each step as well."""
         super().__init__(params, *args, **kwargs)
         self.group, self.average, self.timeout_ms = group, bool(average), int(timeout_ms)
+        self.replicate_master = bool(replicate_master)
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._peer = None
@@ -230,10 +236,13 @@ class DistributedFusedAdam(_FusedAdam):
         self._ctrl_i32 = pm.local("ctrl", torch.int32)
         self._found = torch.zeros(1, dtype=torch.float32, device=dev)
         self._rehome()
-        # owned range: multiples of 4 elements
+        # owned ranges: multiples of 4 elements
         q = (n // 4) // self.world
-        self._lo = 4 * q * self.rank
-        self._hi = n if self.rank == self.world - 1 else 4 * q * (self.rank + 1)
+        self._ranges = [(4 * q * r, n if r == self.world - 1 else 4 * q * (r + 1)) for r in range(self.world)]
+        self._lo, self._hi = self._ranges[self.rank]
+        # the fp16 copy is maintained by this optimiser; a backward pass without a step must not trigger a re-cast from a
+        # master whose non-owned ranges may be one step behind (see ops._F16Cache)
+        self._table._cednerf_f16.version_only = True
         peers = _lib.DpPeers()
         peers.world, peers.rank = self.world, self.rank
         for r in range(self.world):
@@ -353,13 +362,14 @@ class DistributedFusedAdam(_FusedAdam):
             m, v = moments(p, hi - lo)
             a = DpAdam()
             a.world, a.rank = self.world, self.rank
-            for r in range(self.world):
+            for r in range(self.world):  # rank order: the small tensors are summed by every rank, bit-identically
                 a.grad[r] = pm.address(r, grad_name) + 4 * grad_off
             if broadcast:  # entry 0 = the local replica, then the peers
                 order = [self.rank] + [r for r in range(self.world) if r != self.rank]
                 a.n_out = self.world
                 for k, r in enumerate(order):
-                    a.p32_out[k], a.p16_out[k] = pm.address(r, "p32"), pm.address(r, "p16")
+                    a.p32_out[k] = pm.address(r, "p32") if (k == 0 or self.replicate_master) else None
+                    a.p16_out[k] = pm.address(r, "p16")
             else:
                 a.n_out = 1
                 a.p32_out[0], a.p16_out[0] = p.data_ptr(), None
@@ -392,6 +402,22 @@ class DistributedFusedAdam(_FusedAdam):
             dist.all_reduce(full, group=self.group)
             out.append(full)
         return tuple(out)
+
+    @torch.no_grad()
+    def sync_master(self):
+        """One-sided (no collective, safe between steps: a peer cannot enter its next update before this rank reaches the
+        barrier in front of it): pull every peer's OWNED range of the fp32 master into this rank's copy, after which
+        `state_dict()` of the model is complete here.  A no-op with replicate_master=True."""
+        if self._peer is None or self.replicate_master:
+            return
+        for r, (lo, hi) in enumerate(self._ranges):
+            if r == self.rank or hi == lo:
+                continue
+            src = torch.as_tensor(_RawCuda(self._peer.address(r, "p32") + 4 * lo, 4 * (hi - lo), self._peer),
+                                  device=self._table.device).view(torch.float32)
+            self._p32[lo:hi].copy_(src)
+        torch.autograd.graph.increment_version(self._table)
+        self._table._cednerf_f16.adopt(self._table)
 
     def timed_out(self) -> bool:
         """Host read: did a barrier ever give up waiting for a peer?"""

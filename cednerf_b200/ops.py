@@ -260,10 +260,11 @@ class _F16Cache:
 
     def __init__(self):
         self.key, self.val, self.epoch = None, None, -1
+        self.version_only = False  # set by an optimiser that maintains the copy itself and always bumps the version
 
     def get(self, p: torch.Tensor, make):
         key = (p.data_ptr(), p._version, p.numel())
-        if key != self.key or self.epoch != _param_epoch:
+        if key != self.key or (self.epoch != _param_epoch and not self.version_only):
             self.val, self.key, self.epoch = make(p), key, _param_epoch
         return self.val
 

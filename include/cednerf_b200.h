@@ -278,7 +278,7 @@ typedef struct CednerfDpAdam {
   int world, rank;
   const float* grad[CEDNERF_DP_MAX_RANKS];    /* every rank's gradient buffer (same layout), as mapped here */
   int n_out;                                  /* replicas to update: world (broadcast) or 1 (local only) */
-  float* p32_out[CEDNERF_DP_MAX_RANKS];       /* fp32 parameter replicas; entry 0 is the local one (also the input) */
+  float* p32_out[CEDNERF_DP_MAX_RANKS];       /* fp32 replicas; entry 0 = the local master (also the input), others nullable */
   void* p16_out[CEDNERF_DP_MAX_RANKS];        /* fp16 working copies (nullable entries) */
   float* m;                                   /* Adam moments of the owned range, indexed from lo */
   float* v;

@@ -67,6 +67,7 @@ def main():
         scaler.step(opt)
         scaler.update()
         if it == 0:
+            opt.sync_master()   # one-sided: the peers' owned ranges of the fp32 master (they cannot be a step ahead)
             p_after1 = {n: p.detach().clone() for n, p in field.named_parameters()}
     torch.cuda.synchronize()
     assert not opt.timed_out()
@@ -95,7 +96,13 @@ def main():
         d = (got - want)[solid].abs().max() if solid.any() else torch.zeros(())
         assert float(d) <= 2e-6, (n, float(d))
         assert torch.equal(got[~solid & (gavg == 0)], p0[~solid & (gavg == 0)])  # untouched entries did not move
-    # (3) replicas are bit-identical across ranks: fp32 master, fp16 working copy, MLP parameters
+    # (3) replicas are bit-identical across ranks: fp16 working copy, MLP parameters - and the fp32 master once every rank
+    # has pulled the ranges it does not own (one-sided; the default all-gathers only the fp16 copy per step)
+    if world > 1:
+        own = table.detach().view(-1)[opt._lo:opt._hi].clone()
+        opt.sync_master()
+        assert torch.equal(own, table.detach().view(-1)[opt._lo:opt._hi])
+        dist.barrier()
     for n, p in list(field.named_parameters()) + [("table_f16", field.hash_encoder.table_f16())]:
         if p.numel() == 0:
             continue
