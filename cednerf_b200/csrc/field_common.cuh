@@ -91,6 +91,8 @@ __device__ __forceinline__ float rnd16(uint32_t acc_bits) { return __half2float(
 // Time embedding on the special-function unit: arguments are t 2^i (+ pi/2) with t in [0, 1], i <= 3, i.e. below 10 rad,
 // where __sinf's fp32 argument scaling is good to ~6e-7 absolute; the nine values are rounded to fp16 (half ulp 2.4e-4)
 // as soon as they enter the MLP input row.  (Full-precision sinf was 1200 SASS instructions and ~160 executed per sample.)
+// EXACT = true (gradient-carrying kernels): sinf / expf, the arithmetic of the stand-alone encoder (encodings.cu).
+template <bool EXACT = false>
 __device__ __forceinline__ void time_embedding(float tv, float mvnorm, int mode, float* e /*[9]*/) {
   const float half_pi = 1.5707963267948966f;
   e[0] = tv;
@@ -98,17 +100,17 @@ __device__ __forceinline__ void time_embedding(float tv, float mvnorm, int mode,
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float tb = tv * (float)(1 << i);
-      e[1 + i] = __sinf(tb);
-      e[5 + i] = __sinf(tb + half_pi);
+      e[1 + i] = EXACT ? sinf(tb) : __sinf(tb);
+      e[5 + i] = EXACT ? sinf(tb + half_pi) : __sinf(tb + half_pi);
     }
   } else {
     const float scm[4] = {0.f, 2.f, 8.f, 24.f};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float tb = tv * (float)(1 << i);
-      const float att = __expf(-1.f * (mvnorm * scm[i]));
-      e[1 + 2 * i] = __sinf(tb) * att;
-      e[2 + 2 * i] = __sinf(tb + half_pi) * att;
+      const float att = EXACT ? expf(-1.f * (mvnorm * scm[i])) : __expf(-1.f * (mvnorm * scm[i]));
+      e[1 + 2 * i] = (EXACT ? sinf(tb) : __sinf(tb)) * att;
+      e[2 + 2 * i] = (EXACT ? sinf(tb + half_pi) : __sinf(tb + half_pi)) * att;
     }
   }
 }
@@ -208,7 +210,14 @@ __device__ __forceinline__ void packed_sample(const int64_t* __restrict__ ridx, 
   tv = ts[ray * t_stride];
 }
 
-// Frequency(4 dims, 4 octaves) of (v0, v1, v2, v3) -> 32 halves in chunks 0..3 of row `row` of a swizzled tile
+// Frequency(4 dims, 4 octaves) of (v0, v1, v2, v3) -> 32 halves in chunks 0..3 of row `row` of a swizzled tile.
+// EXACT = false: MUFU.SIN / MUFU.COS (2^-21 ABSOLUTE error: values near a zero crossing can land one fp16 ulp off) - the
+// no-grad kernels (sampler pre-pass, eval rendering).  EXACT = true: sincospif (1 ulp of fp32, i.e. the correctly rounded
+// fp16 value except at near-ties) - the gradient-carrying kernels: a hidden unit of the deformation net whose
+// pre-activation sits near zero has its ReLU mask decided by that last fp16 ulp of its inputs, and the mask then
+// multiplies every sample's gradient (measured on the D-NeRF-shaped configuration, 2.8 M samples: one such unit put the
+// deformation net's weight gradient 4.6e-3 away from the oracle's; with exact inputs it is 6e-4, profiles/r2*_parity*).
+template <bool EXACT = false>
 __device__ __forceinline__ void frequency_row(uint8_t* tile, int row, float v0, float v1, float v2, float v3) {
   const float in4[4] = {v0, v1, v2, v3};
 #pragma unroll
@@ -217,7 +226,8 @@ __device__ __forceinline__ void frequency_row(uint8_t* tile, int row, float v0, 
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float sn, cs;  // sin(pi ph) and sin(pi (ph + 1/2)) = cos(pi ph): one range reduction for the pair
-      sincospi_fast(in4[dim] * (float)(1 << k), sn, cs);
+      if (EXACT) sincospif(in4[dim] * (float)(1 << k), &sn, &cs);
+      else sincospi_fast(in4[dim] * (float)(1 << k), sn, cs);
       p[k] = pack_h2(sn, cs);
     }
     *reinterpret_cast<uint4*>(tile + swz(row, dim)) = make_uint4(p[0], p[1], p[2], p[3]);

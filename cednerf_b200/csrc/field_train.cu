@@ -11,6 +11,8 @@
 // the hash-feature gradient: the features are that net's huber target) -> hash-table gradient -> feature predictor ->
 // dL/dx of the encoding -> deformation net.  Everything after the table gradient can run under its all-reduce.  Gradient dtype flow is tcnn's: gradients that cross a
 // module boundary are fp16, hidden gradients are fp16, weight / table gradients and dL/dx are fp32.
+#include <stdlib.h>
+
 #include "field_common.cuh"
 
 namespace {
@@ -76,6 +78,7 @@ struct TrainArgs {
   uint8_t* work;
   float* d_params[4];
   uint32_t tmem_cols;
+  int flush_tiles;  // > 0: flush the TMEM weight-gradient accumulators every this many tiles of a group
   CednerfFieldDesc d;
 };
 
@@ -147,7 +150,7 @@ __global__ void __launch_bounds__(768, 1) field_train_fwd_kernel(TrainArgs a) {
     int64_t ray = 0;
     if (ok) packed_sample(a.ridx, a.t0, a.t1, a.rays_o, a.rays_d, a.t, a.t_stride, s, x, tv, ray);
     // ---- deformation net ---------------------------------------------------------------------------------------
-    frequency_row(abuf, gtid, x[0], x[1], x[2], tv);
+    frequency_row<true>(abuf, gtid, x[0], x[1], x[2], tv);
     fence_proxy_async();
     tc_fence_before();
     group_sync(group);
@@ -200,7 +203,7 @@ __global__ void __launch_bounds__(768, 1) field_train_fwd_kernel(TrainArgs a) {
           put_word(l0, f1w[0]);
         }
       }
-      if (d.time_mode) time_embedding(tv, mvnorm, d.time_mode, temb);
+      if (d.time_mode) time_embedding<true>(tv, mvnorm, d.time_mode, temb);
       int w = L;
       if (d.time_mode && d.time_before_sigma) {
 #pragma unroll
@@ -252,7 +255,7 @@ __global__ void __launch_bounds__(768, 1) field_train_fwd_kernel(TrainArgs a) {
     }
     if (has4) {
       // ---- hash-feature predictor on Frequency(x_norm, t) and its huber loss against the hash features ------------
-      frequency_row(abuf, gtid, xn[0], xn[1], xn[2], tv);
+      frequency_row<true>(abuf, gtid, xn[0], xn[1], xn[2], tv);
       fence_proxy_async();
       tc_fence_before();
       group_sync(group);
@@ -430,10 +433,10 @@ __device__ __forceinline__ void make_input(const TrainArgs& a, const SavedLayout
   int64_t ray;
   packed_sample(a.ridx, a.t0, a.t1, a.rays_o, a.rays_d, a.t, a.t_stride, s, x, tv, ray);
   if constexpr (NET == 1) {
-    frequency_row(tile, row, x[0], x[1], x[2], tv);
+    frequency_row<true>(tile, row, x[0], x[1], x[2], tv);
   } else if constexpr (NET == 4) {
     const float* xs = reinterpret_cast<const float*>(a.saved + sl.xn) + 3 * s;
-    frequency_row(tile, row, xs[0], xs[1], xs[2], tv);
+    frequency_row<true>(tile, row, xs[0], xs[1], xs[2], tv);
   } else {  // NET == 3
     float temb[9];
     if (d.time_mode && !d.time_before_sigma) {
@@ -441,7 +444,7 @@ __device__ __forceinline__ void make_input(const TrainArgs& a, const SavedLayout
       bool sel;
       load_off(a, sl, s, off6);
       apply_move(d, x, off6, mv, xn, sel);
-      time_embedding(tv, sqrtf(mv[0] * mv[0] + mv[1] * mv[1] + mv[2] * mv[2]), d.time_mode, temb);
+      time_embedding<true>(tv, sqrtf(mv[0] * mv[0] + mv[1] * mv[1] + mv[2] * mv[2]), d.time_mode, temb);
     }
     const uint4* src = reinterpret_cast<const uint4*>(a.saved + sl.o2 + s * 32);
     const uint4 q0 = src[0], q1 = src[1];
@@ -512,7 +515,46 @@ __global__ void __launch_bounds__(BWD_GROUPS * MLP_TILE, 1) field_bwd_kernel(Tra
   const int64_t n_tiles = (n + MLP_TILE - 1) / MLP_TILE;
   const bool want_dx = NET != 1;  // the deformation net's input (x, t) carries no gradient
 
-  for (int64_t tile = blockIdx.x + (int64_t)gridDim.x * group; tile < n_tiles; tile += (int64_t)gridDim.x * n_groups) {
+  // flush: TMEM weight-gradient accumulators -> d_params (fp32 atomics); with rezero the accumulation starts over
+  auto flush_wgrad = [&](bool rezero) {
+    if (group == 0) {
+      for (int l = 0; l < L; ++l) {
+        const int K_in = d.dim_in[l], N_out = d.dim_out[l];
+        const int half = l & 1;                       // which 16-lane half of the sub-partition holds this layer
+        const int m = warp * 16 + (lane & 15);
+        for (int cb = 0; cb < K_in / 16; ++cb) {
+          uint32_t r[16];
+          tmem_ld16(wg_warp + 64u * (uint32_t)(l >> 1) + cb * 16, r);
+          tmem_ld_wait();
+          if ((lane >> 4) == half && m < N_out) {
+            float* dst = d_params + d.param_off[l] + m * K_in + cb * 16;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) atomicAdd(dst + j, __uint_as_float(r[j]));
+          }
+        }
+      }
+      if (rezero) {
+        for (int cb = 0; cb < 4 * ((L + 1) / 2); ++cb) tmem_st16_fill(wg_warp + cb * 16, 0u);
+        tmem_st_wait();
+      }
+      tc_fence_before();
+    }
+  };
+  const int64_t stride = (int64_t)gridDim.x * n_groups;
+  const int64_t first = blockIdx.x + (int64_t)gridDim.x * group;
+  // the same trip count for every group of the CTA (the periodic flush below synchronises the whole CTA)
+  const int64_t n_iter = (n_tiles - blockIdx.x + stride - 1) / stride;
+  for (int64_t it = 0; it < n_iter; ++it) {
+    const int64_t tile = first + it * stride;
+    if (a.flush_tiles > 0 && it > 0 && (it % a.flush_tiles) == 0) {
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+      flush_wgrad(true);
+      __syncthreads();
+      tc_fence_after();
+    }
+    if (tile >= n_tiles) continue;
     const int64_t row0 = tile * MLP_TILE;
     const int rows_valid = (int)((n - row0) < MLP_TILE ? (n - row0) : MLP_TILE);
     const int64_t s = row0 + gtid;
@@ -645,24 +687,7 @@ __global__ void __launch_bounds__(BWD_GROUPS * MLP_TILE, 1) field_bwd_kernel(Tra
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (group == 0) {  // every CTA added into zero-initialised accumulators: flush them all (zeros where it had no tile)
-    for (int l = 0; l < L; ++l) {
-      const int K_in = d.dim_in[l], N_out = d.dim_out[l];
-      const int half = l & 1;                       // which 16-lane half of the sub-partition holds this layer
-      const int m = warp * 16 + (lane & 15);
-      for (int cb = 0; cb < K_in / 16; ++cb) {
-        uint32_t r[16];
-        tmem_ld16(wg_warp + 64u * (uint32_t)(l >> 1) + cb * 16, r);
-        tmem_ld_wait();
-        if ((lane >> 4) == half && m < N_out) {
-          float* dst = d_params + d.param_off[l] + m * K_in + cb * 16;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) atomicAdd(dst + j, __uint_as_float(r[j]));
-        }
-      }
-    }
-    tc_fence_before();
-  }
+  flush_wgrad(false);  // every CTA added into zero-initialised accumulators: flush them all (zeros where it had no tile)
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, a.tmem_cols);
 }
@@ -745,11 +770,17 @@ int launch_bwd(TrainArgs a, cudaStream_t st) {
   if (int e = cednerf_opt_in_smem(field_bwd_kernel<NET>, BWD_SMEM_MAX, configured, "cednerf_field_train_bwd")) return e;
   const CednerfMlpDesc& d = NET == 1 ? a.d.f1 : (NET == 2 ? a.d.f2 : (NET == 3 ? a.d.f3 : a.d.f4));
   int groups = BWD_GROUPS;  // as many tiles in flight as shared memory (weights + 48 KB per group) and TMEM allow
+  if (const char* env = getenv("CEDNERF_BWD_GROUPS")) {  // diagnostic: 1 = no weight-gradient accumulator is shared
+    const int g = atoi(env);
+    if (g >= 1 && g < groups) groups = g;
+  }
   const int fixed = ((d.image_bytes + 1023) & ~1023) + 2048;
   while (groups > 1 && (fixed + groups * BWD_GROUP_SMEM > BWD_SMEM_MAX || 64 * (groups + (d.n_layers + 1) / 2) > 512)) --groups;
   uint32_t cols = 64u * (uint32_t)(groups + (d.n_layers + 1) / 2), alloc = 64;
   while (alloc < cols) alloc <<= 1;
   a.tmem_cols = alloc;
+  a.flush_tiles = 0;
+  if (const char* env = getenv("CEDNERF_BWD_FLUSH_TILES")) a.flush_tiles = atoi(env);
   const int64_t tiles = (a.n + MLP_TILE - 1) / MLP_TILE;
   const int64_t max_ctas = (int64_t)cednerf_num_sms();
   field_bwd_kernel<NET><<<(unsigned)(tiles < max_ctas ? tiles : max_ctas), groups * MLP_TILE, fixed + groups * BWD_GROUP_SMEM, st>>>(a);
