@@ -63,6 +63,9 @@ def parse():
     ap.add_argument("--render-frames", type=int, default=300,
                     help="frames of the video leg in total (subsampled from the 300-pose spiral; 0 = skip)")
     ap.add_argument("--headline-only", action="store_true", help="skip the other configurations")
+    ap.add_argument("--host-counts", action="store_true",
+                    help="read the sample totals back to the host inside the step (the reference's behaviour) instead "
+                         "of the capacity mode that keeps them on the device")
     ap.add_argument("--dp", default="peer", choices=["peer", "nccl"], help="multi-GPU optimiser step")
     ap.add_argument("--torch-profile", default="", help="write a torch.profiler kernel table of one step to this file")
     return ap.parse_args()
@@ -152,13 +155,15 @@ class OccupancyUpdate:
         self.step += 1
 
 
-def train_step(impl, field, est, opt, scaler, batch, cfg, rk, reducer=None, sched=None, occ=None):
+def train_step(impl, field, est, opt, scaler, batch, cfg, rk, reducer=None, sched=None, occ=None, device_counts=False):
     if occ is not None:
         occ()
     rays = impl.Rays(batch["origins"], batch["viewdirs"])
+    extra_kw = {"device_counts": True} if device_counts else {}   # this repo only: no host read inside the step
     rgb, acc, depth, n_samples, extra = impl.render_image(field, est, rays, render_bkgd=batch["color_bkgd"],
-                                                          timestamps=batch["timestamps"], jitter=batch["jitter"], **rk)
-    if n_samples == 0:
+                                                          timestamps=batch["timestamps"], jitter=batch["jitter"], **rk,
+                                                          **extra_kw)
+    if not torch.is_tensor(n_samples) and n_samples == 0:
         return None, 0
     if hasattr(impl, "losses"):  # this repo: the same loss as one fused forward / backward launch
         loss = impl.losses.training_loss(rgb, acc, batch["pixels"], extra, acc_entropy_loss=True, weight_rgbper=True,
@@ -227,7 +232,8 @@ class ClockSampler:
 
 
 # algorithmic bytes per launch of each entry point (SURVEY.md §8d per-unit figures x units of the launch)
-def algorithmic_bytes(name, args):
+def algorithmic_bytes(name, args, live=None):
+    live = live or {}
     if name == "cednerf_hashgrid_fwd":
         n, L = args[2], args[4]._obj.n_levels
         return n * (L * 8 * 4 + 12 + L * 4)                     # 512 B table + 12 B xyz + 64 B features (L = 16)
@@ -241,12 +247,18 @@ def algorithmic_bytes(name, args):
         return b
     if name == "cednerf_field_fwd":
         n, L = args[9], args[14]._obj.levels.n_levels
+        if args[17] and live.get("marched"):                     # capacity-sized launch: the live count is what moves
+            n = min(n, live["marched"])
         return n * (L * 8 * 4 + 16 + 4 + (12 if args[16] else 0))  # 512 B table + packed sample 16 B + sigma (+ rgb)
     if name == "cednerf_field_train_fwd":                       # 512 B table + 16 B sample + sigma / rgb / selector / move
         n, L = args[7], args[13]._obj.levels.n_levels
+        if args[-2] and live.get("visible"):
+            n = min(n, live["visible"])
         return n * (L * 8 * 4 + 16 + 4 + 12 + 1 + 12)
     if name == "cednerf_field_train_bwd":                       # 1024 B table-gradient RMW + 512 B table re-read + d_sigma / d_rgb
         n, L = args[7], args[13]._obj.levels.n_levels
+        if args[-2] and live.get("visible"):
+            n = min(n, live["visible"])
         return n * (L * 8 * 8 + L * 8 * 4 + 16 + 16)
     if name == "cednerf_mlp_fwd":
         d, n = args[2]._obj, args[3]
@@ -262,9 +274,9 @@ def algorithmic_bytes(name, args):
     if name == "cednerf_march_fill_runs":
         return None
     if name == "cednerf_composite_fwd":
-        return args[8] * 44 + args[9] * 20
+        return min(args[8], live.get("visible") or args[8]) * 44 + args[9] * 20
     if name == "cednerf_composite_bwd":
-        return args[8] * 60 + args[9] * 20
+        return min(args[8], live.get("visible") or args[8]) * 60 + args[9] * 20
     if name == "cednerf_adam_step":                             # 16 B read + 12 B written (+ 2 B fp16 copy) per parameter
         t = args[0]._obj
         return sum(t.n[k] * (30 if t.p16[k] else 28) for k in range(t.n_tensors))
@@ -300,10 +312,10 @@ class Instrument:
         for m in self.mods:
             m.call = self.real
 
-    def aggregate(self):
+    def aggregate(self, live=None):
         agg = {}
         for name, a, s, e in self.rec:
-            by = algorithmic_bytes(name, a)
+            by = algorithmic_bytes(name, a, live)
             d = agg.setdefault(name, {"ms": 0.0, "launches": 0, "bytes": 0, "has_bytes": by is not None})
             d["ms"] += s.elapsed_time(e)
             d["launches"] += 1
@@ -415,11 +427,12 @@ def train_leg(D, cb, workload, cfg, args, n_rays, steps, warmup, full: bool):
             opt.zero_grad()
 
     def step_resident(i):
-        return train_step(cb, field, est, opt, scaler, resident[i % n_host], cfg, rk, reducer, state.sched, occ)
+        return train_step(cb, field, est, opt, scaler, resident[i % n_host], cfg, rk, reducer, state.sched, occ,
+                          not args.host_counts)
 
     def step_e2e(i):
         b = {k: v.to(dev, non_blocking=True) for k, v in host[i % n_host].items()}
-        loss, n_s = train_step(cb, field, est, opt, scaler, b, cfg, rk, reducer, state.sched, occ)
+        loss, n_s = train_step(cb, field, est, opt, scaler, b, cfg, rk, reducer, state.sched, occ, not args.host_counts)
         return (None if loss is None else float(loss.item())), n_s  # device -> host read of the step's result
 
     def timed(fn, k):
@@ -447,14 +460,23 @@ def train_leg(D, cb, workload, cfg, args, n_rays, steps, warmup, full: bool):
         e1.record()
         D.barrier()
         ms = dp.max_over_ranks(e0.elapsed_time(e1) / k, dev)
-        return ms, n_tot / k, (_lib.launch_count() - l0) // k
+        return ms, float(n_tot) / k, (_lib.launch_count() - l0) // k
 
+    if os.environ.get("BENCH_SYNC_DEBUG"):   # list every host<->device synchronisation of two steady-state steps
+        state.restore()
+        for i in range(4):
+            step_resident(i)
+        torch.cuda.synchronize()
+        torch.cuda.set_sync_debug_mode("warn")
+        for i in range(2):
+            step_resident(4 + i)
+        torch.cuda.set_sync_debug_mode("default")
     clocks = ClockSampler(D.local_rank) if (full and rank == 0) else None
     if clocks:
         clocks.start()
     ms, samples, launches = timed(step_resident, steps)
     out = {"ms": ms, "samples": dp.sum_over_ranks(samples, dev), "launches": int(launches), "occ_updates": occ.updates,
-           "dp_mode": dp_mode, "rays": n_rays * world, "clocks": clocks.stop() if clocks else None,
+           "dp_mode": dp_mode, "rays": n_rays * world, "dropped": int(est.dropped_samples), "clocks": clocks.stop() if clocks else None,
            "h2d": sum(v.numel() * v.element_size() for v in host[0].values())}
     if full:
         out["ms_e2e"] = timed(step_e2e, steps)[0]
@@ -470,7 +492,8 @@ def train_leg(D, cb, workload, cfg, args, n_rays, steps, warmup, full: bool):
             torch.cuda.synchronize()
             prof_ms = (time.perf_counter() - t0) * 1e3 / args.profile_steps
         if rank == 0:
-            agg = ins.aggregate()
+            live = {k: v.get("last") for k, v in est._cap_state.items()}   # totals of a recent batch (capacity mode)
+            agg = ins.aggregate(live)
             out["breakdown"] = {n: {"ms_per_step": round(d["ms"] / args.profile_steps, 4),
                                     "launches_per_step": d["launches"] // args.profile_steps} for n, d in agg.items()}
             out["breakdown"]["_ours_total_ms"] = round(sum(v["ms"] for v in agg.values()) / args.profile_steps, 3)
@@ -594,6 +617,8 @@ def run_ours(args):
                        "samples_per_s": round(t["samples"] / (t["ms"] * 1e-3), 1),
                        "l2": "working set (96 MB fp16 table, 191 MB fp32 master, 383 MB Adam state) exceeds the 126 MB L2; 4 rotating batches",
                        "occ_update": f"every step on a twin estimator; {t['occ_updates']} full update(s) in the timed steps",
+                       "sample_counts": ("host reads (reference behaviour)" if args.host_counts else
+                                         f"device-side, capacity mode; {t['dropped']} samples dropped"),
                        "parallelism": ("single" if world == 1 else
                                        f"dp{world}, optimiser step: " + ("fused reduce-scatter+Adam+all-gather over NVLink peer memory"
                                                                         if t["dp_mode"] == "peer" else "NCCL all-reduce + Adam"))},

@@ -76,8 +76,12 @@ _SIGNATURES = {
     "cednerf_occ_mark_invisible": "pipiipiiiifpp",
     "cednerf_march": "ipplppiippffffippppppppppppppppppppppipp",
     "cednerf_ray_coherence_keys": "plpp",
+    "cednerf_ray_coherence_order": "plppp",
     "cednerf_march_fill_runs": "lppppiffppppp",
     "cednerf_exclusive_scan": "plppppp",
+    "cednerf_exclusive_scan_capped": "pllpppp",
+    "cednerf_march_fill_runs_capped": "lpppppiffppppp",
+    "cednerf_compact_samples_capped": "pppppllpppp",
     "cednerf_hashgrid_fwd": "pilpGpip",
     "cednerf_hashgrid_bwd": "pilpGpiippp",
     "cednerf_hashgrid_bwd_table_lm": "pilGppp",
@@ -92,18 +96,18 @@ _SIGNATURES = {
     "cednerf_mlp_fwd": "ppMlppp",
     "cednerf_mlp_bwd": "ppppMlpippp",
     "cednerf_field_fwd": "ppppppppilppppFpppp",
-    "cednerf_field_train_fwd": "ppppppilpppppFppppppp",
-    "cednerf_field_train_bwd": "ppppppilpppppFpppppppppppppip",
+    "cednerf_field_train_fwd": "ppppppilpppppFpppppppp",
+    "cednerf_field_train_bwd": "ppppppilpppppFpppppppppppppipp",
     "cednerf_ray_offsets": "pllpp",
     "cednerf_composite_fwd": "pppppppillpppppppifp",
     "cednerf_composite_bwd": "pppppppillppppppppppfp",
     "cednerf_visibility_mask": "ppppllffppp",
     "cednerf_compact_samples": "pppppllpppp",
     "cednerf_accumulate_fwd": "ppipllpip",
-    "cednerf_accumulate_bwd": "ppiplpppp",
+    "cednerf_accumulate_bwd": "ppiplppppp",
     "cednerf_nonfinite_check": "App",
-    "cednerf_training_loss_fwd": "ppplppplpiffppp",
-    "cednerf_training_loss_bwd": "pppplpppliffppppp",
+    "cednerf_training_loss_fwd": "ppplppplpiffpppp",
+    "cednerf_training_loss_bwd": "pppplpppliffpppppp",
     "cednerf_adam_step": "Apippfffip",
     "cednerf_peer_alloc": "lp",
     "cednerf_peer_free": "p",

@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(256)
 compact_samples_kernel(const uint8_t* __restrict__ keep, const int64_t* __restrict__ offsets,
                        const int64_t* __restrict__ out_starts, const float* __restrict__ t0, const float* __restrict__ t1,
                        int64_t n_rays, int64_t* __restrict__ ridx_out, float* __restrict__ t0_out,
-                       float* __restrict__ t1_out) {
+                       float* __restrict__ t1_out, int capped) {
   const int gl = threadIdx.x % G;
   const unsigned gm = group_mask<G>();
   const int shift = (threadIdx.x & 31) / G * G;
@@ -286,11 +286,14 @@ compact_samples_kernel(const uint8_t* __restrict__ keep, const int64_t* __restri
   if (ray >= n_rays) return;
   const int64_t s0 = offsets[ray], s1 = offsets[ray + 1];
   int64_t dst = out_starts[ray];
+  // capped: out_starts = offsets [n_rays + 1] clamped to the capacity of the outputs; nothing lands at or beyond the
+  // clamped end of the ray's range
+  const int64_t dst_end = capped ? out_starts[ray + 1] : INT64_MAX;
   for (int64_t base = s0; base < s1; base += G) {
     const int64_t i = base + gl;
     const bool k = i < s1 && keep[i] != 0;
     const unsigned bits = (__ballot_sync(gm, k) & gm) >> shift;
-    if (k) {
+    if (k && dst + __popc(bits & ((1u << gl) - 1u)) < dst_end) {
       const int64_t o = dst + __popc(bits & ((1u << gl) - 1u));
       ridx_out[o] = ray;
       t0_out[o] = t0[i];
@@ -323,9 +326,9 @@ accumulate_fwd_kernel(const float* __restrict__ w, const float* __restrict__ v, 
 
 __global__ void accumulate_bwd_kernel(const float* __restrict__ w, const float* __restrict__ v, int C,
                                       const int64_t* __restrict__ ridx, int64_t S, const float* __restrict__ g_out,
-                                      float* __restrict__ g_w, float* __restrict__ g_v) {
+                                      float* __restrict__ g_w, float* __restrict__ g_v, const int64_t* __restrict__ S_dev) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= S) return;
+  if (i >= S || (S_dev && i >= *S_dev)) return;
   const int64_t r = ridx[i];
   const float wi = w[i];
   float acc = 0.f;
@@ -354,10 +357,10 @@ accumulate_wide_fwd_kernel(const float* __restrict__ w, const float* __restrict_
 __global__ void __launch_bounds__(256)
 accumulate_wide_bwd_kernel(const float* __restrict__ w, const float* __restrict__ v, int C,
                            const int64_t* __restrict__ ridx, int64_t S, const float* __restrict__ g_out,
-                           float* __restrict__ g_w, float* __restrict__ g_v) {
+                           float* __restrict__ g_w, float* __restrict__ g_v, const int64_t* __restrict__ S_dev) {
   const int lane = threadIdx.x & 31;
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (i >= S) return;
+  if (i >= S || (S_dev && i >= *S_dev)) return;
   const int64_t r = ridx[i];
   const float go = lane < C ? g_out[r * C + lane] : 0.f;
   if (g_v && lane < C) g_v[i * C + lane] = w[i] * go;
@@ -393,11 +396,12 @@ accumulate_c32_fwd_kernel(const float* __restrict__ w, const float4* __restrict_
 
 __global__ void __launch_bounds__(256)
 accumulate_c32_bwd_kernel(const float* __restrict__ w, const float4* __restrict__ v, const int64_t* __restrict__ ridx,
-                          int64_t S, const float4* __restrict__ g_out, float* __restrict__ g_w, float4* __restrict__ g_v) {
+                          int64_t S, const float4* __restrict__ g_out, float* __restrict__ g_w, float4* __restrict__ g_v,
+                          const int64_t* __restrict__ S_dev) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t i = t >> 3;
   const int c = (int)(t & 7);
-  const bool ok = i < S;
+  const bool ok = i < S && (!S_dev || i < *S_dev);
   float part = 0.f;
   if (ok) {
     const float4 go = g_out[ridx[i] * 8 + c];
@@ -500,8 +504,22 @@ CEDNERF_EXPORT int cednerf_compact_samples(const uint8_t* keep, const int64_t* o
   if (n_rays == 0 || n_samples == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   DISPATCH_G(pick_group(n_samples, n_rays), compact_samples_kernel, keep, offsets, out_starts, t_starts, t_ends, n_rays,
-             ray_indices_out, t_starts_out, t_ends_out);
+             ray_indices_out, t_starts_out, t_ends_out, 0);
   return cednerf_check_launch("cednerf_compact_samples");
+}
+
+// The same compaction into outputs of a fixed capacity: out_offsets [n_rays + 1] from cednerf_exclusive_scan_capped over
+// the kept counts (kept samples at or beyond the capacity are dropped); n_samples is only an estimate for the launch shape.
+CEDNERF_EXPORT int cednerf_compact_samples_capped(const uint8_t* keep, const int64_t* offsets, const int64_t* out_offsets,
+                                                  const float* t_starts, const float* t_ends, int64_t n_samples,
+                                                  int64_t n_rays, int64_t* ray_indices_out, float* t_starts_out,
+                                                  float* t_ends_out, void* stream) {
+  CEDNERF_REQUIRE(n_rays >= 0 && n_samples >= 0 && keep && offsets && out_offsets, "bad arguments");
+  if (n_rays == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_G(pick_group(n_samples, n_rays), compact_samples_kernel, keep, offsets, out_offsets, t_starts, t_ends, n_rays,
+             ray_indices_out, t_starts_out, t_ends_out, 1);
+  return cednerf_check_launch("cednerf_compact_samples_capped");
 }
 
 CEDNERF_EXPORT int cednerf_accumulate_fwd(const float* weights, const float* values, int n_channels,
@@ -527,7 +545,7 @@ CEDNERF_EXPORT int cednerf_accumulate_fwd(const float* weights, const float* val
 
 CEDNERF_EXPORT int cednerf_accumulate_bwd(const float* weights, const float* values, int n_channels,
                                           const int64_t* ray_indices, int64_t n_samples, const float* g_outputs,
-                                          float* g_weights, float* g_values, void* stream) {
+                                          float* g_weights, float* g_values, const int64_t* n_device, void* stream) {
   CEDNERF_REQUIRE(n_samples >= 0 && n_channels >= 1, "bad sizes");
   if (n_samples == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
@@ -535,15 +553,15 @@ CEDNERF_EXPORT int cednerf_accumulate_bwd(const float* weights, const float* val
       (((uintptr_t)values | (uintptr_t)g_outputs | (uintptr_t)g_values) & 15) == 0) {
     accumulate_c32_bwd_kernel<<<cednerf_blocks(n_samples * 8, 256), 256, 0, st>>>(
         weights, reinterpret_cast<const float4*>(values), ray_indices, n_samples,
-        reinterpret_cast<const float4*>(g_outputs), g_weights, reinterpret_cast<float4*>(g_values));
+        reinterpret_cast<const float4*>(g_outputs), g_weights, reinterpret_cast<float4*>(g_values), n_device);
     return cednerf_check_launch("cednerf_accumulate_bwd");
   }
   if (values && n_channels >= 8 && n_channels <= 32) {
     accumulate_wide_bwd_kernel<<<cednerf_blocks(n_samples * 32, 256), 256, 0, st>>>(
-        weights, values, n_channels, ray_indices, n_samples, g_outputs, g_weights, g_values);
+        weights, values, n_channels, ray_indices, n_samples, g_outputs, g_weights, g_values, n_device);
     return cednerf_check_launch("cednerf_accumulate_bwd");
   }
   accumulate_bwd_kernel<<<cednerf_blocks(n_samples, 256), 256, 0, st>>>(weights, values, n_channels, ray_indices,
-                                                                       n_samples, g_outputs, g_weights, g_values);
+                                                                       n_samples, g_outputs, g_weights, g_values, n_device);
   return cednerf_check_launch("cednerf_accumulate_bwd");
 }

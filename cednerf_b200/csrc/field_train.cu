@@ -61,7 +61,8 @@ struct TrainArgs {
   const float* rays_d;
   const float* t;
   int t_stride;
-  int64_t n;
+  int64_t n;             // capacity of the sample arrays: layouts and strides
+  const int64_t* n_dev;  // nullable: live sample count on the device (min(n, *n_dev) samples are processed)
   const uint8_t* img[4];
   const __half* table;
   // forward outputs (also read by the backward)
@@ -81,6 +82,12 @@ struct TrainArgs {
   int flush_tiles;  // > 0: flush the TMEM weight-gradient accumulators every this many tiles of a group
   CednerfFieldDesc d;
 };
+
+__device__ __forceinline__ int64_t live_count(const TrainArgs& a) {
+  if (!a.n_dev) return a.n;
+  const int64_t v = *a.n_dev;
+  return v < a.n ? v : a.n;
+}
 
 __device__ __forceinline__ float huber(float x) {
   const float ax = fabsf(x);
@@ -135,8 +142,8 @@ __global__ void __launch_bounds__(768, 1) field_train_fwd_kernel(TrainArgs a) {
   const uint32_t tmem_base = tmem_base_s + 64u * (uint32_t)group;
   const uint32_t tmem_warp = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   uint32_t phase = 0;
-  const int64_t n = a.n;
-  const int64_t n_tiles = (n + MLP_TILE - 1) / MLP_TILE;
+  const int64_t n = a.n, nl = live_count(a);
+  const int64_t n_tiles = (nl + MLP_TILE - 1) / MLP_TILE;
   const int L = d.levels.n_levels;
   const uint32_t one2 = 0x3C003C00u;
   const SavedLayout sl = saved_layout(d, n);
@@ -144,8 +151,8 @@ __global__ void __launch_bounds__(768, 1) field_train_fwd_kernel(TrainArgs a) {
 
   for (int64_t tile = blockIdx.x + (int64_t)gridDim.x * group; tile < n_tiles; tile += (int64_t)gridDim.x * n_groups) {
     const int64_t s = tile * MLP_TILE + gtid;
-    const bool ok = s < n;
-    const int rows_valid = (int)((n - tile * MLP_TILE) < MLP_TILE ? (n - tile * MLP_TILE) : MLP_TILE);
+    const bool ok = s < nl;
+    const int rows_valid = (int)((nl - tile * MLP_TILE) < MLP_TILE ? (nl - tile * MLP_TILE) : MLP_TILE);
     float x[3] = {0.f, 0.f, 0.f}, tv = 0.f;
     int64_t ray = 0;
     if (ok) packed_sample(a.ridx, a.t0, a.t1, a.rays_o, a.rays_d, a.t, a.t_stride, s, x, tv, ray);
@@ -346,7 +353,9 @@ __device__ __forceinline__ void make_dout(const TrainArgs& a, const SavedLayout&
   uint32_t w[16];  // up to 32 halves
 #pragma unroll
   for (int j = 0; j < 16; ++j) w[j] = 0u;
-  int n_chunks = 2;
+  // rows past the end are zero-filled over the WHOLE width of this network's output gradient (a stale NaN pattern in
+  // shared memory would otherwise meet a zero activation in the weight-gradient MMA: 0 x NaN)
+  const int n_chunks = NET == 4 ? 4 : 2;
   if (ok) {
     if constexpr (NET == 3) {
       float g[3];
@@ -367,7 +376,6 @@ __device__ __forceinline__ void make_dout(const TrainArgs& a, const SavedLayout&
       const float hi = __half2float(__ushort_as_half((unsigned short)(w[0] >> 16)));
       w[0] = pack_h2(gs, hi);
     } else if constexpr (NET == 4) {
-      n_chunks = 4;
       predictor_dout(a, sl, s, 0, w);
       predictor_dout(a, sl, s, 1, w + 8);
     } else {  // NET == 1: through aabb normalisation, x + move, move = o[:3]*MS + tanh(o[3:])*MS
@@ -482,7 +490,7 @@ __global__ void __launch_bounds__(BWD_GROUPS * MLP_TILE, 1) field_bwd_kernel(Tra
   __shared__ uint64_t bars[BWD_GROUPS];
   __shared__ uint32_t tmem_base_s;
   uint64_t* bar = &bars[group];
-  const int64_t n = a.n;
+  const int64_t n = a.n, nl = live_count(a);
   const SavedLayout sl = saved_layout(a.d, n);
   const BwdWorkLayout wl = bwd_layout(a.d, n);
   const uint8_t* image = a.img[NET - 1];
@@ -512,7 +520,7 @@ __global__ void __launch_bounds__(BWD_GROUPS * MLP_TILE, 1) field_bwd_kernel(Tra
   __syncthreads();
   tc_fence_after();
   uint32_t phase = 0;
-  const int64_t n_tiles = (n + MLP_TILE - 1) / MLP_TILE;
+  const int64_t n_tiles = (nl + MLP_TILE - 1) / MLP_TILE;
   const bool want_dx = NET != 1;  // the deformation net's input (x, t) carries no gradient
 
   // flush: TMEM weight-gradient accumulators -> d_params (fp32 atomics); with rezero the accumulation starts over
@@ -556,7 +564,7 @@ __global__ void __launch_bounds__(BWD_GROUPS * MLP_TILE, 1) field_bwd_kernel(Tra
     }
     if (tile >= n_tiles) continue;
     const int64_t row0 = tile * MLP_TILE;
-    const int rows_valid = (int)((n - row0) < MLP_TILE ? (n - row0) : MLP_TILE);
+    const int rows_valid = (int)((nl - row0) < MLP_TILE ? (nl - row0) : MLP_TILE);
     const int64_t s = row0 + gtid;
     const bool ok = gtid < rows_valid;
     if (L > 1) load_tile_async(ibuf[0], hidden + ((int64_t)(L - 2) * n + row0) * 64, 64, rows_valid, gtid, MLP_TILE);
@@ -698,9 +706,10 @@ __global__ void __launch_bounds__(BWD_GROUPS * MLP_TILE, 1) field_bwd_kernel(Tra
 // once.  Replaces the (sample, level)-per-thread kernel of hashgrid.cu on this path (0.38 ms -> see profiles/).
 __global__ void __launch_bounds__(256) hashgrid_bwd_input_lm_kernel(const float* __restrict__ xn, int64_t n,
                                                                     const __half* __restrict__ table, CednerfGridLevels lv,
-                                                                    const __half2* __restrict__ dy_lm, float* __restrict__ g_x) {
+                                                                    const __half2* __restrict__ dy_lm, float* __restrict__ g_x,
+                                                                    const int64_t* __restrict__ n_dev) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n) return;
+  if (s >= n || (n_dev && s >= *n_dev)) return;
   const float x[3] = {xn[3 * s], xn[3 * s + 1], xn[3 * s + 2]};
   float gx[3] = {0.f, 0.f, 0.f};
   const int L = lv.n_levels;
@@ -790,8 +799,9 @@ int launch_bwd(TrainArgs a, cudaStream_t st) {
 }  // namespace
 
 // hash-grid backward of hashgrid.cu (table gradient with run aggregation, dL/dx)
-extern "C" int cednerf_hashgrid_bwd_table_lm(const float* x, int x_stride, int64_t n, const CednerfGridLevels* levels,
-                                             const void* dy_lm_f16, float* g_table, void* stream);
+extern "C" int cednerf_hashgrid_bwd_table_lm_dev(const float* x, int x_stride, int64_t n, const int64_t* n_device,
+                                                 const CednerfGridLevels* levels, const void* dy_lm_f16, float* g_table,
+                                                 void* stream);
 extern "C" int cednerf_hashgrid_bwd(const float* x, int x_stride, int64_t n, const void* table_f16,
                                     const CednerfGridLevels* levels, const void* dy, int dy_stride, int dy_is_f16,
                                     float* g_table, float* g_x, void* stream);
@@ -810,7 +820,8 @@ CEDNERF_EXPORT int cednerf_field_train_fwd(const int64_t* ray_indices, const flo
                                            int t_stride, int64_t n, const void* image_deform, const void* image_density,
                                            const void* image_colour, const void* image_predict, const void* table_f16,
                                            const CednerfFieldDesc* desc, float* sigma, float* rgb, float* latent,
-                                           uint8_t* selector, float* move, void* saved, void* stream) {
+                                           uint8_t* selector, float* move, void* saved, const int64_t* n_device,
+                                           void* stream) {
   CEDNERF_REQUIRE(check_train_desc(desc), "bad field descriptor");
   CEDNERF_REQUIRE(n >= 0 && ray_indices && t_starts && t_ends && rays_o && rays_d && timestamps && sigma && rgb &&
                       selector && move && saved,
@@ -825,7 +836,7 @@ CEDNERF_EXPORT int cednerf_field_train_fwd(const int64_t* ray_indices, const flo
   if (int e = cednerf_opt_in_smem(field_train_fwd_kernel, 224 * 1024, configured, "cednerf_field_train_fwd")) return e;
   TrainArgs a{};
   a.ridx = ray_indices, a.t0 = t_starts, a.t1 = t_ends, a.rays_o = rays_o, a.rays_d = rays_d, a.t = timestamps;
-  a.t_stride = t_stride, a.n = n;
+  a.t_stride = t_stride, a.n = n, a.n_dev = n_device;
   a.img[0] = (const uint8_t*)image_deform, a.img[1] = (const uint8_t*)image_density;
   a.img[2] = (const uint8_t*)image_colour, a.img[3] = (const uint8_t*)image_predict;
   a.table = (const __half*)table_f16;
@@ -849,7 +860,7 @@ CEDNERF_EXPORT int cednerf_field_train_bwd(const int64_t* ray_indices, const flo
                                            const uint8_t* selector, const void* saved, const float* d_sigma,
                                            const float* d_rgb, const float* d_latent, void* work, float* d_params_deform,
                                            float* d_params_density, float* d_params_colour, float* d_params_predict,
-                                           float* g_table, int phase, void* stream) {
+                                           float* g_table, int phase, const int64_t* n_device, void* stream) {
   CEDNERF_REQUIRE(check_train_desc(desc), "bad field descriptor");
   CEDNERF_REQUIRE(phase >= 0 && phase <= 2, "phase: 0 all, 1 up to the table gradient, 2 the rest");
   CEDNERF_REQUIRE(n >= 0 && ray_indices && t_starts && t_ends && rays_o && rays_d && timestamps && rgb && selector &&
@@ -862,7 +873,7 @@ CEDNERF_EXPORT int cednerf_field_train_bwd(const int64_t* ray_indices, const flo
   cudaStream_t st = (cudaStream_t)stream;
   TrainArgs a{};
   a.ridx = ray_indices, a.t0 = t_starts, a.t1 = t_ends, a.rays_o = rays_o, a.rays_d = rays_d, a.t = timestamps;
-  a.t_stride = t_stride, a.n = n;
+  a.t_stride = t_stride, a.n = n, a.n_dev = n_device;
   a.img[0] = (const uint8_t*)image_deform, a.img[1] = (const uint8_t*)image_density;
   a.img[2] = (const uint8_t*)image_colour, a.img[3] = (const uint8_t*)image_predict;
   a.table = (const __half*)table_f16;
@@ -881,7 +892,7 @@ CEDNERF_EXPORT int cednerf_field_train_bwd(const int64_t* ray_indices, const flo
     if ((rc = launch_bwd<3>(a, st))) return rc;
     if ((rc = launch_bwd<2>(a, st))) return rc;
     launches += 2;
-    rc = cednerf_hashgrid_bwd_table_lm(xn, 3, n, &desc->levels, (const uint8_t*)work + wl.dy_lm, g_table, stream);
+    rc = cednerf_hashgrid_bwd_table_lm_dev(xn, 3, n, n_device, &desc->levels, (const uint8_t*)work + wl.dy_lm, g_table, stream);
     if (rc) return rc;
     // g_table is complete here: with phase == 1 the caller can start its all-reduce while phase 2 runs
     if (phase == 1) return cednerf_check_launch("cednerf_field_train_bwd", launches);
@@ -891,7 +902,8 @@ CEDNERF_EXPORT int cednerf_field_train_bwd(const int64_t* ray_indices, const flo
     ++launches;
   }
   hashgrid_bwd_input_lm_kernel<<<cednerf_blocks(n, 256), 256, 0, st>>>(
-      xn, n, (const __half*)table_f16, desc->levels, reinterpret_cast<const __half2*>((const uint8_t*)work + wl.dy_lm), g_xn);
+      xn, n, (const __half*)table_f16, desc->levels, reinterpret_cast<const __half2*>((const uint8_t*)work + wl.dy_lm), g_xn,
+      n_device);
   if ((rc = launch_bwd<1>(a, st))) return rc;
   return cednerf_check_launch("cednerf_field_train_bwd", launches + 2);
 }

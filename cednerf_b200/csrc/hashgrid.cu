@@ -186,9 +186,17 @@ struct LevelList {
 template <typename GradT, bool LEVEL_MAJOR, bool CACHED>
 __global__ void __launch_bounds__(256)
 hashgrid_bwd_table_kernel(const float* __restrict__ x, int x_stride, int64_t n, CednerfGridLevels lv, LevelList list,
-                          const GradT* __restrict__ dy, int dy_stride, float* __restrict__ g_table, int64_t chunk) {
+                          const GradT* __restrict__ dy, int dy_stride, float* __restrict__ g_table, int64_t chunk,
+                          const int64_t* __restrict__ n_dev) {
   __shared__ uint32_t tags[CACHED ? TG_SLOTS : 1];
   __shared__ float vals[CACHED ? 2 * TG_SLOTS : 1];
+  // n: capacity of the sample arrays (and the level stride of a level-major dy); n_dev (nullable): live sample count
+  int64_t n_live = n;
+  if (n_dev) {
+    const int64_t v = *n_dev;
+    n_live = v < n ? v : n;
+  }
+  if ((int64_t)blockIdx.x * chunk >= n_live) return;
   const int l = list.id[blockIdx.y];
   const int lane = threadIdx.x & 31;
   const uint32_t res = lv.res[l], size = lv.size[l], off = lv.offset[l];
@@ -212,7 +220,7 @@ hashgrid_bwd_table_kernel(const float* __restrict__ x, int x_stride, int64_t n, 
     }
     atomicAdd(t2 + i, make_float2(a, b));
   };
-  const int64_t begin = (int64_t)blockIdx.x * chunk, end = begin + chunk < n ? begin + chunk : n;
+  const int64_t begin = (int64_t)blockIdx.x * chunk, end = begin + chunk < n_live ? begin + chunk : n_live;
   for (int64_t s0 = begin; s0 < end; s0 += blockDim.x) {
     int64_t s = s0 + threadIdx.x;
     const bool active = s < end;
@@ -307,7 +315,7 @@ hashgrid_bwd_table_kernel(const float* __restrict__ x, int x_stride, int64_t n, 
 // small dense levels -> cached pass (long chunks), the others -> direct pass (one block of 256 samples per CTA)
 template <typename GradT, bool LEVEL_MAJOR>
 int launch_table_gradient(const float* x, int x_stride, int64_t n, const CednerfGridLevels& lv, const GradT* dy, int dy_stride,
-                          float* g_table, cudaStream_t st) {
+                          float* g_table, cudaStream_t st, const int64_t* n_dev = nullptr) {
   LevelList cached{}, direct{};
   for (int l = 0; l < lv.n_levels; ++l) {
     // the cache pays where a level has few entries (heavy per-address contention in L2); from 2^20 entries on - hashed
@@ -321,12 +329,12 @@ int launch_table_gradient(const float* x, int x_stride, int64_t n, const Cednerf
     int64_t chunk = ((n + want_ctas - 1) / want_ctas + 255) / 256 * 256;
     if (chunk < 2048) chunk = 2048;
     dim3 grid((unsigned)((n + chunk - 1) / chunk), cached.n);
-    hashgrid_bwd_table_kernel<GradT, LEVEL_MAJOR, true><<<grid, 256, 0, st>>>(x, x_stride, n, lv, cached, dy, dy_stride, g_table, chunk);
+    hashgrid_bwd_table_kernel<GradT, LEVEL_MAJOR, true><<<grid, 256, 0, st>>>(x, x_stride, n, lv, cached, dy, dy_stride, g_table, chunk, n_dev);
     ++launches;
   }
   if (direct.n) {
     dim3 grid(cednerf_blocks(n, 256), direct.n);
-    hashgrid_bwd_table_kernel<GradT, LEVEL_MAJOR, false><<<grid, 256, 0, st>>>(x, x_stride, n, lv, direct, dy, dy_stride, g_table, 256);
+    hashgrid_bwd_table_kernel<GradT, LEVEL_MAJOR, false><<<grid, 256, 0, st>>>(x, x_stride, n, lv, direct, dy, dy_stride, g_table, 256, n_dev);
     ++launches;
   }
   return launches;
@@ -407,6 +415,18 @@ CEDNERF_EXPORT int cednerf_hashgrid_bwd_table_lm(const float* x, int x_stride, i
   if (n == 0) return 0;
   const int launches = launch_table_gradient<__half, true>(x, x_stride, n, *levels, (const __half*)dy_lm_f16, 0, g_table,
                                                            (cudaStream_t)stream);
+  return cednerf_check_launch("cednerf_hashgrid_bwd_table_lm", launches);
+}
+
+// the same with the live sample count on the device (n = capacity = level stride of dy_lm); used by the fused backward
+extern "C" int cednerf_hashgrid_bwd_table_lm_dev(const float* x, int x_stride, int64_t n, const int64_t* n_device,
+                                                 const CednerfGridLevels* levels, const void* dy_lm_f16, float* g_table,
+                                                 void* stream) {
+  CEDNERF_REQUIRE(check_levels(levels), "bad level table");
+  CEDNERF_REQUIRE(n >= 0 && x_stride >= 3 && dy_lm_f16 && g_table, "bad arguments");
+  if (n == 0) return 0;
+  const int launches = launch_table_gradient<__half, true>(x, x_stride, n, *levels, (const __half*)dy_lm_f16, 0, g_table,
+                                                           (cudaStream_t)stream, n_device);
   return cednerf_check_launch("cednerf_hashgrid_bwd_table_lm", launches);
 }
 

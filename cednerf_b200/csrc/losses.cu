@@ -14,7 +14,8 @@ struct LossArgs {
   const float* weights;  // [S]   rendering weights (constants of the loss: the reference detaches them)
   const int64_t* ridx;   // [S]
   const float* latent;   // [R,C] per-ray latent losses (nullable)
-  int64_t R, S;
+  int64_t R, S;          // S: capacity of the per-sample arrays
+  const int64_t* S_dev;  // nullable: live sample count on the device
   int C;
   float w_entropy, w_rgbper;
 };
@@ -51,8 +52,13 @@ __global__ void __launch_bounds__(256) loss_fwd_kernel(LossArgs a, double* __res
       s_ent += (double)(-(t * logf(t) + (1.f - t) * logf(1.f - t)));
     }
   }
+  int64_t S = a.S;
+  if (a.S_dev) {
+    const int64_t v = *a.S_dev;
+    S = v < S ? v : S;
+  }
   if (a.rgbs)
-    for (int64_t s = t0; s < a.S; s += stride) {
+    for (int64_t s = t0; s < S; s += stride) {
       const int64_t r = a.ridx[s];
       float q = 0.f;
 #pragma unroll
@@ -98,8 +104,13 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(LossArgs a, const float* 
       d_acc[r] = (t > 1e-6f && t < 1.f - 1e-6f) ? k_ent * (logf(t) - logf(1.f - t)) : 0.f;
     }
   }
+  int64_t S = a.S;
+  if (a.S_dev) {
+    const int64_t v = *a.S_dev;
+    S = v < S ? v : S;
+  }
   if (d_rgbs)
-    for (int64_t s = t0; s < a.S; s += stride) {
+    for (int64_t s = t0; s < S; s += stride) {
       const int64_t r = a.ridx[s];
       const float w = k_per * a.weights[s];
 #pragma unroll
@@ -125,13 +136,14 @@ unsigned loss_grid(const LossArgs& a) {
 CEDNERF_EXPORT int cednerf_training_loss_fwd(const float* rgb, const float* acc, const float* pixels, int64_t n_rays,
                                              const float* rgbs, const float* weights, const int64_t* ray_indices,
                                              int64_t n_samples, const float* latent, int n_latent, float w_entropy,
-                                             float w_rgbper, double* sums, float* loss, void* stream) {
+                                             float w_rgbper, double* sums, float* loss, const int64_t* n_device,
+                                             void* stream) {
   CEDNERF_REQUIRE(rgb && pixels && n_rays > 0 && sums && loss, "bad arguments");
   CEDNERF_REQUIRE(!rgbs || (weights && ray_indices && n_samples >= 0), "per-sample term needs weights and ray_indices");
   CEDNERF_REQUIRE(!latent || n_latent > 0, "latent term needs its channel count");
   cudaStream_t st = (cudaStream_t)stream;
   LossArgs a{rgb, acc, pixels, n_samples > 0 ? rgbs : nullptr, weights, ray_indices, latent, n_rays,
-             rgbs ? n_samples : 0, n_latent, w_entropy, w_rgbper};
+             rgbs ? n_samples : 0, n_device, n_latent, w_entropy, w_rgbper};
   cudaMemsetAsync(sums, 0, 4 * sizeof(double), st);
   loss_fwd_kernel<<<loss_grid(a), 256, 0, st>>>(a, sums);
   LossArgs fin = a;
@@ -145,12 +157,12 @@ CEDNERF_EXPORT int cednerf_training_loss_bwd(const float* g_loss, const float* r
                                              int64_t n_rays, const float* rgbs, const float* weights,
                                              const int64_t* ray_indices, int64_t n_samples, int n_latent, float w_entropy,
                                              float w_rgbper, float* d_rgb, float* d_acc, float* d_rgbs, float* d_latent,
-                                             void* stream) {
+                                             const int64_t* n_device, void* stream) {
   CEDNERF_REQUIRE(g_loss && rgb && pixels && n_rays > 0, "bad arguments");
   CEDNERF_REQUIRE(!d_acc || acc, "d_acc needs acc");
   CEDNERF_REQUIRE(!d_rgbs || (rgbs && weights && ray_indices), "d_rgbs needs the per-sample inputs");
   LossArgs a{rgb, acc, pixels, rgbs, weights, ray_indices, d_latent ? rgb : nullptr, n_rays, d_rgbs ? n_samples : 0,
-             n_latent > 0 ? n_latent : 1, w_entropy, w_rgbper};
+             n_device, n_latent > 0 ? n_latent : 1, w_entropy, w_rgbper};
   loss_bwd_kernel<<<loss_grid(a), 256, 0, (cudaStream_t)stream>>>(a, g_loss, d_rgb, d_acc, n_samples > 0 ? d_rgbs : nullptr,
                                                                   d_latent);
   return cednerf_check_launch("cednerf_training_loss_bwd");

@@ -335,18 +335,30 @@ __global__ void __launch_bounds__(128)
 march_fill_runs_kernel(int64_t n_rays, const int64_t* __restrict__ sm_starts, const float* __restrict__ run_t,
                        const int32_t* __restrict__ run_n, const int32_t* __restrict__ n_runs, int run_cap,
                        float step_size, float cone, float* __restrict__ t_starts, float* __restrict__ t_ends,
-                       int64_t* __restrict__ ray_indices, uint8_t* __restrict__ overflow) {
+                       int64_t* __restrict__ ray_indices, uint8_t* __restrict__ overflow,
+                       const int32_t* __restrict__ capped_counts) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_rays) return;
   const int runs = n_runs[r];
-  const bool over = runs > run_cap;
+  bool over = runs > run_cap;
+  int64_t k = sm_starts[r];
+  // capped mode (sm_starts = offsets [n_rays + 1] clamped to the capacity of the packed buffers, capped_counts = the
+  // unclamped per-ray counts): nothing is written at or beyond the clamped end of the ray's range
+  const int64_t k_end = capped_counts ? sm_starts[r + 1] : INT64_MAX;
+  if (capped_counts && over && k_end - k != (int64_t)capped_counts[r]) {
+    // a truncated ray cannot take the full-march fallback (it writes its whole range): leave harmless samples
+    for (; k < k_end; ++k) t_starts[k] = 0.0f, t_ends[k] = 0.0f, ray_indices[k] = r;
+    over = false;
+    overflow[r] = 0;
+    return;
+  }
   overflow[r] = (uint8_t)over;
   if (over) return;
-  int64_t k = sm_starts[r];
   auto next = [&](float t) { return (step_size <= 0.0f) ? t : t + step_dt(t, cone, step_size); };
   for (int j = 0; j < runs; ++j) {
     float t = run_t[r * run_cap + j];
-    const int cnt = run_n[r * run_cap + j];
+    int cnt = run_n[r * run_cap + j];
+    if ((int64_t)cnt > k_end - k) cnt = (int)(k_end - k);
     int i = 0;
     // A ray's samples are consecutive in the packed arrays but neighbouring lanes write ~one ray length apart: scalar
     // stores put 4 useful bytes into every 32-byte sector they touch.  Four samples at a time as 16-byte stores (once k
@@ -475,6 +487,35 @@ scan_apply_kernel(const int32_t* __restrict__ counts, int64_t n, const int64_t* 
       }
     }
     off += c[k];
+  }
+}
+
+// offsets[i] = min(exclusive prefix sum, capacity) for i in [0, n]; totals = {min(total, capacity), total}
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_apply_capped_kernel(const int32_t* __restrict__ counts, int64_t n, const int64_t* __restrict__ tile_offsets,
+                         int64_t capacity, int64_t* __restrict__ offsets, const int64_t* __restrict__ total_raw,
+                         int64_t* __restrict__ totals) {
+  __shared__ int64_t smem[SCAN_THREADS / 32];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  int32_t c[SCAN_ITEMS];
+  int64_t s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    c[k] = base + k < n ? counts[base + k] : 0;
+    s += c[k];
+  }
+  int64_t total;
+  int64_t off = tile_offsets[blockIdx.x] + block_excl_scan(s, &total, smem);
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    if (base + k < n) offsets[base + k] = off < capacity ? off : capacity;
+    off += c[k];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const int64_t t = *total_raw;
+    offsets[n] = t < capacity ? t : capacity;
+    totals[0] = t < capacity ? t : capacity;
+    totals[1] = t;
   }
 }
 
@@ -624,7 +665,63 @@ __global__ void ray_coherence_keys_kernel(const float* __restrict__ rays_d, int6
   keys[r] = (int32_t)(spread(qu) | (spread(qv) << 1));
 }
 
+// ---- bucket order by coherence key: histogram -> scan -> scatter (order inside a bucket is irrelevant: the permutation
+// only decides which rays share a warp, every output stays indexed by ray) -------------------------------------------
+#define ORDER_BINS 16384   // the top 14 bits of the 20-bit key: 128 x 128 direction cells
+__global__ void order_hist_kernel(const int32_t* __restrict__ keys, int64_t n, uint32_t* __restrict__ hist) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicAdd(hist + (((uint32_t)keys[i]) >> 6), 1u);
+}
+__global__ void __launch_bounds__(1024) order_scan_kernel(uint32_t* __restrict__ hist) {  // exclusive scan of 16384 bins
+  __shared__ uint32_t warp_tot[32];
+  uint32_t v[16], s = 0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = hist[threadIdx.x * 16 + k], s += v[k];
+  uint32_t incl = s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = warp_tot[lane], wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    warp_tot[lane] = wi - w;
+  }
+  __syncthreads();
+  uint32_t off = warp_tot[warp] + incl - s;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) hist[threadIdx.x * 16 + k] = off, off += v[k];
+}
+__global__ void order_scatter_kernel(const int32_t* __restrict__ keys, int64_t n, uint32_t* __restrict__ cursor,
+                                     int32_t* __restrict__ order) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) order[atomicAdd(cursor + (((uint32_t)keys[i]) >> 6), 1u)] = (int32_t)i;
+}
+
 }  // namespace
+
+// order [n] = a permutation of the rays that groups equal leading key bits (cednerf_ray_coherence_keys): the ray_order
+// argument of cednerf_march.  workspace: 64 KB.  Replaces a general radix sort (4 launches, ~0.1 ms on 2^18 keys).
+CEDNERF_EXPORT int cednerf_ray_coherence_order(const int32_t* keys, int64_t n_rays, int32_t* order, void* workspace,
+                                               void* stream) {
+  CEDNERF_REQUIRE(n_rays >= 0 && n_rays < (1ll << 31) && keys && order && workspace, "bad arguments");
+  if (n_rays == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint32_t* hist = (uint32_t*)workspace;
+  cudaMemsetAsync(hist, 0, ORDER_BINS * sizeof(uint32_t), st);
+  order_hist_kernel<<<cednerf_blocks(n_rays, 256), 256, 0, st>>>(keys, n_rays, hist);
+  order_scan_kernel<<<1, 1024, 0, st>>>(hist);
+  order_scatter_kernel<<<cednerf_blocks(n_rays, 256), 256, 0, st>>>(keys, n_rays, hist, order);
+  return cednerf_check_launch("cednerf_ray_coherence_order", 3);
+}
 
 // keys[r] = coherence key of ray r (sort by it, pass the permutation to cednerf_march as ray_order)
 CEDNERF_EXPORT int cednerf_ray_coherence_keys(const float* rays_d, int64_t n_rays, int32_t* keys, void* stream) {
@@ -677,8 +774,28 @@ CEDNERF_EXPORT int cednerf_march_fill_runs(int64_t n_rays, const int64_t* sm_sta
                   "packed outputs must be 16-byte aligned");
   if (n_rays == 0) return 0;
   march_fill_runs_kernel<<<cednerf_blocks(n_rays, 128), 128, 0, (cudaStream_t)stream>>>(
-      n_rays, sm_starts, run_t, run_n, n_runs, run_cap, step_size, cone_angle, t_starts, t_ends, ray_indices, overflow);
+      n_rays, sm_starts, run_t, run_n, n_runs, run_cap, step_size, cone_angle, t_starts, t_ends, ray_indices, overflow,
+      nullptr);
   return cednerf_check_launch("cednerf_march_fill_runs");
+}
+
+// The same fill for buffers of a fixed capacity (no host read of the sample total): `offsets` [n_rays + 1] comes from
+// cednerf_exclusive_scan_capped and `n_samples` holds the unclamped per-ray counts; samples at or beyond the capacity are
+// dropped (totals[1] > totals[0] of the scan tells the caller).  Rays flagged in `overflow` go through
+// cednerf_march(fill = 1, rays_mask = overflow, sm_starts = offsets) as before; a ray that is both truncated and over
+// the run limit gets zero-length samples instead.
+CEDNERF_EXPORT int cednerf_march_fill_runs_capped(int64_t n_rays, const int64_t* offsets, const int32_t* n_samples,
+                                                  const float* run_t, const int32_t* run_n, const int32_t* n_runs,
+                                                  int run_cap, float step_size, float cone_angle, float* t_starts,
+                                                  float* t_ends, int64_t* ray_indices, uint8_t* overflow, void* stream) {
+  CEDNERF_REQUIRE(n_rays >= 0 && run_cap > 0 && step_size > 0.0f && offsets && n_samples, "bad arguments");
+  CEDNERF_REQUIRE((((uintptr_t)t_starts | (uintptr_t)t_ends | (uintptr_t)ray_indices) & 15) == 0,
+                  "packed outputs must be 16-byte aligned");
+  if (n_rays == 0) return 0;
+  march_fill_runs_kernel<<<cednerf_blocks(n_rays, 128), 128, 0, (cudaStream_t)stream>>>(
+      n_rays, offsets, run_t, run_n, n_runs, run_cap, step_size, cone_angle, t_starts, t_ends, ray_indices, overflow,
+      n_samples);
+  return cednerf_check_launch("cednerf_march_fill_runs_capped");
 }
 
 CEDNERF_EXPORT int64_t cednerf_scan_workspace_bytes(int64_t n) {
@@ -702,4 +819,25 @@ CEDNERF_EXPORT int cednerf_exclusive_scan(const int32_t* counts, int64_t n, int6
   scan_tile_offsets_kernel<<<1, SCAN_THREADS, 0, st>>>(tile_sums, tiles, total);
   scan_apply_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(counts, n, tile_sums, starts, packed_info);
   return cednerf_check_launch("cednerf_exclusive_scan", 3);
+}
+
+// The scan for fixed-capacity buffers: offsets int64[n + 1] = min(exclusive prefix sums, capacity) (offsets[n] = the
+// clamped total), totals int64[2] = {min(total, capacity), total}.  Nothing has to be read back by the host: kernels
+// downstream take their live count from totals[0] and per-ray ranges from `offsets`.
+CEDNERF_EXPORT int cednerf_exclusive_scan_capped(const int32_t* counts, int64_t n, int64_t capacity, int64_t* offsets,
+                                                 int64_t* totals, void* workspace, void* stream) {
+  CEDNERF_REQUIRE(n >= 0 && capacity >= 0 && offsets && totals && workspace, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) {
+    cudaMemsetAsync(offsets, 0, 8, st);
+    cudaMemsetAsync(totals, 0, 16, st);
+    return 0;
+  }
+  const int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  int64_t* tile_sums = (int64_t*)workspace;
+  scan_tile_sums_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(counts, n, tile_sums);
+  scan_tile_offsets_kernel<<<1, SCAN_THREADS, 0, st>>>(tile_sums, tiles, totals + 1);
+  scan_apply_capped_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(counts, n, tile_sums, capacity, offsets, totals + 1,
+                                                                      totals);
+  return cednerf_check_launch("cednerf_exclusive_scan_capped", 3);
 }

@@ -12,14 +12,14 @@ from __future__ import annotations
 import torch
 
 from ._lib import call, ptr, stream
-from .ops import _f32c, _sempty
+from .ops import _f32c, _sempty, counts_of
 
 F32, F64, I64 = torch.float32, torch.float64, torch.int64
 
 
 class TrainingLossFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, rgb, acc, pixels, rgbs, weights, ray_indices, latent, w_entropy, w_rgbper):
+    def forward(ctx, rgb, acc, pixels, rgbs, weights, ray_indices, latent, w_entropy, w_rgbper, n_dev=None):
         rgb, pixels = _f32c(rgb), _f32c(pixels)
         n_rays, dev = rgb.shape[0], rgb.device
         acc_c = None if acc is None else _f32c(acc).view(-1)
@@ -32,18 +32,19 @@ class TrainingLossFunction(torch.autograd.Function):
         sums = torch.empty(4, dtype=F64, device=dev)
         loss = torch.empty(1, dtype=F32, device=dev)
         call("cednerf_training_loss_fwd", ptr(rgb), ptr(acc_c), ptr(pixels), n_rays, ptr(rgbs_c), ptr(w_c), ptr(ridx), n_s,
-             ptr(lat), n_lat, float(w_entropy), float(w_rgbper), ptr(sums), ptr(loss), stream())
+             ptr(lat), n_lat, float(w_entropy), float(w_rgbper), ptr(sums), ptr(loss), ptr(n_dev), stream())
         keep = [t if t is not None else rgb for t in (acc_c, rgbs_c, w_c, ridx)]
         ctx.save_for_backward(rgb, pixels, *keep)
         ctx.flags = (acc_c is not None, rgbs_c is not None, n_lat, n_s, float(w_entropy), float(w_rgbper))
         ctx.shapes = (None if acc is None else acc.shape, None if latent is None else latent.shape)
+        ctx.n_dev = n_dev
         ctx.set_materialize_grads(False)
         return loss.view(())
 
     @staticmethod
     def backward(ctx, g):
         if g is None:
-            return (None,) * 9
+            return (None,) * 10
         rgb, pixels, acc_c, rgbs_c, w_c, ridx = ctx.saved_tensors
         has_acc, has_rgbs, n_lat, n_s, w_entropy, w_rgbper = ctx.flags
         n_rays, dev = rgb.shape[0], rgb.device
@@ -55,10 +56,10 @@ class TrainingLossFunction(torch.autograd.Function):
         d_lat = torch.empty(n_rays, n_lat, device=dev) if (n_lat and need[6]) else None
         call("cednerf_training_loss_bwd", ptr(g), ptr(rgb), ptr(acc_c) if has_acc else None, ptr(pixels), n_rays,
              ptr(rgbs_c) if has_rgbs else None, ptr(w_c) if has_rgbs else None, ptr(ridx) if has_rgbs else None, n_s,
-             n_lat, w_entropy, w_rgbper, ptr(d_rgb), ptr(d_acc), ptr(d_rgbs), ptr(d_lat), stream())
+             n_lat, w_entropy, w_rgbper, ptr(d_rgb), ptr(d_acc), ptr(d_rgbs), ptr(d_lat), ptr(ctx.n_dev), stream())
         acc_shape, lat_shape = ctx.shapes
         return (d_rgb, None if d_acc is None else d_acc.view(acc_shape), None, d_rgbs, None, None,
-                None if d_lat is None else d_lat.view(lat_shape), None, None)
+                None if d_lat is None else d_lat.view(lat_shape), None, None, None)
 
 
 def training_loss(rgb, acc, pixels, extras, acc_entropy_loss: bool = True, weight_rgbper: bool = True,
@@ -68,6 +69,7 @@ def training_loss(rgb, acc, pixels, extras, acc_entropy_loss: bool = True, weigh
         raise ValueError("training_loss fuses the one-chunk case of a training batch (render_image in training mode)")
     ex = extras[0]
     latent = ex.get("latent_losses") if use_feat_predict else None
+    counts = counts_of(ex["ray_indices"])   # capacity-sized sample set: the live count stays on the device
     return TrainingLossFunction.apply(rgb, acc if acc_entropy_loss else None, pixels,
                                       ex["rgbs"] if weight_rgbper else None, ex["weights"].detach(), ex["ray_indices"],
-                                      latent, 1e-3, 1e-3)
+                                      latent, 1e-3, 1e-3, None if counts is None else counts[1])

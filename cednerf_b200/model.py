@@ -124,7 +124,8 @@ class DNGPradianceField(torch.nn.Module):
         sigma, rgb, latent, selector, move = ops.FieldTrainFunction.apply(
             self.xyz_wrap.network.params, self.mlp_base.params, self.mlp_head.params,
             None if f4 is None else f4.params, self.hash_encoder.params.view(-1, 2), self._field_desc(), images,
-            self.hash_encoder.table_f16(), ridx, t0, t1, rays_o, rays_d, timestamps, t_stride, f4 is not None)
+            self.hash_encoder.table_f16(), ridx, t0, t1, rays_o, rays_d, timestamps, t_stride, f4 is not None,
+            None if ops.counts_of(ridx) is None else ops.counts_of(ridx)[1])
         io = {"move": torch.linalg.norm(move, dim=-1) if (self.use_time_embedding and self.use_time_attenuation) else move}
         if self.use_feat_predict:
             io["selector"], io["latent_losses"] = selector, latent

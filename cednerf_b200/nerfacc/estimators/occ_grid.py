@@ -30,6 +30,7 @@ class OccGridEstimator(torch.nn.Module):
         self.register_buffer("grid_indices", torch.arange(self.cells_per_lvl), persistent=False)
         self._occ_mean_key, self._occ_mean = None, 0.0
         self._may_have_invisible, self._occs_seen = False, None  # occs = -1 cells exist (mark_invisible_cells, checkpoints)
+        self._cap_state, self.dropped_samples = {}, 0  # sampling(..., device_counts=True)
 
     def _load_from_state_dict(self, *args, **kwargs):
         self._occs_seen = None  # contents replaced in place: look again at the next update
@@ -62,7 +63,7 @@ class OccGridEstimator(torch.nn.Module):
             if stratified:
                 u = torch.rand(n, device=rays_o.device) if jitter is None else jitter.to(rays_o.device).float()
                 near = near + u * render_step_size
-        mi = ops.MarchInputs(rays_o, rays_d, occupancy_bits(self.binaries), self.aabbs, int(self.resolution[0]),
+        mi = ops.MarchInputs(rays_o, rays_d, occupancy_bits(self.binaries), self.aabbs, int(self.binaries.shape[1]),
                              near, far, float(near_plane), float(far_plane), render_step_size, cone_angle)
         if stratified and n >= 65536:  # a large batch of (random) training rays
             mi.sort_for_coherence()
@@ -74,15 +75,90 @@ class OccGridEstimator(torch.nn.Module):
             ridx, t0, t1, _ = mi.fill_packed(starts, int(total.item()))
         return ridx, t0, t1, packed
 
+    # ---- capacities of the sync-free path ------------------------------------------------------------------------
+    # The sample totals of a batch are copied to pinned host memory asynchronously and looked at when a LATER batch is
+    # sampled: a capacity is 1.25 x the newest total that has arrived.  A batch that outgrows it loses its last samples
+    # (totals[1] > totals[0]); `dropped_samples` counts them and the next capacity already covers the new total.
+    _HEADROOM = 1.25
+
+    def _capacity(self, kind: str):
+        st = self._cap_state.setdefault(kind, {"last": None, "pending": [], "ring": [], "next": 0})
+        while st["pending"] and st["pending"][0][0].query():
+            _, host, cap = st["pending"].pop(0)
+            raw = int(host[1])
+            st["last"] = raw
+            if raw > cap:
+                self.dropped_samples += raw - cap
+        if st["last"] is None:
+            return None
+        return ops._sticky_capacity(max(int(st["last"] * self._HEADROOM), 65536))
+
+    def _note_totals(self, kind: str, totals: torch.Tensor, cap: int):
+        st = self._cap_state[kind]
+        if not st["ring"]:
+            st["ring"] = [torch.empty(2, dtype=torch.int64).pin_memory() for _ in range(32)]
+        if len(st["pending"]) >= len(st["ring"]):   # the host ran 32 batches ahead of the device: wait for the oldest
+            st["pending"][0][0].synchronize()
+            self._capacity(kind)
+        host = st["ring"][st["next"] % len(st["ring"])]
+        st["next"] += 1
+        host.copy_(totals, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        st["pending"].append((ev, host, cap))
+
+    def _seed_capacity(self, kind: str, total: int):
+        self._cap_state.setdefault(kind, {"last": None, "pending": [], "ring": [], "next": 0})["last"] = int(total)
+
+    @torch.no_grad()
+    def _sampling_device_counts(self, rays_o, rays_d, sigma_fn, near_plane, far_plane, render_step_size, early_stop_eps,
+                                alpha_thre, cone_angle, jitter):
+        """.sampling for a stratified training batch without any host read: capacity-sized outputs whose ray_indices
+        carry (offsets, live count) - see ops.counts_of.  None when no capacity is known yet (first batch)."""
+        cap_m, cap_v = self._capacity("marched"), self._capacity("visible")
+        if cap_m is None or cap_v is None or render_step_size <= 0:
+            return None
+        n = rays_o.shape[0]
+        u = torch.rand(n, device=rays_o.device) if jitter is None else jitter.to(rays_o.device).float()
+        near = torch.full((n,), float(near_plane), device=rays_o.device) + u * render_step_size
+        far = torch.full((n,), float(far_plane), device=rays_o.device)
+        mi = ops.MarchInputs(rays_o, rays_d, occupancy_bits(self.binaries), self.aabbs, int(self.binaries.shape[1]),
+                             near, far, float(near_plane), float(far_plane), render_step_size, cone_angle)
+        if n >= 65536:
+            mi.sort_for_coherence()
+        _, n_sm, _ = mi.count(record_runs=True)
+        offsets, totals = ops.exclusive_scan_capped(n_sm, cap_m)
+        ridx, t0, t1 = mi.fill_packed_capped(offsets, n_sm, cap_m)
+        self._note_totals("marched", totals, cap_m)
+        ridx._cednerf_counts = (offsets, totals[0:1])
+        sigmas = sigma_fn(t0, t1, ridx)
+        assert sigmas.shape == t0.shape, f"sigmas must have shape {tuple(t0.shape)}"
+        k_idx, k_t0, k_t1, k_off, k_tot = ops.visible_samples_capped(t0, t1, sigmas, offsets, n, early_stop_eps,
+                                                                     min(alpha_thre, self._occs_mean()), cap_v)
+        self._note_totals("visible", k_tot, cap_v)
+        k_idx._cednerf_counts = (k_off, k_tot[0:1])
+        return k_idx, k_t0, k_t1
+
     @torch.no_grad()
     def sampling(self, rays_o, rays_d, sigma_fn: Optional[Callable] = None, alpha_fn: Optional[Callable] = None,
                  near_plane: float = 0.0, far_plane: float = 1e10, t_min=None, t_max=None,
                  render_step_size: float = 1e-3, early_stop_eps: float = 1e-4, alpha_thre: float = 0.0,
-                 stratified: bool = False, cone_angle: float = 0.0, jitter: Optional[torch.Tensor] = None):
+                 stratified: bool = False, cone_angle: float = 0.0, jitter: Optional[torch.Tensor] = None,
+                 device_counts: bool = False):
+        """device_counts=True (stratified training batches with a sigma_fn): no host read - see render_image."""
         if alpha_fn is not None:
             raise NotImplementedError("alpha_fn is not used by the reference")
+        device_counts = (device_counts and stratified and sigma_fn is not None and t_min is None and t_max is None
+                         and (alpha_thre > 0 or early_stop_eps > 0))
+        if device_counts:
+            out = self._sampling_device_counts(rays_o, rays_d, sigma_fn, near_plane, far_plane, render_step_size,
+                                               early_stop_eps, alpha_thre, cone_angle, jitter)
+            if out is not None:
+                return out
         ridx, t0, t1, packed = self.march(rays_o, rays_d, near_plane, far_plane, render_step_size, cone_angle,
                                           stratified, jitter, t_min, t_max)
+        if device_counts:
+            self._seed_capacity("marched", t0.numel())
         if (alpha_thre > 0 or early_stop_eps > 0) and sigma_fn is not None:
             alpha_thre = min(alpha_thre, self._occs_mean())
             if t0.numel():
@@ -90,6 +166,8 @@ class OccGridEstimator(torch.nn.Module):
                 assert sigmas.shape == t0.shape, f"sigmas must have shape {tuple(t0.shape)}"
                 ridx, t0, t1 = ops.visible_samples(t0, t1, sigmas, ops.offsets_from_packed(packed), rays_o.shape[0],
                                                    early_stop_eps, alpha_thre)
+        if device_counts:
+            self._seed_capacity("visible", t0.numel())
         return ridx, t0, t1
 
     @torch.no_grad()
@@ -102,7 +180,7 @@ class OccGridEstimator(torch.nn.Module):
         dev = self.device
         K, c2w = K.to(dev, torch.float32).contiguous(), c2w.to(dev, torch.float32).contiguous()
         ops.call("cednerf_occ_mark_invisible", ops.ptr(K), K.shape[0], ops.ptr(c2w), c2w.shape[0], c2w.shape[1],
-                 ops.ptr(self.aabbs), self.levels, int(self.resolution[0]), int(width), int(height), float(near_plane),
+                 ops.ptr(self.aabbs), self.levels, int(self.binaries.shape[1]), int(width), int(height), float(near_plane),
                  ops.ptr(self.occs), ops.stream())
         self._may_have_invisible = True
         self.occs.add_(0)  # bump the version: `occs.mean()` is cached per version for `.sampling`

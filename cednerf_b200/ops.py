@@ -75,6 +75,23 @@ def exclusive_scan(counts: torch.Tensor, want_packed: bool = True):
     return starts, packed, total
 
 
+def counts_of(t: Optional[torch.Tensor]):
+    """(offsets int64 [n_rays + 1], n_dev int64 [1]) attached to the ray_indices of a capacity-sized packed sample set
+    (OccGridEstimator.sampling(..., device_counts=True)), else None.  Only the first n_dev[0] rows of such tensors are
+    live; every kernel downstream reads the count from the device, so the host never waits for it."""
+    return getattr(t, "_cednerf_counts", None) if t is not None else None
+
+
+def exclusive_scan_capped(counts: torch.Tensor, capacity: int):
+    """int32 counts -> (offsets int64 [n + 1] clamped to `capacity`, totals int64 [2] = (clamped, raw)); device only."""
+    n, dev = counts.numel(), counts.device
+    offsets = torch.empty(n + 1, dtype=I64, device=dev)
+    totals = torch.empty(2, dtype=I64, device=dev)
+    ws = torch.empty(max(int(_lib.load().cednerf_scan_workspace_bytes(n)) // 8, 1), dtype=I64, device=dev)
+    call("cednerf_exclusive_scan_capped", ptr(counts), n, int(capacity), ptr(offsets), ptr(totals), ptr(ws), stream())
+    return offsets, totals
+
+
 class MarchInputs:
     """Argument bundle shared by the count and fill passes."""
 
@@ -100,7 +117,9 @@ class MarchInputs:
         indexed by ray, so nothing downstream sees the permutation."""
         keys = torch.empty(self.n, dtype=I32, device=self.o.device)
         call("cednerf_ray_coherence_keys", ptr(self.d), self.n, ptr(keys), stream())
-        self.order = torch.sort(keys)[1].to(I32)
+        self.order = torch.empty(self.n, dtype=I32, device=self.o.device)
+        ws = torch.empty(16384, dtype=I32, device=self.o.device)
+        call("cednerf_ray_coherence_order", ptr(keys), self.n, ptr(self.order), ptr(ws), stream())
 
     def _common(self, fill):
         return (fill, ptr(self.o), ptr(self.d), self.n, ptr(self.bits), ptr(self.aabbs), self.nl, self.res,
@@ -137,6 +156,23 @@ class MarchInputs:
         # overflow is 0 for rays the caller masked out (their run count is 0), so it can stand in as the ray mask
         user_mask, self.mask = self.mask, overflow
         call("cednerf_march", *self._common(1), None, ptr(sm_starts), None, None, None, None, None, None, None,
+             ptr(t0), ptr(t1), ptr(ridx), None, None, None, None, None, None, 0, None, stream())
+        self.mask = user_mask
+        return ridx, t0, t1
+
+    def fill_packed_capped(self, offsets, n_sm, capacity):
+        """fill_packed_from_runs into buffers of `capacity` samples: no host read of the total (offsets from
+        exclusive_scan_capped); samples beyond the capacity are dropped."""
+        dev = self.o.device
+        t0 = torch.empty(capacity, device=dev)
+        t1 = torch.empty(capacity, device=dev)
+        ridx = torch.empty(capacity, dtype=I64, device=dev)
+        overflow = torch.empty(self.n, dtype=torch.bool, device=dev)
+        rt, rn, nr = self.runs
+        call("cednerf_march_fill_runs_capped", self.n, ptr(offsets), ptr(n_sm), ptr(rt), ptr(rn), ptr(nr), self.RUN_CAP,
+             self.step, self.cone, ptr(t0), ptr(t1), ptr(ridx), ptr(overflow), stream())
+        user_mask, self.mask = self.mask, overflow   # rays over the run limit: full-march fill into their (whole) range
+        call("cednerf_march", *self._common(1), None, ptr(offsets), None, None, None, None, None, None, None,
              ptr(t0), ptr(t1), ptr(ridx), None, None, None, None, None, None, 0, None, stream())
         self.mask = user_mask
         return ridx, t0, t1
@@ -447,6 +483,19 @@ def visible_samples(t_starts, t_ends, sigmas, offsets, n_rays, early_stop_eps, a
     return ridx, o0, o1
 
 
+def visible_samples_capped(t_starts, t_ends, sigmas, offsets, n_rays, early_stop_eps, alpha_thre, capacity):
+    """visible_samples without the host read: outputs of `capacity` rows + (out_offsets [n_rays + 1], totals [2])."""
+    t0, t1 = _f32c(t_starts), _f32c(t_ends)
+    keep, counts = visibility_mask(t0, t1, sigmas, offsets, n_rays, early_stop_eps, alpha_thre, want_counts=True)
+    out_offsets, totals = exclusive_scan_capped(counts, capacity)
+    dev = t0.device
+    ridx = torch.empty(capacity, dtype=I64, device=dev)
+    o0, o1 = torch.empty(capacity, device=dev), torch.empty(capacity, device=dev)
+    call("cednerf_compact_samples_capped", ptr(keep), ptr(offsets), ptr(out_offsets), ptr(t0), ptr(t1), int(capacity),
+         n_rays, ptr(ridx), ptr(o0), ptr(o1), stream())
+    return ridx, o0, o1, out_offsets, totals
+
+
 class RenderWeightFunction(torch.autograd.Function):
     """(t_starts, t_ends, sigmas) -> (weights, trans, alphas); gradient flows to sigmas only."""
 
@@ -476,21 +525,21 @@ class RenderWeightFunction(torch.autograd.Function):
 
 class AccumulateFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, weights, values, ray_indices, offsets, n_rays):
+    def forward(ctx, weights, values, ray_indices, offsets, n_rays, n_dev=None):
         w = _f32c(weights)
         v = None if values is None else _f32c(values)
         c = 1 if v is None else v.shape[-1]
         out = torch.empty(n_rays, c, device=w.device)
         call("cednerf_accumulate_fwd", ptr(w), ptr(v), c, ptr(offsets), w.numel(), n_rays, ptr(out), 0, stream())
         ctx.save_for_backward(w, v if v is not None else w, ray_indices)
-        ctx.has_v, ctx.c = v is not None, c
+        ctx.has_v, ctx.c, ctx.n_dev = v is not None, c, n_dev
         ctx.set_materialize_grads(False)
         return out
 
     @staticmethod
     def backward(ctx, g):
         if g is None:
-            return None, None, None, None, None
+            return None, None, None, None, None, None
         w, v, ridx = ctx.saved_tensors
         v = v if ctx.has_v else None
         g = _f32c(g)
@@ -498,8 +547,8 @@ class AccumulateFunction(torch.autograd.Function):
         gv = _sempty(v.shape[0], v.shape[1], device=v.device) if (ctx.has_v and ctx.needs_input_grad[1]) else None
         if gw is not None or gv is not None:
             call("cednerf_accumulate_bwd", ptr(w), ptr(v), ctx.c, ptr(ridx), w.numel(), ptr(g), ptr(gw), ptr(gv),
-                 stream())
-        return gw, gv, None, None, None
+                 ptr(ctx.n_dev), stream())
+        return gw, gv, None, None, None, None
 
 
 def accumulate_inplace(weights, values, offsets, outputs):
@@ -662,7 +711,7 @@ class FieldTrainFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, p1, p2, p3, p4, table, desc, images, table_f16, ridx, t0, t1, rays_o, rays_d, ts, t_stride,
-                want_latent):
+                want_latent, n_dev=None):
         _lib.check_device()
         lib = _lib.load()
         n, dev = t0.numel(), t0.device
@@ -679,10 +728,11 @@ class FieldTrainFunction(torch.autograd.Function):
         saved = torch.empty(max(int(lib.cednerf_field_saved_bytes(ctypes.byref(desc), _sticky_capacity(n))), 16), dtype=U8, device=dev)
         call("cednerf_field_train_fwd", ptr(ridx), ptr(t0), ptr(t1), ptr(rays_o), ptr(rays_d), ptr(ts), int(t_stride), n,
              ptr(images[0]), ptr(images[1]), ptr(images[2]), ptr(images[3]), ptr(table_f16), ctypes.byref(desc),
-             ptr(sigma), ptr(rgb), ptr(latent), ptr(selector), ptr(move), ptr(saved), stream())
+             ptr(sigma), ptr(rgb), ptr(latent), ptr(selector), ptr(move), ptr(saved), ptr(n_dev), stream())
         ctx.save_for_backward(ridx, t0, t1, rays_o, rays_d, ts, sigma, rgb, selector, saved, table_f16, images[0],
                               images[1], images[2], images[3] if images[3] is not None else images[0])
         ctx.desc, ctx.t_stride, ctx.has4 = desc, int(t_stride), images[3] is not None and want_latent
+        ctx.n_dev = n_dev
         ctx.shapes = (p1.shape, p2.shape, p3.shape, None if p4 is None else p4.shape, table.shape)
         ctx.mark_non_differentiable(selector, move)
         ctx.set_materialize_grads(False)
@@ -725,7 +775,7 @@ class FieldTrainFunction(torch.autograd.Function):
                      ctx.t_stride, n, ptr(i1), ptr(i2), ptr(i3), ptr(i4) if ctx.has4 else None, ptr(table_f16),
                      ctypes.byref(ctx.desc), ptr(sigma), ptr(rgb), ptr(selector), ptr(saved), ptr(d_sigma), ptr(d_rgb),
                      ptr(dl), ptr(work), ptr(g1), ptr(g2), ptr(g3), ptr(g4) if dl is not None else None, ptr(gt), phase,
-                     stream())
+                     ptr(ctx.n_dev), stream())
             if phase == 1:
                 hook(gt)  # the 191 MB table gradient is complete: its all-reduce overlaps the rest of the backward
-        return (g1, g2, g3, g4 if dl is not None else None, gt) + (None,) * 11
+        return (g1, g2, g3, g4 if dl is not None else None, gt) + (None,) * 12

@@ -26,7 +26,9 @@ def rendering(t_starts, t_ends, ray_indices, n_rays, rgb_sigma_fn=None, rgb_alph
     assert rgbs.shape[-1] == 3, f"rgbs must have 3 channels, got {tuple(rgbs.shape)}"
     sigmas = sigmas.squeeze(-1)
     assert sigmas.shape == t_starts.shape, f"sigmas must have shape {tuple(t_starts.shape)}"
-    offsets = ops.ray_offsets(ray_indices, n_rays)
+    counts = ops.counts_of(ray_indices)   # capacity-sized sample set (sampling(..., device_counts=True))
+    offsets = ops.ray_offsets(ray_indices, n_rays) if counts is None else counts[0]
+    n_dev = None if counts is None else counts[1]
     colors, opac, depth, weights, trans, alphas = ops.CompositeFunction.apply(
         t_starts, t_ends, sigmas, rgbs, offsets, n_rays, render_bkgd)
     extras = {"weights": weights, "alphas": alphas, "trans": trans, "sigmas": sigmas, "rgbs": rgbs}
@@ -36,7 +38,7 @@ def rendering(t_starts, t_ends, ray_indices, n_rays, rgb_sigma_fn=None, rgb_alph
             # reduce_along_rays(..., weights.detach(), "sum") (cednerf/render.py:105-113) as one segmented launch
             ridx = ray_indices.detach().to(torch.int64).contiguous()
             extras["latent_losses"] = ops.AccumulateFunction.apply(weights.detach(), io["latent_losses"], ridx, offsets,
-                                                                   n_rays)
+                                                                   n_rays, n_dev)
         if "weight_losses" in io:
             wl = F.huber_loss(io["weight_losses"].float(), trans[:, None], reduction="none")
             extras["weight_losses"] = reduce_along_rays(ray_indices, wl * io["selector"][:, None], n_rays,

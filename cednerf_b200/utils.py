@@ -35,8 +35,10 @@ def _field_fns(field, rays, timestamps):
     def fused(t0, t1, ridx, sigma_only):
         """One launch from packed samples: positions, encodings and networks never leave the SM."""
         per_ray = field.training and timestamps.numel() == rays.origins.shape[0]
+        counts = ops.counts_of(ridx)
         return field.fused_query(t0.numel(), packed=(ridx, t0, t1, rays.origins, rays.viewdirs), timestamps=timestamps,
-                                 t_stride=1 if per_ray else 0, sigma_only=sigma_only)
+                                 t_stride=1 if per_ray else 0, sigma_only=sigma_only,
+                                 n_dev=None if counts is None else counts[1])
 
     def can_fuse(t0):
         ok = (not torch.is_grad_enabled()) and t0.numel() > 0 and getattr(field, "fused_supported", lambda: False)()
@@ -65,9 +67,14 @@ def _field_fns(field, rays, timestamps):
 
 def render_image(radiance_field, estimator, rays, near_plane=0.0, far_plane=1e10, render_step_size=1e-3,
                  render_bkgd=None, cone_angle=0.0, alpha_thre=0.0, test_chunk_size=8192, timestamps=None,
-                 jitter=None):
+                 jitter=None, device_counts=False):
     """-> (rgb, acc, depth, n_rendering_samples, extras list).  `jitter` (optional, [n_rays] in [0,1)) replaces the
-    stratified random draw so that parity tests do not depend on the RNG stream."""
+    stratified random draw so that parity tests do not depend on the RNG stream.
+
+    device_counts=True (training, fused field only): nothing is read back by the host during the call.  The packed
+    sample tensors in `extras` are then allocated at a capacity derived from earlier batches, only their first
+    n_rendering_samples rows are live, and n_rendering_samples is a 0-dim int64 DEVICE tensor (the reference's training
+    loop reads it once per step for its ray-count controller, train_real.py:354-360: `int(n)` does that)."""
     shape = rays.origins.shape
     rays = Rays(rays.origins.reshape(-1, 3), rays.viewdirs.reshape(-1, 3))
     n = rays.origins.shape[0]
@@ -80,15 +87,19 @@ def render_image(radiance_field, estimator, rays, near_plane=0.0, far_plane=1e10
         ridx, t0, t1 = estimator.sampling(cr.origins, cr.viewdirs, sigma_fn=sigma_fn, near_plane=near_plane,
                                           far_plane=far_plane, render_step_size=render_step_size,
                                           stratified=radiance_field.training, cone_angle=cone_angle,
-                                          alpha_thre=alpha_thre, jitter=None if jitter is None else jitter[i:i + chunk])
+                                          alpha_thre=alpha_thre, jitter=None if jitter is None else jitter[i:i + chunk],
+                                          device_counts=bool(device_counts and radiance_field.training and
+                                                             getattr(radiance_field, "fused_train_supported", lambda: False)()
+                                                             and timestamps is not None and torch.is_grad_enabled()))
         rgb, opac, depth, extras = rendering(t0, t1, ridx, cr.origins.shape[0], rgb_sigma_fn=rgb_sigma_fn,
                                              render_bkgd=render_bkgd)
         extras.update(ray_indices=ridx, t_starts=t0, t_ends=t1)
-        outs.append((rgb, opac, depth, len(t0)))
+        counts = ops.counts_of(ridx)
+        outs.append((rgb, opac, depth, len(t0) if counts is None else counts[1].view(())))
         infos.append(extras)
     rgb, opac, depth = (torch.cat([o[k] for o in outs], 0) for k in range(3))
     return (rgb.view(*shape[:-1], -1), opac.view(*shape[:-1], -1), depth.view(*shape[:-1], -1),
-            sum(o[3] for o in outs), infos)
+            outs[0][3] if len(outs) == 1 else sum(o[3] for o in outs), infos)
 
 
 @torch.no_grad()

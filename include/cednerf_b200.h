@@ -63,6 +63,9 @@ int cednerf_occ_mark_invisible(const float* K, int n_K, const float* c2w, int n_
  * Output groups (each nullable): nerfacc intervals (iv_*), nerfacc samples (sm_*), packed
  * (t_starts, t_ends, ray_indices). */
 int cednerf_ray_coherence_keys(const float* rays_d, int64_t n_rays, int32_t* keys, void* stream);
+/* order [n] = permutation grouping the rays by the leading 14 bits of that key (bucket order: histogram, scan, scatter;
+ * workspace 64 KB) - the ray_order argument of cednerf_march */
+int cednerf_ray_coherence_order(const int32_t* keys, int64_t n_rays, int32_t* order, void* workspace, void* stream);
 int cednerf_march(int fill, const float* rays_o, const float* rays_d, int64_t n_rays, const uint32_t* occ_bits,
                   const float* aabbs, int n_levels, int resolution, const float* near_planes, const float* far_planes,
                   float near_const, float far_const, float step_size, float cone_angle, int steps_limit,
@@ -80,11 +83,21 @@ int cednerf_march(int fill, const float* rays_o, const float* rays_d, int64_t n_
 int cednerf_march_fill_runs(int64_t n_rays, const int64_t* sm_starts, const float* run_t, const int32_t* run_n,
                             const int32_t* n_runs, int run_cap, float step_size, float cone_angle, float* t_starts,
                             float* t_ends, int64_t* ray_indices, uint8_t* overflow, void* stream);
+/* The same fill into buffers of a FIXED CAPACITY (no host read of the sample total - SURVEY.md 7 "hard parts"): offsets
+ * [n_rays + 1] and the drop rule come from cednerf_exclusive_scan_capped, n_samples = the unclamped per-ray counts. */
+int cednerf_march_fill_runs_capped(int64_t n_rays, const int64_t* offsets, const int32_t* n_samples, const float* run_t,
+                                   const int32_t* run_n, const int32_t* n_runs, int run_cap, float step_size,
+                                   float cone_angle, float* t_starts, float* t_ends, int64_t* ray_indices,
+                                   uint8_t* overflow, void* stream);
 /* cumsum between the two traversal passes (nerfacc: torch.cumsum + .item()); stays on the device */
 int64_t cednerf_scan_workspace_bytes(int64_t n);
 int cednerf_exclusive_scan(const int32_t* counts, int64_t n, int64_t* starts /*nullable*/,
                            int64_t* packed_info /*nullable, [n,2]*/, int64_t* total /*nullable*/, void* workspace,
                            void* stream);
+/* the scan for fixed-capacity buffers: offsets [n + 1] = min(exclusive prefix sums, capacity); totals [2] =
+ * {min(total, capacity), total}.  Kernels downstream read their live count from totals[0] (their `n_device`). */
+int cednerf_exclusive_scan_capped(const int32_t* counts, int64_t n, int64_t capacity, int64_t* offsets, int64_t* totals,
+                                  void* workspace, void* stream);
 
 /* ---- K2: hash-grid encoders ------------------------------------------------------------------------ */
 typedef struct CednerfGridLevels {
@@ -180,7 +193,9 @@ int cednerf_field_train_fwd(const int64_t* ray_indices, const float* t_starts, c
                             const float* rays_d, const float* timestamps, int t_stride, int64_t n,
                             const void* image_deform, const void* image_density, const void* image_colour,
                             const void* image_predict, const void* table_f16, const CednerfFieldDesc* desc, float* sigma,
-                            float* rgb, float* latent, uint8_t* selector, float* move, void* saved, void* stream);
+                            float* rgb, float* latent, uint8_t* selector, float* move, void* saved,
+                            const int64_t* n_device /*nullable: live sample count on the device, n = capacity*/,
+                            void* stream);
 int cednerf_field_train_bwd(const int64_t* ray_indices, const float* t_starts, const float* t_ends, const float* rays_o,
                             const float* rays_d, const float* timestamps, int t_stride, int64_t n,
                             const void* image_deform, const void* image_density, const void* image_colour,
@@ -188,7 +203,8 @@ int cednerf_field_train_bwd(const int64_t* ray_indices, const float* t_starts, c
                             const float* sigma, const float* rgb, const uint8_t* selector, const void* saved,
                             const float* d_sigma, const float* d_rgb, const float* d_latent, void* work,
                             float* d_params_deform, float* d_params_density, float* d_params_colour,
-                            float* d_params_predict, float* g_table, int phase, void* stream);
+                            float* d_params_predict, float* g_table, int phase,
+                            const int64_t* n_device /*nullable, as in the forward*/, void* stream);
 /* phase: 0 = the whole backward; 1 = colour and density nets + table gradient (g_table is complete on return: a
  * data-parallel caller starts its all-reduce here); 2 = the rest (predictor net, dL/dx of the encoding, deformation net). */
 
@@ -220,13 +236,18 @@ int cednerf_visibility_mask(const float* t_starts, const float* t_ends, const fl
 int cednerf_compact_samples(const uint8_t* keep, const int64_t* offsets, const int64_t* out_starts, const float* t_starts,
                             const float* t_ends, int64_t n_samples, int64_t n_rays, int64_t* ray_indices_out,
                             float* t_starts_out, float* t_ends_out, void* stream);
+/* ... into outputs of a fixed capacity: out_offsets [n_rays + 1] from cednerf_exclusive_scan_capped over kept_counts */
+int cednerf_compact_samples_capped(const uint8_t* keep, const int64_t* offsets, const int64_t* out_offsets,
+                                   const float* t_starts, const float* t_ends, int64_t n_samples, int64_t n_rays,
+                                   int64_t* ray_indices_out, float* t_starts_out, float* t_ends_out, void* stream);
 /* nerfacc.accumulate_along_rays / accumulate_along_rays_ — cednerf/render.py:158-169, cednerf/utils.py:282-299 */
 int cednerf_accumulate_fwd(const float* weights, const float* values /*nullable*/, int n_channels,
                            const int64_t* offsets, int64_t n_samples, int64_t n_rays, float* outputs, int inplace,
                            void* stream);
 int cednerf_accumulate_bwd(const float* weights, const float* values /*nullable*/, int n_channels,
                            const int64_t* ray_indices, int64_t n_samples, const float* g_outputs,
-                           float* g_weights /*nullable*/, float* g_values /*nullable*/, void* stream);
+                           float* g_weights /*nullable*/, float* g_values /*nullable*/,
+                           const int64_t* n_device /*nullable: live sample count, n_samples = capacity*/, void* stream);
 
 
 /* ------------------------------------------------------------------------------------------------------------------
@@ -304,12 +325,13 @@ int cednerf_dp_adam(const CednerfDpAdam* args, const float* step, const float* g
  * (-f).  acc / rgbs / latent nullable (term absent).  sums: 4 doubles of workspace; loss: 1 float. */
 int cednerf_training_loss_fwd(const float* rgb, const float* acc, const float* pixels, int64_t n_rays, const float* rgbs,
                               const float* weights, const int64_t* ray_indices, int64_t n_samples, const float* latent,
-                              int n_latent, float w_entropy, float w_rgbper, double* sums, float* loss, void* stream);
+                              int n_latent, float w_entropy, float w_rgbper, double* sums, float* loss,
+                              const int64_t* n_device /*nullable: live sample count, n_samples = capacity*/, void* stream);
 /* its gradients times g_loss[0] (device scalar); any of d_rgb [R,3], d_acc [R], d_rgbs [S,3], d_latent [R,n_latent] null */
 int cednerf_training_loss_bwd(const float* g_loss, const float* rgb, const float* acc, const float* pixels, int64_t n_rays,
                               const float* rgbs, const float* weights, const int64_t* ray_indices, int64_t n_samples,
                               int n_latent, float w_entropy, float w_rgbper, float* d_rgb, float* d_acc, float* d_rgbs,
-                              float* d_latent, void* stream);
+                              float* d_latent, const int64_t* n_device /*nullable*/, void* stream);
 
 #ifdef __cplusplus
 }

@@ -158,3 +158,32 @@ def test_shared_tmem_weight_gradient_accumulators_lose_nothing():
         assert rel(again[k], base[k]) <= 2e-6, ("run-to-run", k, rel(again[k], base[k]))
         assert rel(single[k], base[k]) <= 2e-6, ("one group per CTA", k, rel(single[k], base[k]))
         assert rel(flushed[k], base[k]) <= 1e-4, ("flush every tile", k, rel(flushed[k], base[k]))
+
+
+def test_fused_backward_is_finite_for_every_tail_length():
+    """Regression: rows past the end of the last 128-sample tile must be zero over the whole width of every network's
+    output-gradient tile.  The feature predictor's (32 wide) was cleared over 16 columns only, so a stale NaN bit pattern in
+    shared memory met a zero activation in the weight-gradient MMA (0 x NaN) and its last layer's gradient came out NaN
+    whenever the sample count was not a multiple of 128 - which GradScaler then answers by skipping the step."""
+    import cednerf_b200 as cb
+    from cednerf_b200 import workload as w
+
+    cfg = w.DYNERF
+    rk = w.render_kwargs(cfg)
+    est, field = w.build_scene(cfg, DEV, cb, seed=42)
+    est.train(), field.train()
+    b = {k: v.to(DEV) for k, v in w.draw_batch(cfg, 16384, torch.Generator().manual_seed(11)).items()}
+    rays = cb.Rays(b["origins"], b["viewdirs"])
+    sigma_fn, rgb_sigma_fn = cb.utils._field_fns(field, rays, b["timestamps"])
+    ridx, t0, t1 = est.sampling(b["origins"], b["viewdirs"], sigma_fn=sigma_fn, stratified=True, jitter=b["jitter"], **rk)
+    n_all = t0.numel()
+    assert n_all > 60000
+    for n in (n_all, n_all - 1, n_all - 37, n_all // 128 * 128, n_all // 128 * 128 + 1, 4097):
+        for p in field.parameters():
+            p.grad = None
+        rgb, acc, depth, ex = cb.rendering(t0[:n].contiguous(), t1[:n].contiguous(), ridx[:n].contiguous(), 16384,
+                                           rgb_sigma_fn=rgb_sigma_fn, render_bkgd=b["color_bkgd"])
+        ((torch.nn.functional.mse_loss(rgb, b["pixels"]) + ex["latent_losses"].mean()) * 1024.0).backward()
+        for k, p in field.named_parameters():
+            if p.numel():
+                assert p.grad is not None and bool(torch.isfinite(p.grad).all()), (n, k)

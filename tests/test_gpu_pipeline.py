@@ -278,3 +278,52 @@ def test_fused_training_path_matches_op_by_op_path(cb, golden, name, extra):
         if k in grads_m:
             assert p.grad is not None, k
             assert rel(p.grad, grads_m[k]) < 5e-3, (k, rel(p.grad, grads_m[k]))
+
+
+def test_device_count_sampling_matches_the_host_count_path(cb):
+    """render_image(..., device_counts=True): capacity-sized sample tensors whose live count never leaves the device must
+    give the same rendering, loss and gradients as the default path (which reads the totals back, like the reference)."""
+    from cednerf_b200 import workload as w
+
+    cfg = w.TINY
+    rk = w.render_kwargs(cfg)
+    est, field = w.build_scene(cfg, DEV, cb, seed=42)
+    est.train(), field.train()
+    b = {k: v.to(DEV) for k, v in w.draw_batch(cfg, 70000, torch.Generator().manual_seed(3)).items()}
+    rays = cb.Rays(b["origins"], b["viewdirs"])
+
+    def run(device_counts):
+        for p in field.parameters():
+            p.grad = None
+        rgb, acc, depth, n_s, extra = cb.render_image(field, est, rays, render_bkgd=b["color_bkgd"], timestamps=b["timestamps"],
+                                                      jitter=b["jitter"], device_counts=device_counts, **rk)
+        loss = cb.losses.training_loss(rgb, acc, b["pixels"], extra, acc_entropy_loss=True, weight_rgbper=True,
+                                       use_feat_predict=True)
+        (loss * 1024.0).backward()
+        grads = {k: p.grad.detach().clone() for k, p in field.named_parameters() if p.grad is not None}
+        return rgb.detach(), acc.detach(), depth.detach(), n_s, extra[0], float(loss), grads
+
+    ref = run(False)
+    assert isinstance(ref[3], int) and ref[3] > 50000
+    first = run(True)            # no capacity known yet: falls back to the host-count path and seeds the capacities
+    assert isinstance(first[3], int) and first[3] == ref[3]
+    got = run(True)
+    assert torch.is_tensor(got[3]) and got[3].is_cuda and int(got[3]) == ref[3] and est.dropped_samples == 0
+    n = ref[3]
+    ex, ex_ref = got[4], ref[4]
+    assert ex["t_starts"].numel() > n                      # allocated at a capacity with headroom ...
+    for k in ("ray_indices", "t_starts", "t_ends"):        # ... whose live prefix is the default path's sample set
+        assert torch.equal(ex[k][:n], ex_ref[k])
+    for i in range(3):
+        assert torch.equal(got[i], ref[i])
+    assert torch.equal(ex["weights"][:n], ex_ref["weights"]) and torch.equal(ex["rgbs"][:n], ex_ref["rgbs"])
+    assert abs(got[5] - ref[5]) <= 1e-6 * abs(ref[5])
+    for k, g in ref[6].items():
+        assert rel(got[6][k], g) <= 2e-6, (k, rel(got[6][k], g))
+    # a capacity that is too small drops the tail of the batch and says so
+    est._cap_state["visible"]["last"] = n // 4
+    est._cap_state["visible"]["pending"].clear()
+    short = run(True)
+    torch.cuda.synchronize()
+    est._capacity("visible")
+    assert int(short[3]) < n and est.dropped_samples > 0
