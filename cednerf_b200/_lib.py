@@ -105,6 +105,11 @@ _SIGNATURES = {
     "cednerf_compact_samples": "pppppllpppp",
     "cednerf_accumulate_fwd": "ppipllpip",
     "cednerf_accumulate_bwd": "ppiplppppp",
+    "cednerf_render_round_begin": "pliippp",
+    "cednerf_march_round": "ipplppiipfffppppppppppppppip",
+    "cednerf_march_fill_runs_round": "lpppppiffppppppp",
+    "cednerf_render_round_composite": "pppppppplifppppp",
+    "cednerf_render_round_compact": "ppplppp",
     "cednerf_nonfinite_check": "App",
     "cednerf_training_loss_fwd": "ppplppplpiffpppp",
     "cednerf_training_loss_bwd": "pppplpppliffpppppp",

@@ -60,6 +60,12 @@ struct MarchArgs {
   int32_t* n_runs;   // [n]  (may exceed run_cap: the ray then takes the full-march fill)
   int run_cap;
   const int32_t* order;  // nullable: thread i marches ray order[i] (rays sorted for coherence); outputs stay indexed by ray
+  // marching rounds of render_image_test kept on the device (cednerf_march_round): `order` is the list of alive rays,
+  // only its first *n_active_dev entries are live, the per-round sample limit is read from *limit_dev, and every
+  // per-ray array except near / termination (mask, counts, runs, fill offsets) is indexed by SLOT in that list
+  const int32_t* n_active_dev;
+  const int32_t* limit_dev;
+  int by_slot;
 };
 
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
@@ -137,14 +143,20 @@ template <bool FILL>
 __global__ void __launch_bounds__(128) march_kernel(MarchArgs a) {
   const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= a.n_rays) return;
+  if (a.n_active_dev && slot >= (int64_t)*a.n_active_dev) {  // beyond the live part of the alive list
+    if (!FILL && a.n_samples) a.n_samples[slot] = 0;
+    if (!FILL && a.n_runs) a.n_runs[slot] = 0;
+    return;
+  }
   const int64_t r = a.order ? (int64_t)a.order[slot] : slot;
+  const int64_t oi = a.by_slot ? slot : r;  // index of this ray's entries in the count / run / offset arrays
   const float near = a.near ? a.near[r] : a.near_const;
   const float far = a.far ? a.far[r] : a.far_const;
-  if (a.mask && !a.mask[r]) {
-    if (a.n_intervals) a.n_intervals[r] = 0;
-    if (a.n_samples) a.n_samples[r] = 0;
+  if (a.mask && !a.mask[oi]) {
+    if (a.n_intervals) a.n_intervals[oi] = 0;
+    if (a.n_samples) a.n_samples[oi] = 0;
     if (a.termination) a.termination[r] = near;
-    if (!FILL && a.n_runs) a.n_runs[r] = 0;
+    if (!FILL && a.n_runs) a.n_runs[oi] = 0;
     return;
   }
   const int L = a.n_levels, m = 2 * L, res = a.res;
@@ -170,13 +182,13 @@ __global__ void __launch_bounds__(128) march_kernel(MarchArgs a) {
     sort_bounds(ts, ti, m);
   }
 
-  const int64_t iv_base = FILL && a.iv_starts ? a.iv_starts[r] : 0;
-  const int64_t sm_base = FILL && a.sm_starts ? a.sm_starts[r] : 0;
+  const int64_t iv_base = FILL && a.iv_starts ? a.iv_starts[oi] : 0;
+  const int64_t sm_base = FILL && a.sm_starts ? a.sm_starts[oi] : 0;
   int n_iv = 0, n_sm = 0;
   float t_last = near;
   bool continuous = false;
   int runs = 0, run_len = 0;  // run bookkeeping (count pass with run recording)
-  const int limit = a.limit;
+  const int limit = a.limit_dev ? *a.limit_dev : a.limit;
   const float step_size = a.step_size, cone = a.cone_angle;
 
   for (int i = 0; i < m - 1; ++i) {
@@ -286,8 +298,8 @@ __global__ void __launch_bounds__(128) march_kernel(MarchArgs a) {
           }
           if (!FILL && a.run_t) {
             if (!continuous) {  // a new run starts at t_last
-              if (runs > 0 && runs <= a.run_cap) a.run_n[r * a.run_cap + runs - 1] = run_len;
-              if (runs < a.run_cap) a.run_t[r * a.run_cap + runs] = t_last;
+              if (runs > 0 && runs <= a.run_cap) a.run_n[oi * a.run_cap + runs - 1] = run_len;
+              if (runs < a.run_cap) a.run_t[oi * a.run_cap + runs] = t_last;
               ++runs;
               run_len = 0;
             }
@@ -320,12 +332,12 @@ __global__ void __launch_bounds__(128) march_kernel(MarchArgs a) {
     }
   }
   if (!FILL && a.run_t) {
-    if (runs > 0 && runs <= a.run_cap) a.run_n[r * a.run_cap + runs - 1] = run_len;
-    a.n_runs[r] = runs;
+    if (runs > 0 && runs <= a.run_cap) a.run_n[oi * a.run_cap + runs - 1] = run_len;
+    a.n_runs[oi] = runs;
   }
-  if (a.n_intervals) a.n_intervals[r] = n_iv;
-  if (a.n_samples) a.n_samples[r] = n_sm;
-  if (a.termination) a.termination[r] = t_last;
+  if (a.n_intervals) a.n_intervals[oi] = n_iv;
+  if (a.n_samples) a.n_samples[oi] = n_sm;
+  if (a.termination && !(FILL && a.by_slot)) a.termination[r] = t_last;
 }
 
 // Fill pass from recorded runs: no grid traversal, just the step recurrence t <- t + clamp(t*cone, step, 1e10) replayed
@@ -336,9 +348,15 @@ march_fill_runs_kernel(int64_t n_rays, const int64_t* __restrict__ sm_starts, co
                        const int32_t* __restrict__ run_n, const int32_t* __restrict__ n_runs, int run_cap,
                        float step_size, float cone, float* __restrict__ t_starts, float* __restrict__ t_ends,
                        int64_t* __restrict__ ray_indices, uint8_t* __restrict__ overflow,
-                       const int32_t* __restrict__ capped_counts) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                       const int32_t* __restrict__ capped_counts, const int32_t* __restrict__ slot_ray = nullptr,
+                       const int32_t* __restrict__ n_active_dev = nullptr) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // ray, or slot in the alive list (slot_ray)
   if (r >= n_rays) return;
+  if (n_active_dev && r >= (int64_t)*n_active_dev) {
+    overflow[r] = 0;
+    return;
+  }
+  const int64_t ray_id = slot_ray ? (int64_t)slot_ray[r] : r;
   const int runs = n_runs[r];
   bool over = runs > run_cap;
   int64_t k = sm_starts[r];
@@ -347,7 +365,7 @@ march_fill_runs_kernel(int64_t n_rays, const int64_t* __restrict__ sm_starts, co
   const int64_t k_end = capped_counts ? sm_starts[r + 1] : INT64_MAX;
   if (capped_counts && over && k_end - k != (int64_t)capped_counts[r]) {
     // a truncated ray cannot take the full-march fallback (it writes its whole range): leave harmless samples
-    for (; k < k_end; ++k) t_starts[k] = 0.0f, t_ends[k] = 0.0f, ray_indices[k] = r;
+    for (; k < k_end; ++k) t_starts[k] = 0.0f, t_ends[k] = 0.0f, ray_indices[k] = ray_id;
     over = false;
     overflow[r] = 0;
     return;
@@ -365,21 +383,21 @@ march_fill_runs_kernel(int64_t n_rays, const int64_t* __restrict__ sm_starts, co
     // is a multiple of 4) quarter the number of store transactions.
     for (; i < cnt && (k & 3); ++i, ++k) {
       const float t_next = next(t);
-      t_starts[k] = t, t_ends[k] = t_next, ray_indices[k] = r;
+      t_starts[k] = t, t_ends[k] = t_next, ray_indices[k] = ray_id;
       t = t_next;
     }
     for (; i + 4 <= cnt; i += 4, k += 4) {
       const float a1 = next(t), a2 = next(a1), a3 = next(a2), a4 = next(a3);
       *reinterpret_cast<float4*>(t_starts + k) = make_float4(t, a1, a2, a3);
       *reinterpret_cast<float4*>(t_ends + k) = make_float4(a1, a2, a3, a4);
-      const longlong2 rr = make_longlong2((long long)r, (long long)r);
+      const longlong2 rr = make_longlong2((long long)ray_id, (long long)ray_id);
       *reinterpret_cast<longlong2*>(ray_indices + k) = rr;
       *reinterpret_cast<longlong2*>(ray_indices + k + 2) = rr;
       t = a4;
     }
     for (; i < cnt; ++i, ++k) {
       const float t_next = next(t);
-      t_starts[k] = t, t_ends[k] = t_next, ray_indices[k] = r;
+      t_starts[k] = t, t_ends[k] = t_next, ray_indices[k] = ray_id;
       t = t_next;
     }
   }
@@ -756,7 +774,7 @@ CEDNERF_EXPORT int cednerf_march(int fill, const float* rays_o, const float* ray
   MarchArgs a{rays_o, rays_d, n_rays, occ_bits, aabbs, n_levels, resolution, near_planes, far_planes, near_const,
               far_const, step_size, cone_angle, steps_limit, rays_mask, t_sorted, t_indices, hits, iv_starts,
               sm_starts, iv_vals, iv_left, iv_right, iv_ray, sm_vals, sm_ray, sm_valid, t_starts, t_ends, ray_indices,
-              n_intervals, n_samples, termination, run_t, run_n, n_runs, run_cap, ray_order};
+              n_intervals, n_samples, termination, run_t, run_n, n_runs, run_cap, ray_order, nullptr, nullptr, 0};
   const unsigned grid = cednerf_blocks(n_rays, 128);
   if (fill) march_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
   else march_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
@@ -840,4 +858,90 @@ CEDNERF_EXPORT int cednerf_exclusive_scan_capped(const int32_t* counts, int64_t 
   scan_apply_capped_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(counts, n, tile_sums, capacity, offsets, totals + 1,
                                                                       totals);
   return cednerf_check_launch("cednerf_exclusive_scan_capped", 3);
+}
+
+// ---- marching rounds of render_image_test kept on the device (cednerf/utils.py:224-318) ---------------------------
+// state (int32 [8], device): [0] alive rays of this round, [1] k = samples per ray this round, [2] samples per ray marched
+// so far ("done"), [3] rays appended to the NEXT round's list by the compositing kernel, [4] round index, [5] 1 once the
+// loop is over.  total (int64 [1]) accumulates the rounds' sample totals.
+namespace {
+__global__ void render_round_begin_kernel(int32_t* __restrict__ state, int64_t n_rays, int max_samples, int min_samples,
+                                          const int64_t* __restrict__ prev_totals, int64_t* __restrict__ total) {
+  if (prev_totals && total) total[0] += prev_totals[0];
+  int n_alive = state[3];
+  state[3] = 0;
+  int k = 0;
+  if (n_alive <= 0 || state[2] >= max_samples) {
+    n_alive = 0;
+    state[5] = 1;
+  } else {
+    const int64_t q = n_rays / (int64_t)n_alive;            // the reference: k = max(min(n // n_alive, 64), min_samples)
+    k = (int)(q < 64 ? q : 64);
+    if (k < min_samples) k = min_samples;
+    state[2] += k;
+  }
+  state[0] = n_alive;
+  state[1] = k;
+  state[4] += 1;
+}
+}  // namespace
+
+// start of a round: state[0] <- state[3] (rays the previous round kept alive; the caller seeds state[3] = n_rays),
+// k and done are advanced as the reference's host loop does; prev_totals (nullable): the previous round's scan totals
+CEDNERF_EXPORT int cednerf_render_round_begin(int32_t* state, int64_t n_rays, int max_samples, int min_samples,
+                                              const int64_t* prev_totals, int64_t* total, void* stream) {
+  CEDNERF_REQUIRE(state && n_rays >= 0 && max_samples > 0 && min_samples > 0, "bad arguments");
+  render_round_begin_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, n_rays, max_samples, min_samples, prev_totals, total);
+  return cednerf_check_launch("cednerf_render_round_begin");
+}
+
+// One marching pass of a round over the alive list (first state[0] entries of `alive`; n_bound >= state[0] sizes the
+// launch).  near_term [n_rays]: the rays' start planes on entry; the count pass (fill == 0) leaves the termination
+// planes there.  Per-slot outputs: n_samples, runs.  fill == 1: the full-march fill for the slots flagged in slot_mask
+// (rays over the run limit), at offsets[slot].  The sample limit k is read from state[1].
+CEDNERF_EXPORT int cednerf_march_round(int fill, const float* rays_o, const float* rays_d, int64_t n_bound,
+                                       const uint32_t* occ_bits, const float* aabbs, int n_levels, int resolution,
+                                       float* near_term, float far_const, float step_size, float cone_angle,
+                                       const float* t_sorted, const int64_t* t_indices, const uint8_t* hits,
+                                       const int32_t* alive, const int32_t* state, const uint8_t* slot_mask,
+                                       const int64_t* offsets, float* t_starts, float* t_ends, int64_t* ray_indices,
+                                       int32_t* n_samples, float* run_t, int32_t* run_n, int32_t* n_runs, int run_cap,
+                                       void* stream) {
+  CEDNERF_REQUIRE(n_bound >= 0 && n_levels >= 1 && n_levels <= MARCH_MAX_LEVELS && resolution >= 1 && alive && state &&
+                      near_term && t_sorted && t_indices && hits,
+                  "bad arguments");
+  CEDNERF_REQUIRE(fill ? (slot_mask && offsets && t_starts && t_ends && ray_indices)
+                       : (n_samples && run_t && run_n && n_runs && run_cap > 0 && step_size > 0.0f),
+                  "count pass: counts and runs; fill pass: mask, offsets and packed outputs");
+  if (n_bound == 0) return 0;
+  MarchArgs a{};
+  a.rays_o = rays_o, a.rays_d = rays_d, a.n_rays = n_bound, a.occ_bits = occ_bits, a.aabbs = aabbs;
+  a.n_levels = n_levels, a.res = resolution, a.near = near_term, a.far = nullptr, a.near_const = 0.0f, a.far_const = far_const;
+  a.step_size = step_size, a.cone_angle = cone_angle, a.limit = 0, a.mask = fill ? slot_mask : nullptr;
+  a.t_sorted = t_sorted, a.t_indices = t_indices, a.hits = hits;
+  a.sm_starts = offsets, a.t_starts = t_starts, a.t_ends = t_ends, a.ray_indices = ray_indices;
+  a.n_samples = fill ? nullptr : n_samples, a.termination = fill ? nullptr : near_term;
+  a.run_t = fill ? nullptr : run_t, a.run_n = fill ? nullptr : run_n, a.n_runs = fill ? nullptr : n_runs, a.run_cap = run_cap;
+  a.order = alive, a.n_active_dev = state, a.limit_dev = state + 1, a.by_slot = 1;
+  const unsigned grid = cednerf_blocks(n_bound, 128);
+  if (fill) march_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  else march_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  return cednerf_check_launch("cednerf_march_round");
+}
+
+// packed fill of a round from the recorded runs: slot-indexed offsets (cednerf_exclusive_scan_capped over n_samples),
+// ray ids taken from the alive list; overflow[slot] = 1 where the run list did not fit (-> cednerf_march_round(fill = 1))
+CEDNERF_EXPORT int cednerf_march_fill_runs_round(int64_t n_bound, const int64_t* offsets, const int32_t* n_samples,
+                                                 const float* run_t, const int32_t* run_n, const int32_t* n_runs,
+                                                 int run_cap, float step_size, float cone_angle, const int32_t* alive,
+                                                 const int32_t* state, float* t_starts, float* t_ends,
+                                                 int64_t* ray_indices, uint8_t* overflow, void* stream) {
+  CEDNERF_REQUIRE(n_bound >= 0 && run_cap > 0 && step_size > 0.0f && offsets && n_samples && alive && state, "bad arguments");
+  CEDNERF_REQUIRE((((uintptr_t)t_starts | (uintptr_t)t_ends | (uintptr_t)ray_indices) & 15) == 0,
+                  "packed outputs must be 16-byte aligned");
+  if (n_bound == 0) return 0;
+  march_fill_runs_kernel<<<cednerf_blocks(n_bound, 128), 128, 0, (cudaStream_t)stream>>>(
+      n_bound, offsets, run_t, run_n, n_runs, run_cap, step_size, cone_angle, t_starts, t_ends, ray_indices, overflow,
+      n_samples, alive, state);
+  return cednerf_check_launch("cednerf_march_fill_runs_round");
 }

@@ -102,6 +102,104 @@ def render_image(radiance_field, estimator, rays, near_plane=0.0, far_plane=1e10
             outs[0][3] if len(outs) == 1 else sum(o[3] for o in outs), infos)
 
 
+_DEVICE_ROUNDS = True   # False: the host-driven rounds below (one host read per round, as the reference does)
+_ROUND_LAG = 4          # rounds the host may run ahead of the newest alive count it has seen
+
+
+def _render_rounds_on_device(max_samples, field, rays, bits, aabbs, res, near, far_plane, step, cone, early_stop_eps,
+                             timestamps, t_sorted, t_indices, hits, min_samples, rgb, opacity, depth) -> int:
+    """The marching rounds of cednerf/utils.py:224-304 with the alive-ray list, the per-round k and the termination test
+    on the device (csrc/march.cu: cednerf_render_round_begin / cednerf_march_round / cednerf_march_fill_runs_round,
+    csrc/composite.cu: cednerf_render_round_composite).  The host enqueues rounds and reads a copy of the round state
+    that is up to _ROUND_LAG rounds old: it tells it when every ray is done and how far the launches can shrink
+    (the alive count never grows).  Rays are marched in alive-list order; the list is the ORDERED compaction of the
+    survivors, so neighbouring lanes keep neighbouring pixels and a round's warps are dense however few rays survive;
+    per ray the samples, their order and the arithmetic are those of the host-driven loop."""
+    from ._lib import call, ptr, stream
+
+    n, dev = rays.origins.shape[0], rays.origins.device
+    o, d = ops._f32c(rays.origins), ops._f32c(rays.viewdirs)
+    aabbs_c = ops._f32c(aabbs)
+    n_levels = aabbs_c.shape[0]
+    I32, I64 = torch.int32, torch.int64
+    # n_alive * k <= n when k = n // n_alive, and <= min_samples * n_alive otherwise
+    cap = ops._sticky_capacity(n * max(1, min_samples))
+    state = torch.zeros(8, dtype=I32, device=dev)
+    state[3] = n
+    total = torch.zeros(1, dtype=I64, device=dev)
+    lists = [torch.arange(n, dtype=I32, device=dev), torch.empty(n, dtype=I32, device=dev)]
+    n_sm = torch.empty(n, dtype=I32, device=dev)
+    run_cap = ops.MarchInputs.RUN_CAP
+    run_t = torch.empty(n, run_cap, device=dev)
+    run_n = torch.empty(n, run_cap, dtype=I32, device=dev)
+    n_runs = torch.empty(n, dtype=I32, device=dev)
+    overflow = torch.empty(n, dtype=torch.bool, device=dev)
+    t0, t1 = torch.empty(cap, device=dev), torch.empty(cap, device=dev)
+    ridx = torch.empty(cap, dtype=I64, device=dev)
+    offsets = torch.empty(n + 1, dtype=I64, device=dev)
+    totals = torch.zeros(2, dtype=I64, device=dev)
+    flags = torch.empty(n, dtype=I32, device=dev)
+    pos, pos_tot = torch.empty(n + 1, dtype=I64, device=dev), torch.empty(2, dtype=I64, device=dev)
+    ws = torch.empty(max(int(_lib_scan_ws(n)) // 8, 1), dtype=I64, device=dev)
+    ts = ops._f32c(timestamps).view(-1)
+    images = (field.xyz_wrap.network.weight_image(), field.mlp_base.weight_image(), field.mlp_head.weight_image())
+    desc, table = field._field_desc(), field.hash_encoder.table_f16()
+    sigma, rgbs = torch.empty(cap, device=dev), torch.empty(cap, 3, device=dev)
+    ring = [torch.empty(8, dtype=I32).pin_memory() for _ in range(_ROUND_LAG + 2)]
+    pending = []          # (event, host copy of the state at the START of a round)
+    bound, k_hint = n, max(1, min_samples)
+    max_rounds = (max_samples + min_samples - 1) // min_samples + 1
+    import ctypes as _ct
+
+    for rnd in range(max_rounds):
+        cur, nxt = lists[rnd & 1], lists[(rnd + 1) & 1]
+        call("cednerf_render_round_begin", ptr(state), n, int(max_samples), int(min_samples),
+             ptr(totals) if rnd else None, ptr(total), stream())
+        host = ring[rnd % len(ring)]
+        host.copy_(state, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        pending.append((ev, host))
+        call("cednerf_march_round", 0, ptr(o), ptr(d), bound, ptr(bits), ptr(aabbs_c), n_levels, res, ptr(near), far_plane,
+             float(step), float(cone), ptr(t_sorted), ptr(t_indices), ptr(hits), ptr(cur), ptr(state), None, None, None,
+             None, None, ptr(n_sm), ptr(run_t), ptr(run_n), ptr(n_runs), run_cap, stream())
+        call("cednerf_exclusive_scan_capped", ptr(n_sm), bound, cap, ptr(offsets), ptr(totals), ptr(ws), stream())
+        call("cednerf_march_fill_runs_round", bound, ptr(offsets), ptr(n_sm), ptr(run_t), ptr(run_n), ptr(n_runs), run_cap,
+             float(step), float(cone), ptr(cur), ptr(state), ptr(t0), ptr(t1), ptr(ridx), ptr(overflow), stream())
+        call("cednerf_march_round", 1, ptr(o), ptr(d), bound, ptr(bits), ptr(aabbs_c), n_levels, res, ptr(near), far_plane,
+             float(step), float(cone), ptr(t_sorted), ptr(t_indices), ptr(hits), ptr(cur), ptr(state), ptr(overflow),
+             ptr(offsets), ptr(t0), ptr(t1), ptr(ridx), None, None, None, None, run_cap, stream())
+        call("cednerf_field_fwd", ptr(ridx), ptr(t0), ptr(t1), ptr(o), ptr(d), None, None, ptr(ts), 0, cap, ptr(images[0]),
+             ptr(images[1]), ptr(images[2]), ptr(table), _ct.byref(desc), ptr(sigma), ptr(rgbs), ptr(totals), stream())
+        call("cednerf_render_round_composite", ptr(t0), ptr(t1), ptr(sigma), ptr(rgbs), ptr(offsets), ptr(cur), ptr(state),
+             ptr(n_sm), bound, int(k_hint), float(early_stop_eps), ptr(rgb), ptr(opacity), ptr(depth), ptr(flags), stream())
+        # ordered compaction of the surviving rays: the list stays in pixel order, so a warp's rays stay coherent
+        call("cednerf_exclusive_scan_capped", ptr(flags), bound, n, ptr(pos), ptr(pos_tot), ptr(ws), stream())
+        call("cednerf_render_round_compact", ptr(flags), ptr(pos), ptr(cur), bound, ptr(state), ptr(nxt), stream())
+        # look at the oldest state copies that have arrived; never run more than _ROUND_LAG rounds ahead of one
+        stop = False
+        while pending and (pending[0][0].query() or len(pending) > _ROUND_LAG):
+            ev0, h0 = pending.pop(0)
+            ev0.synchronize()
+            n_alive, k_seen, over = int(h0[0]), int(h0[1]), int(h0[5])
+            if over or n_alive == 0:
+                stop = True
+                break
+            bound = min(bound, n_alive)                    # valid for every later round: the list only shrinks
+            k_hint = max(k_hint, min(64, n // max(n_alive, 1)))
+        if stop:
+            break
+    # the rounds still in flight when the host saw the end did nothing (state[0] == 0); collect the total
+    call("cednerf_render_round_begin", ptr(state), n, int(max_samples), int(min_samples), ptr(totals), ptr(total), stream())
+    return int(total.item())
+
+
+def _lib_scan_ws(n):
+    from . import _lib
+
+    return _lib.load().cednerf_scan_workspace_bytes(n)
+
+
 @torch.no_grad()
 def render_image_test(max_samples, radiance_field, estimator, rays, near_plane=0.0, far_plane=1e10,
                       render_step_size=1e-3, render_bkgd=None, cone_angle=0.0, alpha_thre=0.0, early_stop_eps=1e-4,
@@ -120,11 +218,18 @@ def render_image_test(max_samples, radiance_field, estimator, rays, near_plane=0
     t_sorted, t_indices = ops.sort_boundaries(t_mins, t_maxs)
     bits = nerfacc.grid.occupancy_bits(estimator.binaries)
     res = int(estimator.binaries.shape[1])
+    fuse = (getattr(radiance_field, "fused_supported", lambda: False)() and not radiance_field.training
+            and timestamps is not None and timestamps.numel() == 1 and render_step_size > 0 and n < 2 ** 31)
+    if fuse and _DEVICE_ROUNDS:
+        total = _render_rounds_on_device(max_samples, radiance_field, rays, bits, estimator.aabbs, res, near, float(far_plane),
+                                         render_step_size, cone_angle, early_stop_eps, timestamps, t_sorted, t_indices, hits,
+                                         min_samples, rgb, opacity, depth)
+        rgb = rgb + render_bkgd * (1.0 - opacity)
+        depth = depth / opacity.clamp_min(torch.finfo(torch.float32).eps)
+        return rgb.view(*shape[:-1], -1), opacity.view(*shape[:-1], -1), depth.view(*shape[:-1], -1), total
     done = total = 0
     # With the fused field kernel a round needs ONE host read (the reference's `alive.sum()`): the round's sample total
     # stays on the device - outputs are sized for the bound n_alive * k and the kernels read the live count themselves.
-    fuse = (getattr(radiance_field, "fused_supported", lambda: False)() and not radiance_field.training
-            and timestamps is not None and timestamps.numel() == 1 and render_step_size > 0)
     total_dev = torch.zeros(1, dtype=torch.int64, device=dev)
     while done < max_samples:
         n_alive = int(alive.sum())                     # the reference's host read (utils.py:231)

@@ -240,6 +240,33 @@ int cednerf_compact_samples(const uint8_t* keep, const int64_t* offsets, const i
 int cednerf_compact_samples_capped(const uint8_t* keep, const int64_t* offsets, const int64_t* out_offsets,
                                    const float* t_starts, const float* t_ends, int64_t n_samples, int64_t n_rays,
                                    int64_t* ray_indices_out, float* t_starts_out, float* t_ends_out, void* stream);
+/* ---- marching rounds of render_image_test kept on the device (cednerf/utils.py:224-318): the alive-ray list, the
+ * per-round sample limit k and the termination test never leave the GPU; the host only enqueues rounds and looks at a
+ * lagged copy of `state` to know when to stop.  state int32[8]: [0] alive rays of this round, [1] k, [2] samples per ray
+ * marched so far, [3] rays kept alive for the next round (seed with n_rays), [4] round index, [5] 1 when the loop is
+ * over. */
+int cednerf_render_round_begin(int32_t* state, int64_t n_rays, int max_samples, int min_samples,
+                               const int64_t* prev_totals /*nullable*/, int64_t* total /*nullable, += prev_totals[0]*/,
+                               void* stream);
+int cednerf_march_round(int fill, const float* rays_o, const float* rays_d, int64_t n_bound, const uint32_t* occ_bits,
+                        const float* aabbs, int n_levels, int resolution, float* near_term /*[n_rays] in: start planes; out (count pass): termination planes*/, float far_const, float step_size, float cone_angle,
+                        const float* t_sorted, const int64_t* t_indices, const uint8_t* hits, const int32_t* alive,
+                        const int32_t* state, const uint8_t* slot_mask /*fill*/, const int64_t* offsets /*fill*/,
+                        float* t_starts, float* t_ends, int64_t* ray_indices, int32_t* n_samples /*count, per slot*/,
+                        float* run_t, int32_t* run_n, int32_t* n_runs, int run_cap, void* stream);
+int cednerf_march_fill_runs_round(int64_t n_bound, const int64_t* offsets, const int32_t* n_samples, const float* run_t,
+                                  const int32_t* run_n, const int32_t* n_runs, int run_cap, float step_size,
+                                  float cone_angle, const int32_t* alive, const int32_t* state, float* t_starts,
+                                  float* t_ends, int64_t* ray_indices, uint8_t* overflow, void* stream);
+int cednerf_render_round_composite(const float* t_starts, const float* t_ends, const float* sigmas, const float* rgbs,
+                                   const int64_t* offsets, const int32_t* alive, int32_t* round_state,
+                                   const int32_t* slot_counts, int64_t n_bound, int k_hint, float early_stop_eps,
+                                   float* colors, float* opacity, float* depth, int32_t* alive_flags /*[n_bound]*/,
+                                   void* stream);
+/* ordered compaction of the flagged slots into the next round's list (positions = cednerf_exclusive_scan_capped of the
+ * flags): neighbouring lanes keep marching neighbouring pixels.  state[3] <- number of rays kept. */
+int cednerf_render_round_compact(const int32_t* alive_flags, const int64_t* positions, const int32_t* alive,
+                                 int64_t n_bound, int32_t* round_state, int32_t* next_alive, void* stream);
 /* nerfacc.accumulate_along_rays / accumulate_along_rays_ — cednerf/render.py:158-169, cednerf/utils.py:282-299 */
 int cednerf_accumulate_fwd(const float* weights, const float* values /*nullable*/, int n_channels,
                            const int64_t* offsets, int64_t n_samples, int64_t n_rays, float* outputs, int inplace,

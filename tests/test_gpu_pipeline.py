@@ -327,3 +327,33 @@ def test_device_count_sampling_matches_the_host_count_path(cb):
     torch.cuda.synchronize()
     est._capacity("visible")
     assert int(short[3]) < n and est.dropped_samples > 0
+
+
+def test_device_resident_render_rounds_match_the_host_driven_loop(cb):
+    """render_image_test with the alive list / per-round k / termination test on the device against the loop that reads
+    `alive.sum()` back every round (cednerf/utils.py:231): same image, same sample total - per ray the two paths do the
+    same arithmetic on the same samples, only the packing order of the rays inside a round differs."""
+    from cednerf_b200 import utils as U, workload as w
+
+    for cfg, opengl in ((w.TINY, False), (w.DNERF, True)):
+        rk = w.render_kwargs(cfg)
+        est, field = w.build_scene(cfg, DEV, cb, seed=42)
+        est.eval(), field.eval()
+        pose = w.orbit_pose(4.0, 0.3) if opengl else w.spiral_poses(cfg, 8)[3]
+        o, d = w.pose_rays(cfg, pose, opengl, DEV)
+        if cfg is w.DNERF:   # a 96 x 128 window of the 800 x 800 frame
+            sel = (torch.arange(352, 448, device=DEV)[:, None] * cfg.width + torch.arange(336, 464, device=DEV)[None, :]).reshape(-1)
+            o, d = o[sel].contiguous(), d[sel].contiguous()
+        rays = cb.Rays(o, d)
+        t = torch.tensor([[0.37]], device=DEV)
+        bk = torch.tensor([0.1, 0.6, 0.9], device=DEV)
+        outs = {}
+        for mode in (True, False):
+            U._DEVICE_ROUNDS = mode
+            try:
+                outs[mode] = cb.render_image_test(1024, field, est, rays, render_bkgd=bk, timestamps=t, **rk)
+            finally:
+                U._DEVICE_ROUNDS = True
+        assert outs[True][3] == outs[False][3] and outs[True][3] > 1000, (cfg.name, outs[True][3], outs[False][3])
+        for i in range(3):   # (the lane group per ray is picked differently: shuffle-scan order, i.e. fp32 rounding, differs)
+            torch.testing.assert_close(outs[True][i], outs[False][i], rtol=0, atol=2e-6)
