@@ -143,10 +143,9 @@ class OccupancyUpdate:
         self.twin.binaries, self.twin.occs = est.binaries.clone(), est.occs.clone()
         self.twin.train()
         self.field, self.step_size, self.step, self.updates, self.rng = field, step_size, 0, 0, rng
-
-    def occ_eval_fn(self, x):
-        t = self.rng.rand(x.shape[0], 1)
-        return self.field.query_density(x, t)["density"] * self.step_size
+        # the closure of train_real.py:324-328 as an object: called like a function it computes the same thing, and it
+        # lets this repo's estimator run each level of the update as one fused launch
+        self.occ_eval_fn = impl.utils.FieldOccEval(field, step_size, rng=rng)
 
     def __call__(self):
         if self.step % 16 == 0:
@@ -167,7 +166,8 @@ def train_step(impl, field, est, opt, scaler, batch, cfg, rk, reducer=None, sche
         return None, 0
     if hasattr(impl, "losses"):  # this repo: the same loss as one fused forward / backward launch
         loss = impl.losses.training_loss(rgb, acc, batch["pixels"], extra, acc_entropy_loss=True, weight_rgbper=True,
-                                         use_feat_predict=bool(cfg.flags.get("use_feat_predict")))
+                                         use_feat_predict=bool(cfg.flags.get("use_feat_predict")),
+                                         distortion_loss=cfg.name.startswith("hypernerf"))   # run_hyper.sh: -d
     else:
         loss = torch.nn.functional.mse_loss(rgb, batch["pixels"]) + aux_losses(rgb, acc, batch["pixels"], extra, cfg.flags)
     opt.zero_grad()
@@ -530,11 +530,11 @@ def render_leg(D, cb, workload, cfg, args, poses, times, opengl, bkgd, profile: 
     mine = dp.shard_interleaved(len(poses), rank, world)
     bk = torch.tensor(bkgd, dtype=torch.float32, device=dev)
     frames = [(poses[i].to(dev), torch.tensor([[float(times[i])]], device=dev)) for i in mine]
+    K = [[cfg.focal, 0.0, cfg.width / 2], [0.0, cfg.focal, cfg.height / 2], [0.0, 0.0, 1.0]]
 
     def render_one(k):
-        c2w, t = frames[k]   # pixel -> ray generation on the device, inside the timed region (gui.py:43-86 does it per frame)
-        o, d = workload.pose_rays(cfg, c2w, opengl)
-        rays = cb.Rays(o.view(cfg.height, cfg.width, 3), d.view(cfg.height, cfg.width, 3))
+        c2w, t = frames[k]   # pixel -> ray generation inside the timed region, one launch (gui.py:43-86 does it per frame)
+        rays = cb.utils.generate_rays(K, c2w, cfg.width, cfg.height, opengl)
         return cb.render_image_test(1024, field, est, rays, render_bkgd=bk, timestamps=t, **rk)[3]
 
     for k in range(min(2, len(frames))):

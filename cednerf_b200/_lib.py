@@ -96,6 +96,7 @@ _SIGNATURES = {
     "cednerf_mlp_fwd": "ppMlppp",
     "cednerf_mlp_bwd": "ppppMlpippp",
     "cednerf_field_fwd": "ppppppppilppppFpppp",
+    "cednerf_occ_update_level": "plpppiffpppFpppp",
     "cednerf_field_train_fwd": "ppppppilpppppFpppppppp",
     "cednerf_field_train_bwd": "ppppppilpppppFpppppppppppppipp",
     "cednerf_ray_offsets": "pllpp",
@@ -110,6 +111,9 @@ _SIGNATURES = {
     "cednerf_march_fill_runs_round": "lpppppiffppppppp",
     "cednerf_render_round_composite": "pppppppplifppppp",
     "cednerf_render_round_compact": "ppplppp",
+    "cednerf_generate_rays": "ppppiffffiilpppp",
+    "cednerf_distortion_fwd": "pppplpppp",
+    "cednerf_distortion_bwd": "pppplpppp",
     "cednerf_nonfinite_check": "App",
     "cednerf_training_loss_fwd": "ppplppplpiffpppp",
     "cednerf_training_loss_bwd": "pppplpppliffpppppp",

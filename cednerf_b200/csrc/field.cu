@@ -32,8 +32,18 @@ struct FieldFwdArgs {
   const uint8_t* img2;
   const uint8_t* img3;
   const __half* table;
-  float* sigma;   // [n]
+  float* sigma;   // [n] (nullable in cell mode)
   float* rgb;     // [n,3] or null (density only)
+  // cell mode (occupancy-grid update): sample s is one jittered point inside grid cell cells[s] (or s)
+  // of a level's R^3 grid and the result goes straight into the level's occupancy values
+  const int64_t* cells;   // nullable: cell ids (x R^2 + y R + z); null = cell s
+  const float* jitter;    // [n,3] in [0,1): position inside the cell
+  float cell_lo[3], cell_hi[3];
+  int cell_res;           // R; 0 = not in cell mode
+  int cell_update;        // 1: occs[c] = max(occs[c] * decay, occ) (every cell at most once); 2: atomic max into cand[c]
+  float occ_scale, occ_decay;
+  float* occs;            // the level's R^3 values (mode 1) or zero-initialised candidates (mode 2)
+  uint8_t* touched;       // mode 2: cells that received a candidate
   CednerfFieldDesc d;
 };
 
@@ -98,6 +108,18 @@ __global__ void __launch_bounds__(896, 1) field_fwd_kernel(FieldFwdArgs a) {
         for (int k = 0; k < 3; ++k)
           x[k] = __fadd_rn(a.rays_o[3 * r + k], __fmul_rn(__fmul_rn(a.rays_d[3 * r + k], tm), 0.5f));
         tv = a.t[r * a.t_stride];
+      } else if (a.cell_res) {
+        // x = aabb_lo + ((coord + jitter) / R) * (aabb_hi - aabb_lo): nerfacc's element-wise chain, op by op
+        const int64_t c = a.cells ? a.cells[s] : s;
+        const int R = a.cell_res;
+        const int cz = (int)(c % R), cy = (int)((c / R) % R), cx = (int)(c / ((int64_t)R * R));
+        const int cc[3] = {cx, cy, cz};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float u = __fdiv_rn(__fadd_rn((float)cc[k], a.jitter[3 * s + k]), (float)R);
+          x[k] = __fadd_rn(a.cell_lo[k], __fmul_rn(u, __fsub_rn(a.cell_hi[k], a.cell_lo[k])));
+        }
+        tv = a.t[s * a.t_stride];
       } else {
 #pragma unroll
         for (int k = 0; k < 3; ++k) x[k] = a.x[3 * s + k];
@@ -171,7 +193,20 @@ __global__ void __launch_bounds__(896, 1) field_fwd_kernel(FieldFwdArgs a) {
     uint32_t o2[16];
     tmem_ld16(tmem_warp, o2);
     tmem_ld_wait();
-    if (ok) a.sigma[s] = selector ? expf(rnd16(o2[0]) - 1.f) : 0.f;  // trunc_exp(raw - 1) * selector (model.py:414-417)
+    if (ok) {
+      const float sg = selector ? expf(rnd16(o2[0]) - 1.f) : 0.f;  // trunc_exp(raw - 1) * selector (model.py:414-417)
+      if (a.sigma) a.sigma[s] = sg;
+      if (a.cell_res) {  // occ = sigma * step;  occs = max(occs * decay, occ)   (nerfacc _update, train_real.py:324-336)
+        const int64_t c = a.cells ? a.cells[s] : s;
+        const float occ = __fmul_rn(sg, a.occ_scale);
+        if (a.cell_update == 1) {
+          a.occs[c] = fmaxf(__fmul_rn(a.occs[c], a.occ_decay), occ);
+        } else {  // duplicates possible: the largest candidate wins (non-negative floats order like their bit patterns)
+          atomicMax(reinterpret_cast<int*>(a.occs + c), __float_as_int(occ));
+          a.touched[c] = 1;
+        }
+      }
+    }
     if (!want_rgb) {
       tc_fence_before();
       group_sync(group);
@@ -273,12 +308,68 @@ CEDNERF_EXPORT int cednerf_field_fwd(const int64_t* ray_indices, const float* t_
   static CednerfOncePerDevice configured;
   if (int e = cednerf_opt_in_smem(field_fwd_kernel, 224 * 1024, configured, "cednerf_field_fwd")) return e;
   CEDNERF_REQUIRE(smem <= 224 * 1024, "networks too large for the fused kernel");
-  FieldFwdArgs a{ray_indices, t_starts, t_ends, rays_o, rays_d, x, dirs, timestamps, t_stride, n, n_device,
-                 (const uint8_t*)image_deform, (const uint8_t*)image_density, (const uint8_t*)image_colour,
-                 (const __half*)table_f16, sigma, rgb, *desc};
+  FieldFwdArgs a{};
+  a.ridx = ray_indices, a.t0 = t_starts, a.t1 = t_ends, a.rays_o = rays_o, a.rays_d = rays_d, a.x = x, a.dirs = dirs;
+  a.t = timestamps, a.t_stride = t_stride, a.n = n, a.n_dev = n_device;
+  a.img1 = (const uint8_t*)image_deform, a.img2 = (const uint8_t*)image_density, a.img3 = (const uint8_t*)image_colour;
+  a.table = (const __half*)table_f16, a.sigma = sigma, a.rgb = rgb, a.d = *desc;
   const int64_t tiles = (n + MLP_TILE - 1) / MLP_TILE;
   const int64_t ctas = tiles;  // tiles go round-robin over CTAs first, then over the groups of a CTA
   const int64_t max_ctas = (int64_t)cednerf_num_sms();
   field_fwd_kernel<<<(unsigned)(ctas < max_ctas ? ctas : max_ctas), n_groups * MLP_TILE, smem, (cudaStream_t)stream>>>(a);
   return cednerf_check_launch("cednerf_field_fwd");
+}
+
+namespace {
+__global__ void occ_finalize_kernel(float* __restrict__ occs, float* __restrict__ cand, uint8_t* __restrict__ touched,
+                                    int64_t n_cells, float decay) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cells || !touched[c]) return;
+  occs[c] = fmaxf(__fmul_rn(occs[c], decay), cand[c]);
+  cand[c] = 0.f;
+  touched[c] = 0;
+}
+}  // namespace
+
+// Occupancy-grid update of one level, fused (nerfacc OccGridEstimator._update as called at
+// train_real.py:324-336 with occ_eval_fn(x) = query_density(x, t)["density"] * step): n jittered points, one per entry of
+// `cells` (null: every cell of the level once, the warm-up case), are pushed through the deformation net, the hash
+// grid and the density net, and occs[cell] = max(occs[cell] * ema_decay, sigma * step) is written by the same kernel.
+// `cells` without duplicates: leave cand / touched null.  With duplicates (the uniform + occupied draws after the
+// warm-up) pass zero-initialised cand [R^3] and touched [R^3]: the largest candidate of a cell wins (what scatter-amax
+// gives), applied by a second small launch that also clears the two buffers again.
+CEDNERF_EXPORT int cednerf_occ_update_level(const int64_t* cells, int64_t n, const float* jitter, const float* timestamps,
+                                            const float* level_aabb, int resolution, float step_scale, float ema_decay,
+                                            const void* image_deform, const void* image_density, const void* table_f16,
+                                            const CednerfFieldDesc* desc, float* occs_level, float* cand, uint8_t* touched,
+                                            void* stream) {
+  CEDNERF_REQUIRE(check_field(desc, false), "bad field descriptor");
+  CEDNERF_REQUIRE(n >= 0 && jitter && timestamps && level_aabb && resolution > 0 && occs_level, "bad arguments");
+  CEDNERF_REQUIRE((cand == nullptr) == (touched == nullptr), "cand and touched go together");
+  CEDNERF_REQUIRE(cells || n <= (int64_t)resolution * resolution * resolution, "more points than cells");
+  if (n == 0) return 0;
+  const int n_groups = 7;
+  const int smem = desc->f1.image_bytes + desc->f2.image_bytes + n_groups * MLP_TILE_BYTES + 2048;
+  static CednerfOncePerDevice configured;
+  if (int e = cednerf_opt_in_smem(field_fwd_kernel, 224 * 1024, configured, "cednerf_occ_update_level")) return e;
+  CEDNERF_REQUIRE(smem <= 224 * 1024, "networks too large for the fused kernel");
+  FieldFwdArgs a{};
+  a.t = timestamps, a.t_stride = 1, a.n = n;
+  a.img1 = (const uint8_t*)image_deform, a.img2 = (const uint8_t*)image_density;
+  a.table = (const __half*)table_f16, a.d = *desc;
+  a.cells = cells, a.jitter = jitter, a.cell_res = resolution, a.cell_update = cand ? 2 : 1;
+  // level_aabb is a HOST array of 6 floats (the estimator's aabbs[level])
+  for (int k = 0; k < 3; ++k) a.cell_lo[k] = level_aabb[k], a.cell_hi[k] = level_aabb[3 + k];
+  a.occ_scale = step_scale, a.occ_decay = ema_decay, a.occs = cand ? cand : occs_level, a.touched = touched;
+  const int64_t tiles = (n + MLP_TILE - 1) / MLP_TILE;
+  const int64_t max_ctas = (int64_t)cednerf_num_sms();
+  cudaStream_t st = (cudaStream_t)stream;
+  field_fwd_kernel<<<(unsigned)(tiles < max_ctas ? tiles : max_ctas), n_groups * MLP_TILE, smem, st>>>(a);
+  int launches = 1;
+  if (cand) {
+    const int64_t n_cells = (int64_t)resolution * resolution * resolution;
+    occ_finalize_kernel<<<cednerf_blocks(n_cells, 256), 256, 0, st>>>(occs_level, cand, touched, n_cells, ema_decay);
+    ++launches;
+  }
+  return cednerf_check_launch("cednerf_occ_update_level", launches);
 }

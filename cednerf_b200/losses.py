@@ -63,13 +63,66 @@ class TrainingLossFunction(torch.autograd.Function):
 
 
 def training_loss(rgb, acc, pixels, extras, acc_entropy_loss: bool = True, weight_rgbper: bool = True,
-                  use_feat_predict: bool = True) -> torch.Tensor:
-    """`extras` is the list `render_image` returns (one dict per ray chunk; training renders the batch as one chunk)."""
+                  use_feat_predict: bool = True, distortion_loss: bool = False) -> torch.Tensor:
+    """`extras` is the list `render_image` returns (one dict per ray chunk; training renders the batch as one chunk).
+    distortion_loss: + 1e-3 * distortion(ray_indices, weights, t_starts, t_ends) (the `-d` flag, train_real.py:380-386)."""
     if len(extras) != 1:
         raise ValueError("training_loss fuses the one-chunk case of a training batch (render_image in training mode)")
     ex = extras[0]
     latent = ex.get("latent_losses") if use_feat_predict else None
     counts = counts_of(ex["ray_indices"])   # capacity-sized sample set: the live count stays on the device
+    if distortion_loss:
+        return _fused_terms(rgb, acc, pixels, ex, latent, counts, acc_entropy_loss, weight_rgbper) + 1e-3 * distortion(
+            ex["ray_indices"], ex["weights"], ex["t_starts"], ex["t_ends"], n_rays=rgb.shape[0])
     return TrainingLossFunction.apply(rgb, acc if acc_entropy_loss else None, pixels,
                                       ex["rgbs"] if weight_rgbper else None, ex["weights"].detach(), ex["ray_indices"],
                                       latent, 1e-3, 1e-3, None if counts is None else counts[1])
+
+
+def _fused_terms(rgb, acc, pixels, ex, latent, counts, acc_entropy_loss, weight_rgbper):
+    return TrainingLossFunction.apply(rgb, acc if acc_entropy_loss else None, pixels,
+                                      ex["rgbs"] if weight_rgbper else None, ex["weights"].detach(), ex["ray_indices"],
+                                      latent, 1e-3, 1e-3, None if counts is None else counts[1])
+
+
+class DistortionFunction(torch.autograd.Function):
+    """flatten_eff_distloss(weights, mid-points, interval lengths, ray ids) of packed samples; gradient w.r.t. weights."""
+
+    @staticmethod
+    def forward(ctx, weights, t_starts, t_ends, offsets, n_rays):
+        w, t0, t1 = _f32c(weights).view(-1), _f32c(t_starts).view(-1), _f32c(t_ends).view(-1)
+        dev = w.device
+        work = torch.empty(2, dtype=F64, device=dev)
+        loss = torch.empty(1, dtype=F32, device=dev)
+        inv = torch.empty(1, dtype=F32, device=dev)
+        call("cednerf_distortion_fwd", ptr(w), ptr(t0), ptr(t1), ptr(offsets), int(n_rays), ptr(work), ptr(loss), ptr(inv),
+             stream())
+        ctx.save_for_backward(w, t0, t1, offsets, inv)
+        ctx.n_rays, ctx.shape = int(n_rays), weights.shape
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        w, t0, t1, offsets, inv = ctx.saved_tensors
+        g = g.detach().to(F32).reshape(1).contiguous()
+        gw = torch.zeros_like(w)
+        call("cednerf_distortion_bwd", ptr(w), ptr(t0), ptr(t1), ptr(offsets), ctx.n_rays, ptr(g), ptr(inv), ptr(gw), stream())
+        return gw.view(ctx.shape), None, None, None, None
+
+
+def distortion(ray_ids, weights, t_starts, t_ends, n_rays=None):
+    """cednerf/losses.py:4-11 (the `-d` flag of the HyperNeRF recipe, train_real.py:380-386): the distortion regulariser
+    of Mip-NeRF 360 in its O(N) form (torch_efficient_distloss.flatten_eff_distloss).  `ray_ids` sorted, as the sampler
+    emits them.  n_rays: number of rays of the batch (only sizes the per-ray launch; the loss is normalised by
+    ray_ids.max() + 1 as in the package).  With capacity-sized inputs (ops.counts_of) the live prefix is used."""
+    from . import ops
+
+    counts = counts_of(ray_ids)
+    if counts is not None:
+        offsets = counts[0]
+        n_rays = offsets.numel() - 1
+    else:
+        if n_rays is None:
+            n_rays = int(ray_ids.max()) + 1 if ray_ids.numel() else 0
+        offsets = ops.ray_offsets(ray_ids, n_rays)
+    return DistortionFunction.apply(weights, t_starts, t_ends, offsets, n_rays)

@@ -31,6 +31,7 @@ class OccGridEstimator(torch.nn.Module):
         self._occ_mean_key, self._occ_mean = None, 0.0
         self._may_have_invisible, self._occs_seen = False, None  # occs = -1 cells exist (mark_invisible_cells, checkpoints)
         self._cap_state, self.dropped_samples = {}, 0  # sampling(..., device_counts=True)
+        self._aabbs_host, self._occ_cand, self._occ_touched = None, None, None  # fused occupancy update
 
     def _load_from_state_dict(self, *args, **kwargs):
         self._occs_seen = None  # contents replaced in place: look again at the next update
@@ -193,6 +194,43 @@ class OccGridEstimator(torch.nn.Module):
         if step % n == 0:
             self._update(step, occ_eval_fn, occ_thre, ema_decay, warmup_steps, rng)
 
+    def _fused_occ_eval(self, occ_eval_fn):
+        """The FieldOccEval behind `occ_eval_fn` when its field can run the fused occupancy update, else None."""
+        from ...utils import FieldOccEval
+
+        if not isinstance(occ_eval_fn, FieldOccEval):
+            return None
+        f = occ_eval_fn.field
+        ok = getattr(f, "fused_supported", lambda: False)() and self.occs.is_cuda and self.occs.dtype == torch.float32
+        return occ_eval_fn if ok else None
+
+    def _update_level_fused(self, l: int, idx, fn, rand, ema_decay: float, unique: bool):
+        """One level of `_update` in one launch (cednerf_occ_update_level); draws in the order of the op-by-op path."""
+        import ctypes
+
+        dev, cpl = self.device, self.cells_per_lvl
+        n = cpl if idx is None else int(idx.numel())
+        if n == 0:
+            return
+        jitter = rand(n, 3).to(dev).float().contiguous()
+        tt = fn.rand_t(n, dev).float().contiguous().view(-1)
+        f = fn.field
+        if self._aabbs_host is None or self._aabbs_host[0] != (self.aabbs.data_ptr(), self.aabbs._version):
+            self._aabbs_host = ((self.aabbs.data_ptr(), self.aabbs._version), self.aabbs.cpu().tolist())  # one host read
+        box = (ctypes.c_float * 6)(*self._aabbs_host[1][l])
+        cells = None if idx is None else idx.to(torch.int64).contiguous()
+        cand = touched = None
+        if not unique:
+            if self._occ_cand is None or self._occ_cand.device != dev:
+                self._occ_cand = torch.zeros(cpl, device=dev)
+                self._occ_touched = torch.zeros(cpl, dtype=torch.uint8, device=dev)
+            cand, touched = self._occ_cand, self._occ_touched
+        lvl = self.occs[l * cpl:(l + 1) * cpl]
+        ops.call("cednerf_occ_update_level", ops.ptr(cells), n, ops.ptr(jitter), ops.ptr(tt), box, int(self.binaries.shape[1]),
+                 float(fn.step), float(ema_decay), ops.ptr(f.xyz_wrap.network.weight_image()), ops.ptr(f.mlp_base.weight_image()),
+                 ops.ptr(f.hash_encoder.table_f16()), ctypes.byref(f._field_desc()), ops.ptr(lvl), ops.ptr(cand),
+                 ops.ptr(touched), ops.stream())
+
     @torch.no_grad()
     def _update(self, step, occ_eval_fn, occ_thre=1e-2, ema_decay=0.95, warmup_steps=256, rng=None):
         """SURVEY.md Appendix A.2.  `rng` (randint(high, n), rand(*shape)) lets parity tests share draws."""
@@ -220,7 +258,11 @@ class OccGridEstimator(torch.nn.Module):
                 if k < len(occ_idx):
                     occ_idx = occ_idx[randint(len(occ_idx), k).to(dev)]
                 lvl_indices.append(torch.cat([uni, occ_idx]))
+        fused = self._fused_occ_eval(occ_eval_fn)
         for l, idx in enumerate(lvl_indices):
+            if fused is not None:
+                self._update_level_fused(l, idx, fused, rand, ema_decay, unique=step < warmup_steps)
+                continue
             coords = self.grid_coords if idx is None else self.grid_coords[idx]
             x = (coords.float() + rand(coords.shape[0], 3).to(dev)) / self.resolution.float()
             x = self.aabbs[l, :3] + x * (self.aabbs[l, 3:] - self.aabbs[l, :3])

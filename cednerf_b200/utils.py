@@ -25,6 +25,60 @@ def set_random_seed(seed):
     torch.manual_seed(seed)
 
 
+def generate_rays(K, c2w, width: int, height: int, opengl: bool = False, x=None, y=None, image_id=None,
+                  return_directions: bool = False):
+    """Pixel -> ray generation of the reference's datasets (datasets/dnerf_3d_video_IS.py:330-358,
+    datasets/dnerf_synthetic.py:196-224, gui.py:43-86) in one launch.  K: 3x3 intrinsics (host tensor / nested list);
+    c2w: [n_cams, 3|4, 4] (or one [3|4, 4] pose) on the device.  Without x / y: every pixel of one frame, row-major
+    (origins / viewdirs shaped [height, width, 3]); with them: one ray per (x[i], y[i], image_id[i])."""
+    import ctypes  # noqa: F401
+
+    from ._lib import call, ptr, stream
+
+    c2w = c2w if c2w.dim() == 3 else c2w[None]
+    c2w = ops._f32c(c2w)
+    Kh = torch.as_tensor(K, dtype=torch.float32).cpu()
+    fx, fy, cx, cy = float(Kh[0, 0]), float(Kh[1, 1]), float(Kh[0, 2]), float(Kh[1, 2])
+    dev = c2w.device
+    if x is None:
+        n = int(width) * int(height)
+        px = py = cam = None
+    else:
+        px, py = x.to(dev, torch.int64).contiguous(), y.to(dev, torch.int64).contiguous()
+        cam = None if image_id is None else image_id.to(dev, torch.int64).contiguous()
+        n = px.numel()
+    o, d = torch.empty(n, 3, device=dev), torch.empty(n, 3, device=dev)
+    dirs = torch.empty(n, 3, device=dev) if return_directions else None
+    call("cednerf_generate_rays", ptr(px), ptr(py), ptr(cam), ptr(c2w), int(c2w.shape[1]), fx, fy, cx, cy, int(width),
+         int(bool(opengl)), n, ptr(o), ptr(d), ptr(dirs), stream())
+    if x is None:
+        o, d = o.view(height, width, 3), d.view(height, width, 3)
+        dirs = None if dirs is None else dirs.view(height, width, 3)
+    return (Rays(o, d), dirs) if return_directions else Rays(o, d)
+
+
+class FieldOccEval:
+    """occ_eval_fn of the reference's training loop (train_real.py:324-328) as an object:
+
+        occ_eval_fn = FieldOccEval(radiance_field, render_step_size)
+        estimator.update_every_n_steps(step=step, occ_eval_fn=occ_eval_fn, occ_thre=1e-2)
+
+    Called like the reference's closure it returns query_density(x, rand_t)["density"] * render_step_size.  Handed to
+    cednerf_b200's OccGridEstimator it additionally lets `_update` run each level as ONE launch (cell -> jittered point
+    -> field -> EMA-max, csrc/field.cu::cednerf_occ_update_level) instead of the fused density kernel plus ~10 element-wise
+    launches per level.  `rng` (randint(high, n), rand(*shape)): the source of the random timestamps (default torch.rand);
+    dp.SharedRng keeps data-parallel replicas identical."""
+
+    def __init__(self, field, render_step_size: float, rng=None):
+        self.field, self.step, self.rng = field, float(render_step_size), rng
+
+    def rand_t(self, n: int, device):
+        return torch.rand(n, 1, device=device) if self.rng is None else self.rng.rand(n, 1).to(device)
+
+    def __call__(self, x):
+        return self.field.query_density(x, self.rand_t(x.shape[0], x.device))["density"] * self.step
+
+
 def _field_fns(field, rays, timestamps):
     def positions_of(t0, t1, ridx):
         o, d = rays.origins[ridx], rays.viewdirs[ridx]

@@ -182,6 +182,18 @@ int cednerf_field_fwd(const int64_t* ray_indices, const float* t_starts, const f
                       const void* table_f16, const CednerfFieldDesc* desc, float* sigma, float* rgb,
                       const int64_t* n_device /*nullable: live sample count on the device, n = capacity*/, void* stream);
 
+/* Occupancy-grid update of one level, fused (nerfacc OccGridEstimator._update as the reference calls
+ * it, train_real.py:324-336, occ_eval_fn(x) = query_density(x, t)["density"] * render_step_size): one jittered point per
+ * entry of `cells` (NULL: every cell of the level once - the warm-up case) goes through deformation net, hash grid and
+ * density net, and occs_level[cell] = max(occs_level[cell] * ema_decay, sigma * step_scale) is written by the same
+ * kernel.  level_aabb: HOST array of 6 floats.  Cells with duplicates: pass zero-initialised cand [R^3] and touched [R^3]
+ * (the largest candidate wins, as scatter-amax; both come back cleared). */
+int cednerf_occ_update_level(const int64_t* cells /*nullable*/, int64_t n, const float* jitter /*[n,3]*/,
+                             const float* timestamps /*[n]*/, const float* level_aabb /*host, [6]*/, int resolution,
+                             float step_scale, float ema_decay, const void* image_deform, const void* image_density,
+                             const void* table_f16, const CednerfFieldDesc* desc, float* occs_level,
+                             float* cand /*nullable*/, uint8_t* touched /*nullable*/, void* stream);
+
 /* DNGPradianceField.forward in training (cednerf/model.py:468-488, return_interal=True) on packed ray samples, and its
  * backward.  `saved` (cednerf_field_saved_bytes) carries the activations; the backward accumulates into the fp32
  * parameter gradients (tcnn flat layout) and the fp32 hash-table gradient (caller zeroes), using `work`
@@ -359,6 +371,23 @@ int cednerf_training_loss_bwd(const float* g_loss, const float* rgb, const float
                               const float* rgbs, const float* weights, const int64_t* ray_indices, int64_t n_samples,
                               int n_latent, float w_entropy, float w_rgbper, float* d_rgb, float* d_acc, float* d_rgbs,
                               float* d_latent, const int64_t* n_device /*nullable*/, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * The steps either side of the hot path.
+ * Pixel -> ray generation (datasets/dnerf_3d_video_IS.py:330-358, datasets/dnerf_synthetic.py:196-224): camera_dirs =
+ * [(x - cx + 0.5) / fx, (y - cy + 0.5) / fy * s, s], s = -1 for OpenGL cameras; directions = R camera_dirs; viewdirs =
+ * directions / |directions|; origins = translation.  px / py nullable (ray i = pixel (i % width, i / width)); cam nullable
+ * (pose index per ray into c2w [n_cams, c2w_rows, 4]); directions nullable. */
+int cednerf_generate_rays(const int64_t* px, const int64_t* py, const int64_t* cam, const float* c2w, int c2w_rows,
+                          float fx, float fy, float cx, float cy, int width, int opengl, int64_t n, float* origins,
+                          float* viewdirs, float* directions, void* stream);
+/* Distortion loss (cednerf/losses.py:4-11 = torch_efficient_distloss.flatten_eff_distloss on weights, interval
+ * mid-points and lengths) of packed samples: sum_rays sum_i [d_i w_i^2 / 3 + 2 w_i (m_i W_i - M_i)] / (max ray + 1).
+ * work: 16 bytes; loss, inv_rays: one float each (inv_rays feeds the backward).  Gradient w.r.t. the weights only. */
+int cednerf_distortion_fwd(const float* weights, const float* t_starts, const float* t_ends, const int64_t* offsets,
+                           int64_t n_rays, void* work, float* loss, float* inv_rays, void* stream);
+int cednerf_distortion_bwd(const float* weights, const float* t_starts, const float* t_ends, const int64_t* offsets,
+                           int64_t n_rays, const float* g_loss, const float* inv_rays, float* g_weights, void* stream);
 
 #ifdef __cplusplus
 }

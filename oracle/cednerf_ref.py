@@ -271,3 +271,39 @@ def render_image_test(max_samples, field, estimator, rays, near_plane=0.0, far_p
     rgb = rgb + render_bkgd * (1.0 - opacity)
     depth = depth / opacity.clamp_min(torch.finfo(torch.float32).eps)
     return rgb.view(*shape[:-1], -1), opacity.view(*shape[:-1], -1), depth.view(*shape[:-1], -1), total
+
+
+def distortion(ray_ids, weights, t_starts, t_ends):
+    """cednerf/losses.py:4-11: flatten_eff_distloss(w, mid-points, interval lengths, ray ids) of the third-party package
+    torch_efficient_distloss (not vendored, version un-pinned in the reference; algorithm: Sun et al., "Improved Direct
+    Voxel Grid Optimization", 2022, eq. 12-14 - the O(N) form of Mip-NeRF 360's distortion loss):
+        L = [ sum_i d_i w_i^2 / 3 + 2 sum_i w_i (m_i W_i - M_i) ] / (ray_ids.max() + 1)
+    with W_i / M_i the exclusive prefix sums of w and w m inside sample i's ray.  fp64; autograd gives d/dw."""
+    w = weights.reshape(-1).double()
+    t0, t1 = t_starts.reshape(-1).double(), t_ends.reshape(-1).double()
+    if w.numel() == 0:
+        return w.sum()
+    m, d = (t0 + t1) / 2, t1 - t0
+    n_rays = int(ray_ids.max()) + 1
+    first = torch.ones_like(ray_ids, dtype=torch.bool)
+    first[1:] = ray_ids[1:] != ray_ids[:-1]
+    start = torch.cummax(torch.where(first, torch.arange(w.numel()), torch.zeros_like(ray_ids)), 0)[0]
+    cw, cwm = torch.cumsum(w, 0), torch.cumsum(w * m, 0)
+    base_w = torch.cat([w.new_zeros(1), cw])[start]      # cumulative sums just before the ray's first sample
+    base_wm = torch.cat([w.new_zeros(1), cwm])[start]
+    W, M = cw - w - base_w, cwm - w * m - base_wm
+    return ((d * w * w / 3).sum() + (2 * w * (m * W - M)).sum()) / n_rays
+
+
+def distortion_bruteforce(ray_ids, weights, t_starts, t_ends):
+    """The definition the O(N) form is derived from (Barron et al., Mip-NeRF 360, eq. 15, per ray):
+    sum_ij w_i w_j |m_i - m_j| + sum_i w_i^2 d_i / 3, summed over rays and divided by ray_ids.max() + 1."""
+    w = weights.reshape(-1).double()
+    m = ((t_starts.double() + t_ends.double()) / 2).reshape(-1)
+    d = (t_ends.double() - t_starts.double()).reshape(-1)
+    total = w.new_zeros(())
+    for r in ray_ids.unique().tolist():
+        k = ray_ids == r
+        wr, mr, dr = w[k], m[k], d[k]
+        total = total + (wr[:, None] * wr[None, :] * (mr[:, None] - mr[None, :]).abs()).sum() + (wr * wr * dr / 3).sum()
+    return total / (int(ray_ids.max()) + 1)

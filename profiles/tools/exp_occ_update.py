@@ -1,30 +1,31 @@
-#!/usr/bin/env python
-"""Diagnostic (GPU): cost of OccGridEstimator._update on the bench scene (warm-up step: all cells; later: R^3/4 + occupied)."""
-import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-import torch
+"""Time of one warm-up occupancy update (4 x 128^3 cells, 8.4 M field queries): fused per-level launch vs closure."""
+import sys, torch
+sys.path.insert(0,'/root/repo')
 import cednerf_b200 as cb
-from cednerf_b200 import workload as W, _lib
-
-cfg, dev = W.DYNERF, torch.device("cuda:0")
-est, fld = W.build_scene(cfg, dev, cb)
-fld.train(); est.train()
-
-
-def occ_eval_fn(x):  # train_real.py:324-328
-    t = torch.rand(x.shape[0], 1, device=x.device)
-    with torch.no_grad():
-        return fld.query_density(x, t)["density"] * cfg.render_step_size
-
-
-for step in (0, 1024):
-    for rep in range(3):
-        torch.cuda.synchronize(); l0 = _lib.launch_count(); t0 = time.perf_counter()
-        est._update(step, occ_eval_fn)
+from cednerf_b200 import workload as w, dp
+DEV=torch.device('cuda:0')
+cfg=w.DYNERF; rk=w.render_kwargs(cfg)
+est, field = w.build_scene(cfg,DEV,cb,seed=42); est.train(); field.train()
+rng=dp.SharedRng(1,DEV)
+fused=cb.utils.FieldOccEval(field, rk['render_step_size'], rng=rng)
+plain=lambda x: field.query_density(x, rng.rand(x.shape[0],1))['density']*rk['render_step_size']
+for name,fn in (('closure',plain),('FieldOccEval',fused)):
+    for step in (0,256):
+        for _ in range(2): est._update(step, fn, rng=rng)
         torch.cuda.synchronize()
-        print(f"step {step}: {(time.perf_counter() - t0) * 1e3:.2f} ms, {_lib.launch_count() - l0} library launches")
-if len(sys.argv) > 1:
-    from torch.profiler import profile, ProfilerActivity
-    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-        est._update(1024, occ_eval_fn); torch.cuda.synchronize()
-    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))
+        e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
+        l0=cb._lib.launch_count()
+        e0.record()
+        for _ in range(5): est._update(step, fn, rng=rng)
+        e1.record(); torch.cuda.synchronize()
+        print(f"{name:14s} step {step:3d}: {e0.elapsed_time(e1)/5:.3f} ms per update, {(cb._lib.launch_count()-l0)//5} library launches")
+import bench
+from cednerf_b200 import _lib
+with bench.Instrument(cb,_lib) as ins:
+    est._update(0, fused, rng=rng); torch.cuda.synchronize()
+for name,a,s,e in ins.rec: print(name, round(s.elapsed_time(e),3))
+e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(4): j=rng.rand(128**3,3); t=rng.rand(128**3,1)
+e1.record(); torch.cuda.synchronize(); print('rand for 4 levels', e0.elapsed_time(e1))
+e0.record(); m=est.occs.mean(); e1.record(); torch.cuda.synchronize(); print('mean', e0.elapsed_time(e1))

@@ -357,3 +357,37 @@ def test_device_resident_render_rounds_match_the_host_driven_loop(cb):
         assert outs[True][3] == outs[False][3] and outs[True][3] > 1000, (cfg.name, outs[True][3], outs[False][3])
         for i in range(3):   # (the lane group per ray is picked differently: shuffle-scan order, i.e. fp32 rounding, differs)
             torch.testing.assert_close(outs[True][i], outs[False][i], rtol=0, atol=2e-6)
+
+
+def test_fused_occupancy_update_matches_the_op_by_op_update(cb):
+    """OccGridEstimator._update with a FieldOccEval (one launch per level: cell -> jittered point -> field -> EMA-max,
+    cednerf_occ_update_level) against the same update driven by a plain closure (element-wise torch glue around the
+    fused density kernel), draws shared through seeded generators: bit-identical occs and binaries, in the warm-up
+    (every cell once) and afterwards (uniform + occupied draws with duplicate cells)."""
+    from cednerf_b200 import dp, workload as w
+
+    cfg = w.TINY
+    rk = w.render_kwargs(cfg)
+    _, field = w.build_scene(cfg, DEV, cb, seed=42)
+    field.eval()
+    ests = [cb.OccGridEstimator(list(cfg.roi_aabb), resolution=cfg.occ_res, levels=cfg.occ_levels).to(DEV).train()
+            for _ in range(2)]
+    rng_a, rng_b = dp.SharedRng(99, DEV), dp.SharedRng(99, DEV)
+    fused_fn = cb.utils.FieldOccEval(field, rk["render_step_size"], rng=rng_a)
+
+    def plain_fn(x):   # what train_real.py:324-328 writes
+        return field.query_density(x, rng_b.rand(x.shape[0], 1))["density"] * rk["render_step_size"]
+
+    launches = []
+    for step in (0, 16, 32, 256, 272, 288):
+        l0 = cb._lib.launch_count()
+        ests[0].update_every_n_steps(step, fused_fn, occ_thre=1e-2, rng=rng_a)
+        launches.append(cb._lib.launch_count() - l0)
+        ests[1].update_every_n_steps(step, plain_fn, occ_thre=1e-2, rng=rng_b)
+        assert torch.equal(ests[0].occs, ests[1].occs), step
+        assert torch.equal(ests[0].binaries, ests[1].binaries), step
+    assert bool(ests[0].binaries.any()) and float(ests[0].occs.max()) > 0
+    assert launches[1] == cfg.occ_levels + 1          # one fused launch per level + threshold / pack (images cached)
+    # the reference's calling convention still works with the object
+    x = torch.rand(100, 3, device=DEV)
+    assert fused_fn(x).shape == (100, 1)

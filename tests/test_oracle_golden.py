@@ -109,3 +109,28 @@ def test_render_paths(golden, name):
     for a, k in ((rgb, "rgb"), (acc, "acc"), (depth, "depth")):
         torch.testing.assert_close(a, golden[f"{name}.test.{k}"], rtol=1e-6, atol=1e-7)
     assert float(acc.max()) > 0.5  # the synthetic density really occludes
+
+
+def test_distortion_restatement_against_its_definition():
+    """torch_efficient_distloss is not vendored: the O(N) restatement is pinned to the loss it implements (Mip-NeRF 360
+    eq. 15, the O(N^2) double sum) on random packed samples with sorted mid-points, value and gradient."""
+    g = torch.Generator().manual_seed(4)
+    counts = torch.randint(0, 9, (40,), generator=g)
+    counts[-3:] = 0                                    # trailing empty rays: n_rays of the loss = last ray with samples + 1
+    ray_ids = torch.repeat_interleave(torch.arange(40), counts)
+    n = ray_ids.numel()
+    dt = torch.rand(n, generator=g) * 0.1 + 0.01
+    t0 = torch.zeros(n)
+    for r in range(40):   # consecutive, sorted intervals inside every ray
+        k = torch.nonzero(ray_ids == r).flatten()
+        if k.numel():
+            t0[k] = 0.3 + torch.cumsum(dt[k], 0) - dt[k]
+    t1 = t0 + dt * 0.8
+    w = torch.rand(n, generator=g).double().requires_grad_(True)
+    a = cr.distortion(ray_ids, w, t0, t1)
+    (ga,) = torch.autograd.grad(a, w)
+    w2 = w.detach().clone().requires_grad_(True)
+    b = cr.distortion_bruteforce(ray_ids, w2, t0, t1)
+    (gb,) = torch.autograd.grad(b, w2)
+    torch.testing.assert_close(a, b, rtol=1e-12, atol=1e-14)
+    torch.testing.assert_close(ga, gb, rtol=1e-10, atol=1e-13)
