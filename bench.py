@@ -67,6 +67,8 @@ def parse():
                     help="read the sample totals back to the host inside the step (the reference's behaviour) instead "
                          "of the capacity mode that keeps them on the device")
     ap.add_argument("--dp", default="peer", choices=["peer", "nccl"], help="multi-GPU optimiser step")
+    ap.add_argument("--dp-transport", default="auto", choices=["auto", "nvls", "p2p"],
+                    help="peer-memory DP: reduce / broadcast inside the NVSwitch (multimem) or by peer loads / stores")
     ap.add_argument("--torch-profile", default="", help="write a torch.profiler kernel table of one step to this file")
     return ap.parse_args()
 
@@ -394,6 +396,8 @@ def train_leg(D, cb, workload, cfg, args, n_rays, steps, warmup, full: bool):
             ok.zero_()
         D.dist.all_reduce(ok, op=D.dist.ReduceOp.MIN)
         dp_mode = "peer" if float(ok.item()) == 1.0 else "nccl"
+        if dp_mode == "peer" and args.dp_transport != "auto":
+            opt.nvls = args.dp_transport == "nvls"
     if world > 1 and dp_mode != "peer":
         dp_mode = "nccl"
         opt = cb.optim.FusedAdam(field.parameters(), lr=1e-2, eps=1e-15)
@@ -509,6 +513,7 @@ def train_leg(D, cb, workload, cfg, args, n_rays, steps, warmup, full: bool):
             with open(args.torch_profile, "w") as f:
                 f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=70))
     if dp_mode == "peer":
+        out["dp_mode"] = "peer/" + opt.transport()
         out["dp_timed_out"] = bool(opt.timed_out())
         opt.close()
     if reducer is not None:
@@ -620,8 +625,8 @@ def run_ours(args):
                        "sample_counts": ("host reads (reference behaviour)" if args.host_counts else
                                          f"device-side, capacity mode; {t['dropped']} samples dropped"),
                        "parallelism": ("single" if world == 1 else
-                                       f"dp{world}, optimiser step: " + ("fused reduce-scatter+Adam+all-gather over NVLink peer memory"
-                                                                        if t["dp_mode"] == "peer" else "NCCL all-reduce + Adam"))},
+                                       f"dp{world}, optimiser step: " + (f"fused reduce-scatter+Adam+all-gather over NVLink peer memory ({t['dp_mode']})"
+                                                                        if t["dp_mode"].startswith("peer") else "NCCL all-reduce + Adam"))},
             "e2e": {"value": round(rays_all / (t["ms_e2e"] * 1e-3), 1), "unit": "rays/s", "ms_per_step": round(t["ms_e2e"], 4),
                     "h2d_bytes_per_step": t["h2d"], "d2h_bytes_per_step": 4},
             "gpu_launches": t["launches"], "clocks": t["clocks"], "roofline": t.get("roofline")})

@@ -64,7 +64,14 @@ class DpAdam(ctypes.Structure):
                 ("n_out", ctypes.c_int), ("p32_out", ctypes.c_void_p * DP_MAX_RANKS),
                 ("p16_out", ctypes.c_void_p * DP_MAX_RANKS), ("m", ctypes.c_void_p), ("v", ctypes.c_void_p),
                 ("lo", ctypes.c_int64), ("hi", ctypes.c_int64), ("lr", ctypes.c_float), ("weight_decay", ctypes.c_float),
-                ("grad_div", ctypes.c_float)]
+                ("grad_div", ctypes.c_float), ("grad_mc", ctypes.c_void_p), ("p16_mc", ctypes.c_void_p)]
+
+
+class DpSmall(ctypes.Structure):
+    _fields_ = [("world", ctypes.c_int), ("n_tensors", ctypes.c_int), ("grad", ctypes.c_void_p * DP_MAX_RANKS),
+                ("p", ctypes.c_void_p * 8), ("m", ctypes.c_void_p * 8), ("v", ctypes.c_void_p * 8),
+                ("off", ctypes.c_int64 * 8), ("n", ctypes.c_int64 * 8), ("lr", ctypes.c_float * 8),
+                ("weight_decay", ctypes.c_float * 8), ("grad_div", ctypes.c_float), ("chunk_begin", ctypes.c_int64 * 9)]
 
 
 # p = pointer, i = int, l = int64, f = float, A = AdamTensors*, G = GridLevels*, M = MlpDesc*, F = FieldDesc*
@@ -126,10 +133,12 @@ _SIGNATURES = {
     "cednerf_dp_barrier": "Puip",
     "cednerf_dp_found_inf": "Pppp",
     "cednerf_dp_adam": "Dpppfffip",
+    "cednerf_dp_adam_small": "Spppfffip",
 }
 _CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_int64, "f": ctypes.c_float,
        "G": ctypes.POINTER(GridLevels), "M": ctypes.POINTER(MlpDesc), "F": ctypes.POINTER(FieldDesc),
-       "A": ctypes.POINTER(AdamTensors), "P": ctypes.POINTER(DpPeers), "D": ctypes.POINTER(DpAdam), "u": ctypes.c_uint32}
+       "A": ctypes.POINTER(AdamTensors), "P": ctypes.POINTER(DpPeers), "D": ctypes.POINTER(DpAdam), "S": ctypes.POINTER(DpSmall),
+       "u": ctypes.c_uint32}
 
 _lib = None
 

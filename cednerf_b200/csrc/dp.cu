@@ -49,6 +49,29 @@ struct CednerfDpAdam {
   float* v;
   int64_t lo, hi;                   // owned element range; lo is a multiple of 4
   float lr, weight_decay, grad_div; // the summed gradient is divided by grad_div (world for an average)
+  // NVLink SHARP (NVLS), when the buffers are multicast-mapped (torch symmetric memory): grad_mc = the multicast address of
+  // the gradient buffers - one multimem.ld_reduce returns the sum over all ranks, formed inside the switch; p16_mc = the
+  // multicast address of the fp16 working copies - one multimem.st updates every replica.  Both nullable.
+  const float* grad_mc;
+  void* p16_mc;
+};
+
+// The small (MLP) parameter tensors of a step in ONE launch: every rank sums every peer's copy of the staged gradients in
+// rank order (bit-identical replicas without a broadcast) and applies Adam to its own replica.
+#define DP_SMALL_MAX 8
+#define DP_SMALL_CHUNK 1024
+struct CednerfDpSmall {
+  int world, n_tensors;
+  const float* grad[DP_MAX_RANKS];   // every rank's staging region of the small gradients (same layout), as mapped here
+  float* p[DP_SMALL_MAX];            // this rank's parameters, moments
+  float* m[DP_SMALL_MAX];
+  float* v[DP_SMALL_MAX];
+  int64_t off[DP_SMALL_MAX];         // element offset of the tensor's gradient inside the staging region
+  int64_t n[DP_SMALL_MAX];
+  float lr[DP_SMALL_MAX];
+  float weight_decay[DP_SMALL_MAX];
+  float grad_div;
+  int64_t chunk_begin[DP_SMALL_MAX + 1];  // scratch, filled by the library
 };
 
 namespace {
@@ -189,6 +212,85 @@ __global__ void __launch_bounds__(256) dp_adam_kernel(CednerfDpAdam a, const flo
     }
   }
   __threadfence_system();  // the replica stores are performed before this rank's next barrier signal
+}
+
+__global__ void __launch_bounds__(256) dp_adam_small_kernel(CednerfDpSmall a, const float* step, const float* scale_p,
+                                                            const float* found_inf, float b1, float b2, float eps, int adamw) {
+  if (found_inf && *found_inf != 0.f) return;
+  int k = 0;
+  while (k + 1 < a.n_tensors && (int64_t)blockIdx.x >= a.chunk_begin[k + 1]) ++k;
+  const int64_t base = ((int64_t)blockIdx.x - a.chunk_begin[k]) * DP_SMALL_CHUNK;
+  const float inv_scale = scale_p ? 1.f / *scale_p : 1.f;
+  const float g_mul = a.grad_div != 1.f ? inv_scale / a.grad_div : inv_scale;
+  const float st = *step;
+  const float bc1 = 1.f - powf(b1, st), bc2_sqrt = sqrtf(1.f - powf(b2, st));
+  for (int64_t i = base + threadIdx.x; i < a.n[k] && i < base + DP_SMALL_CHUNK; i += 256) {
+    float x[DP_MAX_RANKS];
+#pragma unroll
+    for (int r = 0; r < DP_MAX_RANKS; ++r) x[r] = r < a.world ? __ldcs(a.grad[r] + a.off[k] + i) : 0.f;  // all in flight
+    float g = x[0];
+#pragma unroll
+    for (int r = 1; r < DP_MAX_RANKS; ++r)
+      if (r < a.world) g += x[r];
+    float pp = a.p[k][i], mm = a.m[k][i], vv = a.v[k][i];
+    adam_one(pp, g, mm, vv, g_mul, a.lr[k], a.weight_decay[k], adamw, b1, b2, eps, bc1, bc2_sqrt);
+    a.p[k][i] = pp, a.m[k][i] = mm, a.v[k][i] = vv;
+  }
+}
+
+// NVLS variant: the reduce-scatter is ONE instruction per 16 bytes (multimem.ld_reduce: the NVSwitch fetches the element
+// from every rank's buffer and returns the fp32 sum, so only the owned slice crosses this GPU's ingress links instead of
+// N - 1 copies of it) and the all-gather of the fp16 copy is one multimem.st (one copy leaves the GPU, the switch fans it
+// out).  Everything else - unscale, Adam on the owned slice, local master and moments - is as in the kernels below.
+__device__ __forceinline__ float4 multimem_ld_reduce_add4(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st_h4(void* mc, uint32_t lo, uint32_t hi) {
+  asm volatile("multimem.st.relaxed.sys.global.v2.f16x2 [%0], {%1, %2};" ::"l"(mc), "r"(lo), "r"(hi) : "memory");
+}
+
+__global__ void __launch_bounds__(256) dp_adam_nvls_kernel(CednerfDpAdam a, const float* step, const float* scale_p,
+                                                           const float* found_inf, float b1, float b2, float eps, int adamw) {
+  if (found_inf && *found_inf != 0.f) return;
+  const int64_t base = a.lo + (int64_t)blockIdx.x * DP_CHUNK;   // the launcher passes full chunks only
+  const float inv_scale = scale_p ? 1.f / *scale_p : 1.f;
+  const float g_mul = a.grad_div != 1.f ? inv_scale / a.grad_div : inv_scale;
+  const float st = *step;
+  const float bc1 = 1.f - powf(b1, st), bc2_sqrt = sqrtf(1.f - powf(b2, st));
+  float* p_loc = a.p32_out[0];
+  constexpr int IT = DP_CHUNK / 4 / 256;
+  int64_t e[IT];
+  float4 g[IT], pp[IT], mm[IT], vv[IT];
+#pragma unroll
+  for (int j = 0; j < IT; ++j) {
+    e[j] = base + (int64_t)(j * 256 + threadIdx.x) * 4;
+    g[j] = multimem_ld_reduce_add4(a.grad_mc + e[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < IT; ++j) {
+    pp[j] = *reinterpret_cast<const float4*>(p_loc + e[j]);
+    mm[j] = ld_stream4(a.m + (e[j] - a.lo));
+    vv[j] = ld_stream4(a.v + (e[j] - a.lo));
+  }
+#pragma unroll
+  for (int j = 0; j < IT; ++j) {
+    adam_one(pp[j].x, g[j].x, mm[j].x, vv[j].x, g_mul, a.lr, a.weight_decay, adamw, b1, b2, eps, bc1, bc2_sqrt);
+    adam_one(pp[j].y, g[j].y, mm[j].y, vv[j].y, g_mul, a.lr, a.weight_decay, adamw, b1, b2, eps, bc1, bc2_sqrt);
+    adam_one(pp[j].z, g[j].z, mm[j].z, vv[j].z, g_mul, a.lr, a.weight_decay, adamw, b1, b2, eps, bc1, bc2_sqrt);
+    adam_one(pp[j].w, g[j].w, mm[j].w, vv[j].w, g_mul, a.lr, a.weight_decay, adamw, b1, b2, eps, bc1, bc2_sqrt);
+    __stcs(reinterpret_cast<float4*>(a.m + (e[j] - a.lo)), mm[j]);
+    __stcs(reinterpret_cast<float4*>(a.v + (e[j] - a.lo)), vv[j]);
+    *reinterpret_cast<float4*>(p_loc + e[j]) = pp[j];
+    const __half2 h0 = __floats2half2_rn(pp[j].x, pp[j].y), h1 = __floats2half2_rn(pp[j].z, pp[j].w);
+    multimem_st_h4(reinterpret_cast<__half*>(a.p16_mc) + e[j], *reinterpret_cast<const uint32_t*>(&h0),
+                   *reinterpret_cast<const uint32_t*>(&h1));
+  }
+  __threadfence_system();
 }
 
 // The same step for large ranges, with the peers' gradient tiles STAGED THROUGH SHARED MEMORY BY TMA: a persistent CTA
@@ -379,6 +481,21 @@ CEDNERF_EXPORT int cednerf_dp_adam(const CednerfDpAdam* args, const float* step,
   cudaStream_t st = (cudaStream_t)stream;
   int launches = 0;
   CednerfDpAdam rest = a;
+  // multicast-mapped buffers: reduce-scatter and all-gather inside the NVSwitch (full chunks; the tail goes direct)
+  if (a.world > 1 && a.grad_mc && a.p16_mc && n >= DP_CHUNK && (((uintptr_t)a.grad_mc | (uintptr_t)a.p16_mc) & 15) == 0) {
+    const int64_t chunks = n / DP_CHUNK;
+    dp_adam_nvls_kernel<<<(unsigned)chunks, 256, 0, st>>>(a, step, grad_scale, found_inf, beta1, beta2, eps, adam_w_mode);
+    ++launches;
+    rest.lo = a.lo + chunks * DP_CHUNK;
+    rest.m = a.m + chunks * DP_CHUNK;
+    rest.v = a.v + chunks * DP_CHUNK;
+    if (rest.hi > rest.lo) {
+      const int64_t ctas = (rest.hi - rest.lo + DP_CHUNK - 1) / DP_CHUNK;
+      dp_adam_kernel<<<(unsigned)ctas, 256, 0, st>>>(rest, step, grad_scale, found_inf, beta1, beta2, eps, adam_w_mode);
+      ++launches;
+    }
+    return cednerf_check_launch("cednerf_dp_adam", launches);
+  }
   // large ranges with remote gradients: TMA-staged persistent kernel on the full tiles, direct-load kernel on the tail
   const int64_t n_tiles = n / DP_TILE;
   const int smem = DP_STAGES * (a.world - 1) * DP_TILE * 4;
@@ -403,4 +520,26 @@ CEDNERF_EXPORT int cednerf_dp_adam(const CednerfDpAdam* args, const float* step,
     ++launches;
   }
   return cednerf_check_launch("cednerf_dp_adam", launches);
+}
+
+// Adam on up to 8 small replicated tensors in one launch; gradients = rank-ordered sum of every rank's staging region.
+CEDNERF_EXPORT int cednerf_dp_adam_small(const CednerfDpSmall* args, const float* step, const float* grad_scale,
+                                         const float* found_inf, float beta1, float beta2, float eps, int adam_w_mode,
+                                         void* stream) {
+  CEDNERF_REQUIRE(args && step && args->world >= 1 && args->world <= DP_MAX_RANKS && args->n_tensors >= 0 &&
+                      args->n_tensors <= DP_SMALL_MAX,
+                  "bad arguments");
+  CednerfDpSmall a = *args;
+  int64_t c = 0;
+  for (int k = 0; k < a.n_tensors; ++k) {
+    CEDNERF_REQUIRE(a.n[k] >= 0 && (a.n[k] == 0 || (a.p[k] && a.m[k] && a.v[k])), "bad tensor entry");
+    a.chunk_begin[k] = c;
+    c += (a.n[k] + DP_SMALL_CHUNK - 1) / DP_SMALL_CHUNK;
+  }
+  a.chunk_begin[a.n_tensors] = c;
+  for (int r = 0; r < a.world; ++r) CEDNERF_REQUIRE(a.grad[r], "gradient staging regions missing");
+  if (c == 0) return 0;
+  dp_adam_small_kernel<<<(unsigned)c, 256, 0, (cudaStream_t)stream>>>(a, step, grad_scale, found_inf, beta1, beta2, eps,
+                                                                      adam_w_mode);
+  return cednerf_check_launch("cednerf_dp_adam_small");
 }

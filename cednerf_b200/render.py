@@ -7,14 +7,32 @@ import torch.nn.functional as F
 from . import ops
 
 
-def reduce_along_rays(ray_indices, values, n_rays, weights=None, reduce: str = "mean"):
-    """scatter_reduce_ with include_self=True, exactly as cednerf/render.py:8-39 ('mean' divides by count+1)."""
-    src = values if weights is None else weights * values
-    out = torch.zeros(n_rays, src.shape[-1], dtype=src.dtype, device=src.device)
+def reduce_along_rays(ray_indices, values, n_rays=None, weights=None, reduce: str = "mean"):
+    """cednerf/render.py:8-39: out = zeros(n_rays, C).scatter_reduce_(0, ray_indices, weights * values, reduce) with
+    include_self=True ('mean' therefore divides a ray's sum by its sample count + 1).  'sum' and 'mean' - what the
+    reference calls it with - are one segmented launch forward and one backward (cednerf_accumulate_fwd / _bwd, gradients
+    to both `values` and `weights`); ray_indices sorted, as the sampler emits them."""
+    assert ray_indices.dim() == 1 and values.dim() == 2
+    if not values.is_cuda:
+        raise NotImplementedError("Only support cuda inputs.")
+    if reduce not in ("sum", "mean"):
+        raise NotImplementedError("reduce_along_rays: 'sum' and 'mean' (what the reference uses)")
+    if weights is not None:
+        assert values.shape[0] == weights.shape[0], f"Invalid shapes: {tuple(values.shape)} vs {tuple(weights.shape)}"
     if ray_indices.numel() == 0:
-        return out
-    index = ray_indices[:, None].long().expand(-1, src.shape[-1])
-    return out.scatter_reduce(0, index, src, reduce=reduce)
+        assert n_rays is not None
+        return torch.zeros(n_rays, values.shape[-1], device=values.device)
+    if n_rays is None:
+        n_rays = int(ray_indices.max()) + 1
+    counts = ops.counts_of(ray_indices)
+    offsets = ops.ray_offsets(ray_indices, n_rays) if counts is None else counts[0]
+    n_dev = None if counts is None else counts[1]
+    ridx = ray_indices.detach().to(torch.int64).contiguous()
+    w = torch.ones(values.shape[0], device=values.device) if weights is None else weights.reshape(-1)
+    out = ops.AccumulateFunction.apply(w, values, ridx, offsets, n_rays, n_dev)
+    if reduce == "mean":
+        out = out / (offsets[1:] - offsets[:-1] + 1).to(out.dtype)[:, None]
+    return out
 
 
 def rendering(t_starts, t_ends, ray_indices, n_rays, rgb_sigma_fn=None, rgb_alpha_fn=None, render_bkgd=None):
@@ -42,5 +60,5 @@ def rendering(t_starts, t_ends, ray_indices, n_rays, rgb_sigma_fn=None, rgb_alph
         if "weight_losses" in io:
             wl = F.huber_loss(io["weight_losses"].float(), trans[:, None], reduction="none")
             extras["weight_losses"] = reduce_along_rays(ray_indices, wl * io["selector"][:, None], n_rays,
-                                                        weights[:, None])
+                                                        weights[:, None])   # 'mean': segmented kernel + count division
     return colors, opac, depth, extras

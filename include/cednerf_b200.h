@@ -344,7 +344,23 @@ typedef struct CednerfDpAdam {
   float* v;
   int64_t lo, hi;                             /* owned element range, lo % 4 == 0 */
   float lr, weight_decay, grad_div;           /* summed gradient / grad_div (world: average) */
+  const float* grad_mc;                       /* nullable: multicast address of the gradient buffers (NVLS ld_reduce) */
+  void* p16_mc;                               /* nullable: multicast address of the fp16 copies (NVLS multimem.st) */
 } CednerfDpAdam;
+#define CEDNERF_DP_SMALL_MAX 8
+typedef struct CednerfDpSmall {   /* the small (MLP) tensors of a step: summed from all ranks in rank order, updated locally */
+  int world, n_tensors;
+  const float* grad[CEDNERF_DP_MAX_RANKS];   /* every rank's staging region of the small gradients, as mapped here */
+  float* p[CEDNERF_DP_SMALL_MAX];
+  float* m[CEDNERF_DP_SMALL_MAX];
+  float* v[CEDNERF_DP_SMALL_MAX];
+  int64_t off[CEDNERF_DP_SMALL_MAX];         /* element offset of the tensor's gradient inside the staging region */
+  int64_t n[CEDNERF_DP_SMALL_MAX];
+  float lr[CEDNERF_DP_SMALL_MAX];
+  float weight_decay[CEDNERF_DP_SMALL_MAX];
+  float grad_div;
+  int64_t chunk_begin[CEDNERF_DP_SMALL_MAX + 1]; /* scratch */
+} CednerfDpSmall;
 int cednerf_peer_alloc(int64_t bytes, void** ptr);            /* cudaMalloc + zero fill */
 int cednerf_peer_free(void* ptr);
 int cednerf_ipc_export(void* ptr, void* handle64);            /* cudaIpcGetMemHandle of a cednerf_peer_alloc pointer */
@@ -355,6 +371,9 @@ int64_t cednerf_dp_ctrl_bytes(void);
 int cednerf_dp_barrier(const CednerfDpPeers* peers, uint32_t epoch, int timeout_ms, void* stream);
 /* *found_out (nullable) = OR of all ranks' found_inf; *step (nullable) += 1 unless set */
 int cednerf_dp_found_inf(const CednerfDpPeers* peers, float* found_out, float* step, void* stream);
+int cednerf_dp_adam_small(const CednerfDpSmall* args, const float* step, const float* grad_scale /*nullable*/,
+                          const float* found_inf /*nullable*/, float beta1, float beta2, float eps, int adam_w_mode,
+                          void* stream);
 int cednerf_dp_adam(const CednerfDpAdam* args, const float* step, const float* grad_scale /*nullable*/,
                     const float* found_inf /*nullable*/, float beta1, float beta2, float eps, int adam_w_mode, void* stream);
 

@@ -16,6 +16,8 @@ dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
 dist.init_process_group("nccl", device_id=dev)
 n = 2 * 23928800
 pm = dp.PeerMemory([("grad", 4 * n), ("p32", 4 * n), ("p16", 2 * n)], dev)
+if rank == 0:
+    print("provider", pm.provider, "multicast", bool(pm.mc_base), flush=True)
 q = (n // 4) // world
 lo, hi = 4 * q * rank, (n if rank == world - 1 else 4 * q * (rank + 1))
 m = torch.zeros(hi - lo, device=dev)
@@ -24,7 +26,7 @@ step = torch.ones(1, device=dev)
 pm.local("grad", torch.float32).normal_()
 
 
-def run(read_world, n_out, label, p32_remote=True):
+def run(read_world, n_out, label, p32_remote=True, nvls=False):
     a = _lib.DpAdam()
     a.world, a.rank = read_world, (rank if read_world == world else 0)
     order = [rank] + [r for r in range(world) if r != rank]
@@ -36,6 +38,8 @@ def run(read_world, n_out, label, p32_remote=True):
         a.p16_out[k] = pm.address(order[k], "p16")
     a.m, a.v, a.lo, a.hi = m.data_ptr(), v.data_ptr(), lo, hi
     a.lr, a.weight_decay, a.grad_div = 1e-4, 0.0, float(world)
+    if nvls:
+        a.grad_mc, a.p16_mc = pm.multicast_address("grad"), pm.multicast_address("p16")
     def go():
         _lib.call("cednerf_dp_adam", ctypes.byref(a), step.data_ptr(), None, None, 0.9, 0.999, 1e-15, 1, _lib.stream())
     for _ in range(3):
@@ -59,6 +63,8 @@ run(world, 1, "remote reads + local")
 run(1, world, "replica stores + local")
 run(world, world, "full")
 run(world, world, "full, fp16 replicas only", False)
+if pm.mc_base:
+    run(world, world, "NVLS (ld_reduce + multimem.st)", False, True)
 # raw P2P bandwidth of this box with a plain SM copy kernel (torch's elementwise copy on UVA pointers)
 peer = (rank + 1) % world
 nb = 4 * n

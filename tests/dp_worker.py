@@ -53,8 +53,12 @@ def main():
         p.grad = None
 
     # ---- data-parallel step -----------------------------------------------------------------------------------------
-    opt = dp.DistributedFusedAdam(field.parameters(), lr=1e-2, eps=1e-15)
+    provider = os.environ.get("CEDNERF_DP_PROVIDER", "auto")   # "auto": symmetric memory (NVLS) if the box has it; "ipc"
+    opt = dp.DistributedFusedAdam(field.parameters(), lr=1e-2, eps=1e-15, provider=provider,
+                                  nvls=True if provider == "auto" else "auto")   # exercise the in-switch path at N = 2 too
     opt.setup()
+    if rank == 0:
+        print("transport:", opt.transport(), flush=True)
     scaler = cb.optim.GradScaler(scale)
     table = field.hash_encoder.params
     assert table.data_ptr() == opt._p32.data_ptr(), "table parameter was not re-homed into peer memory"

@@ -49,6 +49,8 @@ def test_ctypes_signatures_match_header():
                 sig += "P"
             elif "CednerfDpAdam" in a:
                 sig += "D"
+            elif "CednerfDpSmall" in a:
+                sig += "S"
             elif a.startswith("uint32_t "):
                 sig += "u"
             elif "*" in a:
@@ -73,8 +75,11 @@ def test_descriptor_structs_match_header_layout():
     assert ctypes.sizeof(_lib.AdamTensors) == 8 + 5 * 8 * 8 + 8 * 8 + 2 * 4 * 8 + 9 * 8
     assert ctypes.sizeof(_lib.DpCtrl) == 8 * 4 + 4 + 4 == _lib.load().cednerf_dp_ctrl_bytes()
     assert ctypes.sizeof(_lib.DpPeers) == 8 + 8 * 8
-    # world, rank, grad[8], n_out (+ padding), p32_out[8], p16_out[8], m, v, lo, hi, lr, weight_decay, grad_div (+ padding)
-    assert ctypes.sizeof(_lib.DpAdam) == 8 + 64 + 8 + 64 + 64 + 16 + 16 + 16
+    # world, rank, grad[8], n_out (+ padding), p32_out[8], p16_out[8], m, v, lo, hi, lr, weight_decay, grad_div (+ padding),
+    # grad_mc, p16_mc
+    assert ctypes.sizeof(_lib.DpAdam) == 8 + 64 + 8 + 64 + 64 + 16 + 16 + 16 + 16
+    # world, n_tensors, grad[8], p/m/v[8], off[8], n[8], lr[8], weight_decay[8], grad_div (+ padding), chunk_begin[9]
+    assert ctypes.sizeof(_lib.DpSmall) == 8 + 64 + 3 * 64 + 64 + 64 + 32 + 32 + 8 + 72
     assert ctypes.sizeof(_lib.FieldDesc) == 6 * 4 + 4 + 3 * 4 + 4 * ctypes.sizeof(_lib.MlpDesc) + ctypes.sizeof(_lib.GridLevels)
 
 

@@ -391,3 +391,31 @@ def test_mlp_with_input_encoding(cb):
     y_ref = ref(x).detach()
     y = net(x.to(DEV)).float().cpu()
     torch.testing.assert_close(y, y_ref, rtol=2e-3, atol=2e-3 * float(y_ref.abs().max()))
+
+
+@pytest.mark.parametrize("reduce", ["sum", "mean"])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_reduce_along_rays_against_scatter_reduce(cb, reduce, weighted):
+    """cednerf/render.py:8-39 is torch scatter_reduce_ with include_self=True; here a segmented kernel (+ the count
+    division for 'mean'), forward and backward to both values and weights."""
+    g = torch.Generator().manual_seed(12)
+    n_rays, c = 700, 5
+    counts = torch.randint(0, 40, (n_rays,), generator=g)
+    counts[::9] = 0
+    ridx = torch.repeat_interleave(torch.arange(n_rays), counts)
+    v = torch.randn(ridx.numel(), c, generator=g)
+    w = torch.rand(ridx.numel(), 1, generator=g) if weighted else None
+    v_ref = v.clone().double().requires_grad_(True)
+    w_ref = None if w is None else w.clone().double().requires_grad_(True)
+    src = v_ref if w_ref is None else w_ref * v_ref
+    want = torch.zeros(n_rays, c, dtype=torch.float64).scatter_reduce(0, ridx[:, None].expand(-1, c), src, reduce=reduce)
+    go = torch.randn(n_rays, c, generator=g)
+    want.backward(go.double())
+    v_g = v.to(DEV).requires_grad_(True)
+    w_g = None if w is None else w.to(DEV).requires_grad_(True)
+    got = cb.render.reduce_along_rays(ridx.to(DEV), v_g, n_rays, w_g, reduce)
+    got.backward(go.to(DEV))
+    torch.testing.assert_close(got.detach().cpu().double(), want.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(v_g.grad.cpu().double(), v_ref.grad, rtol=1e-5, atol=1e-6)
+    if weighted:
+        torch.testing.assert_close(w_g.grad.cpu().double(), w_ref.grad, rtol=1e-5, atol=1e-6)
