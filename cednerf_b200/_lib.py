@@ -81,7 +81,8 @@ _SIGNATURES = {
     "cednerf_occ_pack_bits": "plpp",
     "cednerf_occ_threshold_pack": "plpppp",
     "cednerf_occ_mark_invisible": "pipiipiiiifpp",
-    "cednerf_march": "ipplppiippffffippppppppppppppppppppppipp",
+    "cednerf_march": "ipplppiippffffippppppppppppppppppppppippp",
+    "cednerf_occ_coarsen": "piipp",
     "cednerf_ray_coherence_keys": "plpp",
     "cednerf_ray_coherence_order": "plppp",
     "cednerf_march_fill_runs": "lppppiffppppp",
@@ -114,7 +115,7 @@ _SIGNATURES = {
     "cednerf_accumulate_fwd": "ppipllpip",
     "cednerf_accumulate_bwd": "ppiplppppp",
     "cednerf_render_round_begin": "pliippp",
-    "cednerf_march_round": "ipplppiipfffppppppppppppppip",
+    "cednerf_march_round": "ipplppiipfffppppppppppppppipp",
     "cednerf_march_fill_runs_round": "lpppppiffppppppp",
     "cednerf_render_round_composite": "pppppppplifppppp",
     "cednerf_render_round_compact": "ppplppp",

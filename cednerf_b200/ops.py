@@ -92,6 +92,21 @@ def exclusive_scan_capped(counts: torch.Tensor, capacity: int):
     return offsets, totals
 
 
+def occupancy_coarse(bits: torch.Tensor, n_levels: int, res: int):
+    """One bit per 4x4x4 block of cells (cednerf_occ_coarsen), cached on the bit-field tensor it was derived from (a new
+    bit field is a new tensor).  None when the resolution is not a multiple of 4."""
+    if res % 4 or bits is None:
+        return None
+    hit = getattr(bits, "_cednerf_coarse", None)
+    if hit is not None and hit[0] == bits._version:
+        return hit[1]
+    words = (n_levels * (res // 4) ** 3 + 31) // 32
+    coarse = torch.empty(words, dtype=I32, device=bits.device)
+    call("cednerf_occ_coarsen", ptr(bits), n_levels, res, ptr(coarse), stream())
+    bits._cednerf_coarse = (bits._version, coarse)
+    return coarse
+
+
 class MarchInputs:
     """Argument bundle shared by the count and fill passes."""
 
@@ -110,6 +125,11 @@ class MarchInputs:
         self.t_indices = None if t_indices is None else t_indices.detach().to(I64).contiguous()
         self.hits = None if hits is None else hits.detach().to(torch.bool).contiguous()
         self.order = None  # int32 permutation for the count pass (sort_for_coherence)
+        # 4^3-block bits for the marcher's empty-space skip.  Measured: it pays in the marching rounds of render_image_test
+        # (dense warps of coherent rays: -7 % per frame) and costs in the two-pass count of a training batch (+18 %: the
+        # count pass is bound by the latency of the DDA's dependent chain, which the skipped look-ups are not on), so only
+        # the rounds pass it (utils._render_rounds_on_device)
+        self.coarse = None
 
     def sort_for_coherence(self):
         """Random training rays: march them in the order of a direction key so that the lanes of a warp walk
@@ -140,7 +160,7 @@ class MarchInputs:
         rt, rn, nr = self.runs if self.runs is not None else (None, None, None)
         call("cednerf_march", *self._common(0), None, None, None, None, None, None, None, None, None, None, None,
              None, ptr(n_iv), ptr(n_sm), ptr(term), ptr(rt), ptr(rn), ptr(nr), self.RUN_CAP if rt is not None else 0,
-             ptr(self.order), stream())
+             ptr(self.order), ptr(self.coarse), stream())
         return n_iv, n_sm, term
 
     def fill_packed_from_runs(self, sm_starts, total):
@@ -156,7 +176,7 @@ class MarchInputs:
         # overflow is 0 for rays the caller masked out (their run count is 0), so it can stand in as the ray mask
         user_mask, self.mask = self.mask, overflow
         call("cednerf_march", *self._common(1), None, ptr(sm_starts), None, None, None, None, None, None, None,
-             ptr(t0), ptr(t1), ptr(ridx), None, None, None, None, None, None, 0, None, stream())
+             ptr(t0), ptr(t1), ptr(ridx), None, None, None, None, None, None, 0, None, ptr(self.coarse), stream())
         self.mask = user_mask
         return ridx, t0, t1
 
@@ -173,7 +193,7 @@ class MarchInputs:
              self.step, self.cone, ptr(t0), ptr(t1), ptr(ridx), ptr(overflow), stream())
         user_mask, self.mask = self.mask, overflow   # rays over the run limit: full-march fill into their (whole) range
         call("cednerf_march", *self._common(1), None, ptr(offsets), None, None, None, None, None, None, None,
-             ptr(t0), ptr(t1), ptr(ridx), None, None, None, None, None, None, 0, None, stream())
+             ptr(t0), ptr(t1), ptr(ridx), None, None, None, None, None, None, 0, None, ptr(self.coarse), stream())
         self.mask = user_mask
         return ridx, t0, t1
 
@@ -184,7 +204,7 @@ class MarchInputs:
         ridx = _sempty(total, dtype=I64, device=dev)
         term = torch.empty(self.n, device=dev)
         call("cednerf_march", *self._common(1), None, ptr(sm_starts), None, None, None, None, None, None, None,
-             ptr(t0), ptr(t1), ptr(ridx), None, None, ptr(term), None, None, None, 0, None, stream())
+             ptr(t0), ptr(t1), ptr(ridx), None, None, ptr(term), None, None, None, 0, None, ptr(self.coarse), stream())
         return ridx, t0, t1, term
 
     def fill_nerfacc(self, iv_starts, sm_starts, n_iv_total, n_sm_total):
@@ -201,7 +221,7 @@ class MarchInputs:
         term = torch.empty(self.n, device=dev)
         call("cednerf_march", *self._common(1), ptr(iv_starts), ptr(sm_starts), ptr(iv_vals), ptr(iv_left),
              ptr(iv_right), ptr(iv_ray), ptr(sm_vals), ptr(sm_ray), ptr(sm_valid), None, None, None, ptr(n_iv),
-             ptr(n_sm), ptr(term), None, None, None, 0, None, stream())
+             ptr(n_sm), ptr(term), None, None, None, 0, None, ptr(self.coarse), stream())
         return (iv_vals, iv_left, iv_right, iv_ray), (sm_vals, sm_ray, sm_valid), n_iv, n_sm, term
 
 

@@ -175,6 +175,7 @@ def _render_rounds_on_device(max_samples, field, rays, bits, aabbs, res, near, f
     o, d = ops._f32c(rays.origins), ops._f32c(rays.viewdirs)
     aabbs_c = ops._f32c(aabbs)
     n_levels = aabbs_c.shape[0]
+    coarse = ops.occupancy_coarse(bits, n_levels, res)
     I32, I64 = torch.int32, torch.int64
     # n_alive * k <= n when k = n // n_alive, and <= min_samples * n_alive otherwise
     cap = ops._sticky_capacity(n * max(1, min_samples))
@@ -216,13 +217,13 @@ def _render_rounds_on_device(max_samples, field, rays, bits, aabbs, res, near, f
         pending.append((ev, host))
         call("cednerf_march_round", 0, ptr(o), ptr(d), bound, ptr(bits), ptr(aabbs_c), n_levels, res, ptr(near), far_plane,
              float(step), float(cone), ptr(t_sorted), ptr(t_indices), ptr(hits), ptr(cur), ptr(state), None, None, None,
-             None, None, ptr(n_sm), ptr(run_t), ptr(run_n), ptr(n_runs), run_cap, stream())
+             None, None, ptr(n_sm), ptr(run_t), ptr(run_n), ptr(n_runs), run_cap, ptr(coarse), stream())
         call("cednerf_exclusive_scan_capped", ptr(n_sm), bound, cap, ptr(offsets), ptr(totals), ptr(ws), stream())
         call("cednerf_march_fill_runs_round", bound, ptr(offsets), ptr(n_sm), ptr(run_t), ptr(run_n), ptr(n_runs), run_cap,
              float(step), float(cone), ptr(cur), ptr(state), ptr(t0), ptr(t1), ptr(ridx), ptr(overflow), stream())
         call("cednerf_march_round", 1, ptr(o), ptr(d), bound, ptr(bits), ptr(aabbs_c), n_levels, res, ptr(near), far_plane,
              float(step), float(cone), ptr(t_sorted), ptr(t_indices), ptr(hits), ptr(cur), ptr(state), ptr(overflow),
-             ptr(offsets), ptr(t0), ptr(t1), ptr(ridx), None, None, None, None, run_cap, stream())
+             ptr(offsets), ptr(t0), ptr(t1), ptr(ridx), None, None, None, None, run_cap, ptr(coarse), stream())
         call("cednerf_field_fwd", ptr(ridx), ptr(t0), ptr(t1), ptr(o), ptr(d), None, None, ptr(ts), 0, cap, ptr(images[0]),
              ptr(images[1]), ptr(images[2]), ptr(table), _ct.byref(desc), ptr(sigma), ptr(rgbs), ptr(totals), stream())
         call("cednerf_render_round_composite", ptr(t0), ptr(t1), ptr(sigma), ptr(rgbs), ptr(offsets), ptr(cur), ptr(state),

@@ -62,6 +62,10 @@ int cednerf_occ_mark_invisible(const float* K, int n_K, const float* c2w, int n_
  * t_sorted / t_indices / hits (nullable, all or none): computed in-kernel when absent.
  * Output groups (each nullable): nerfacc intervals (iv_*), nerfacc samples (sm_*), packed
  * (t_starts, t_ends, ray_indices). */
+/* coarse occupancy for the marcher's empty-space skip: one bit per 4x4x4 block of cells (resolution % 4 == 0),
+ * ceil(n_levels (resolution / 4)^3 / 32) words.  Passing it changes no result: inside an empty block the DDA is stepped
+ * with the same fp32 additions, only the per-cell look-ups are skipped. */
+int cednerf_occ_coarsen(const uint32_t* occ_bits, int n_levels, int resolution, uint32_t* coarse, void* stream);
 int cednerf_ray_coherence_keys(const float* rays_d, int64_t n_rays, int32_t* keys, void* stream);
 /* order [n] = permutation grouping the rays by the leading 14 bits of that key (bucket order: histogram, scan, scatter;
  * workspace 64 KB) - the ray_order argument of cednerf_march */
@@ -75,8 +79,8 @@ int cednerf_march(int fill, const float* rays_o, const float* rays_d, int64_t n_
                   float* t_starts, float* t_ends, int64_t* ray_indices, int32_t* n_intervals, int32_t* n_samples,
                   float* termination, float* run_t /*nullable: [n,run_cap], count pass only*/,
                   int32_t* run_n /*[n,run_cap]*/, int32_t* n_runs /*[n]*/, int run_cap,
-                  const int32_t* ray_order /*nullable: thread i marches ray ray_order[i]; outputs stay indexed by ray*/,
-                  void* stream);
+                  const int32_t* ray_order /*nullable: thread i marches ray ray_order[i], outputs stay indexed by ray*/,
+                  const uint32_t* occ_coarse /*nullable: cednerf_occ_coarsen*/, void* stream);
 /* Packed fill that replays the runs a count pass recorded (first left edge + length of every stretch of back-to-back
  * samples): no second grid traversal.  overflow[r] = 1 where a ray had more than run_cap runs; fill those rays with
  * cednerf_march(fill = 1, rays_mask = overflow). */
@@ -261,11 +265,12 @@ int cednerf_render_round_begin(int32_t* state, int64_t n_rays, int max_samples, 
                                const int64_t* prev_totals /*nullable*/, int64_t* total /*nullable, += prev_totals[0]*/,
                                void* stream);
 int cednerf_march_round(int fill, const float* rays_o, const float* rays_d, int64_t n_bound, const uint32_t* occ_bits,
-                        const float* aabbs, int n_levels, int resolution, float* near_term /*[n_rays] in: start planes; out (count pass): termination planes*/, float far_const, float step_size, float cone_angle,
+                        const float* aabbs, int n_levels, int resolution, float* near_term /*[n_rays] in: start planes. out (count pass): termination planes*/, float far_const, float step_size, float cone_angle,
                         const float* t_sorted, const int64_t* t_indices, const uint8_t* hits, const int32_t* alive,
                         const int32_t* state, const uint8_t* slot_mask /*fill*/, const int64_t* offsets /*fill*/,
                         float* t_starts, float* t_ends, int64_t* ray_indices, int32_t* n_samples /*count, per slot*/,
-                        float* run_t, int32_t* run_n, int32_t* n_runs, int run_cap, void* stream);
+                        float* run_t, int32_t* run_n, int32_t* n_runs, int run_cap,
+                        const uint32_t* occ_coarse /*nullable*/, void* stream);
 int cednerf_march_fill_runs_round(int64_t n_bound, const int64_t* offsets, const int32_t* n_samples, const float* run_t,
                                   const int32_t* run_n, const int32_t* n_runs, int run_cap, float step_size,
                                   float cone_angle, const int32_t* alive, const int32_t* state, float* t_starts,
