@@ -118,7 +118,7 @@ _SIGNATURES = {
     "cednerf_march_round": "ipplppiipfffppppppppppppppipp",
     "cednerf_march_fill_runs_round": "lpppppiffppppppp",
     "cednerf_render_round_composite": "pppppppplifppppp",
-    "cednerf_render_round_compact": "ppplppp",
+    "cednerf_render_round_compact":"ppplppliippp",
     "cednerf_generate_rays": "ppppiffffiilpppp",
     "cednerf_distortion_fwd": "pppplpppp",
     "cednerf_distortion_bwd": "pppplpppp",

@@ -90,3 +90,26 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+
+// State transition at the start of a marching round of render_image_test (cednerf/utils.py:231-240), shared by
+// cednerf_render_round_begin and the compaction kernel that ends the previous round.  state int32[8]: [0] alive rays of
+// the round, [1] k, [2] samples per ray marched so far, [3] rays kept alive for the next round, [4] round index, [5] over.
+__device__ __forceinline__ void cednerf_round_begin(int32_t* state, int64_t n_rays, int max_samples, int min_samples,
+                                                    const int64_t* prev_totals, int64_t* total) {
+  if (prev_totals && total) total[0] += prev_totals[0];
+  int n_alive = state[3];
+  state[3] = 0;
+  int k = 0;
+  if (n_alive <= 0 || state[2] >= max_samples) {
+    n_alive = 0;
+    state[5] = 1;
+  } else {
+    const int64_t q = n_rays / (int64_t)n_alive;  // the reference: k = max(min(n // n_alive, 64), min_samples)
+    k = (int)(q < 64 ? q : 64);
+    if (k < min_samples) k = min_samples;
+    state[2] += k;
+  }
+  state[0] = n_alive;
+  state[1] = k;
+  state[4] += 1;
+}

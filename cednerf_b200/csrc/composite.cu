@@ -514,20 +514,28 @@ CEDNERF_EXPORT int cednerf_render_round_composite(const float* t_starts, const f
 namespace {
 __global__ void render_round_compact_kernel(const int32_t* __restrict__ flags, const int64_t* __restrict__ pos,
                                             const int32_t* __restrict__ cur, int64_t n_bound, int32_t* __restrict__ state,
-                                            int32_t* __restrict__ next) {
+                                            int32_t* __restrict__ next, int64_t n_rays, int max_samples, int min_samples,
+                                            const int64_t* __restrict__ round_totals, int64_t* __restrict__ total) {
   const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot == 0) state[3] = (int32_t)pos[n_bound];   // rays alive in the next round
   if (slot < n_bound && flags[slot]) next[pos[slot]] = cur[slot];
+  if (slot == 0) {   // nobody else in this launch reads the state: start the NEXT round here (saves a launch per round)
+    state[3] = (int32_t)pos[n_bound];   // rays alive in the next round
+    if (max_samples > 0) cednerf_round_begin(state, n_rays, max_samples, min_samples, round_totals, total);
+  }
 }
 }  // namespace
 
 // next[pos[slot]] = alive[slot] for the flagged slots (pos = exclusive scan of alive_flags, [n_bound + 1]); state[3] <- count
+// max_samples > 0: the same launch also performs cednerf_render_round_begin for the next round (with this round's scan
+// totals added to *total)
 CEDNERF_EXPORT int cednerf_render_round_compact(const int32_t* alive_flags, const int64_t* positions, const int32_t* alive,
-                                                int64_t n_bound, int32_t* round_state, int32_t* next_alive, void* stream) {
+                                                int64_t n_bound, int32_t* round_state, int32_t* next_alive, int64_t n_rays,
+                                                int max_samples, int min_samples, const int64_t* round_totals,
+                                                int64_t* total, void* stream) {
   CEDNERF_REQUIRE(n_bound >= 0 && alive_flags && positions && alive && round_state && next_alive, "bad arguments");
   if (n_bound == 0) return 0;
-  render_round_compact_kernel<<<cednerf_blocks(n_bound, 256), 256, 0, (cudaStream_t)stream>>>(alive_flags, positions, alive,
-                                                                                             n_bound, round_state, next_alive);
+  render_round_compact_kernel<<<cednerf_blocks(n_bound, 256), 256, 0, (cudaStream_t)stream>>>(
+      alive_flags, positions, alive, n_bound, round_state, next_alive, n_rays, max_samples, min_samples, round_totals, total);
   return cednerf_check_launch("cednerf_render_round_compact");
 }
 

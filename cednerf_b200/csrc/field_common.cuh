@@ -128,6 +128,28 @@ __device__ __forceinline__ __half2 gather_h2(const __half2* base, uint32_t idx) 
   return __ldg(reinterpret_cast<const __half2*>(addr));
 }
 
+// packed fp32 pairs (sm_100: add / sub / mul / fma .f32x2 on 64-bit registers)
+__device__ __forceinline__ uint64_t pack_f2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack_f2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t sub_f2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fma_f2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t h2_to_f2(__half2 h) {
+  const float2 f = __half22float2(h);
+  return pack_f2(f.x, f.y);
+}
+
 // the 8*LG gathers of levels l_first .. l_first+LG-1 (fractions kept for the weights)
 template <int LG>
 __device__ __forceinline__ void hash_issue(const float* xn, const __half* __restrict__ table, const CednerfGridLevels& lv,
@@ -173,16 +195,22 @@ __device__ __forceinline__ void hash_levels(const float* xn, const __half* __res
   __half2 v[LG][8];
   hash_issue<LG>(xn, table, lv, level_base + l0, frac, v);  // issue all 8*LG gathers first ...
 #pragma unroll
-  for (int a = 0; a < LG; ++a) {  // ... then the weights (recomputed from 3 fractions) and the blend
-    float w[8];
-    cell_weights(frac[a], w);
-    float a0 = 0.f, a1 = 0.f;
+  for (int a = 0; a < LG; ++a) {
+    // ... then the blend, as seven lerps on both features at once (Blackwell's packed fp32 pipe: FADD2 / FFMA2): 14
+    // instructions instead of 12 weight products + 16 FMAs.  Same value as the weighted sum up to fp32 rounding, i.e.
+    // the same fp16 feature except at near-ties (the stand-alone encoder keeps the oracle's operation order).
+    const uint64_t fx = pack_f2(frac[a][0], frac[a][0]), fy = pack_f2(frac[a][1], frac[a][1]),
+                   fz = pack_f2(frac[a][2], frac[a][2]);
+    uint64_t c[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float2 f = __half22float2(v[a][k]);
-      a0 = fmaf(w[k], f.x, a0);
-      a1 = fmaf(w[k], f.y, a1);
+    for (int j = 0; j < 4; ++j) {
+      const uint64_t lo = h2_to_f2(v[a][2 * j]), hi = h2_to_f2(v[a][2 * j + 1]);
+      c[j] = fma_f2(fx, sub_f2(hi, lo), lo);
     }
+    const uint64_t d0 = fma_f2(fy, sub_f2(c[1], c[0]), c[0]), d1 = fma_f2(fy, sub_f2(c[3], c[2]), c[2]);
+    const uint64_t e = fma_f2(fz, sub_f2(d1, d0), d0);
+    float a0, a1;
+    unpack_f2(e, a0, a1);
     feat[l0 + a] = pack_h2(a0, a1);
   }
 }

@@ -143,8 +143,11 @@ __global__ void sort_boundaries_kernel(const float* __restrict__ t_mins, const f
   }
 }
 
+#ifndef MARCH_MIN_BLOCKS
+#define MARCH_MIN_BLOCKS 8
+#endif
 template <bool FILL>
-__global__ void __launch_bounds__(128) march_kernel(MarchArgs a) {
+__global__ void __launch_bounds__(128, MARCH_MIN_BLOCKS) march_kernel(MarchArgs a) {
   const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= a.n_rays) return;
   if (a.n_active_dev && slot >= (int64_t)*a.n_active_dev) {  // beyond the live part of the alive list
@@ -540,13 +543,19 @@ scan_apply_kernel(const int32_t* __restrict__ counts, int64_t n, const int64_t* 
   }
 }
 
-// offsets[i] = min(exclusive prefix sum, capacity) for i in [0, n]; totals = {min(total, capacity), total}
+// The capped scan in ONE pass (decoupled look-back): tiles take tickets in launch order, publish their aggregate, then
+// add up the published values of their predecessors (aggregate -> keep looking back, inclusive prefix -> stop).
+// state[0] = ticket counter, state[1 + t] = (flag << 62) | value with flag 1 = aggregate, 2 = inclusive prefix; zeroed by
+// the launcher.  One launch instead of three: the marching rounds of a frame scan twice per round.
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_apply_capped_kernel(const int32_t* __restrict__ counts, int64_t n, const int64_t* __restrict__ tile_offsets,
-                         int64_t capacity, int64_t* __restrict__ offsets, const int64_t* __restrict__ total_raw,
-                         int64_t* __restrict__ totals) {
+scan_capped_onepass_kernel(const int32_t* __restrict__ counts, int64_t n, int64_t capacity, int64_t* __restrict__ offsets,
+                           int64_t* __restrict__ totals, unsigned long long* __restrict__ state) {
   __shared__ int64_t smem[SCAN_THREADS / 32];
-  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  __shared__ int64_t tile_s, excl_s;
+  if (threadIdx.x == 0) tile_s = (int64_t)atomicAdd(state, 1ull);
+  __syncthreads();
+  const int64_t tile = tile_s;
+  const int64_t base = tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
   int32_t c[SCAN_ITEMS];
   int64_t s = 0;
 #pragma unroll
@@ -555,17 +564,39 @@ scan_apply_capped_kernel(const int32_t* __restrict__ counts, int64_t n, const in
     s += c[k];
   }
   int64_t total;
-  int64_t off = tile_offsets[blockIdx.x] + block_excl_scan(s, &total, smem);
+  const int64_t local = block_excl_scan(s, &total, smem);
+  if (threadIdx.x == 0) {
+    volatile unsigned long long* st = state + 1;
+    const unsigned long long FLAG_AGG = 1ull << 62, FLAG_INC = 2ull << 62, MASK = (1ull << 62) - 1ull;
+    if (tile > 0) {
+      st[tile] = FLAG_AGG | (unsigned long long)total;
+      __threadfence();
+    }
+    int64_t excl = 0;
+    for (int64_t j = tile - 1; j >= 0; --j) {
+      unsigned long long v;
+      do {
+        v = st[j];
+      } while ((v >> 62) == 0ull);
+      excl += (int64_t)(v & MASK);
+      if ((v >> 62) == 2ull) break;
+    }
+    st[tile] = FLAG_INC | (unsigned long long)(excl + total);
+    __threadfence();
+    excl_s = excl;
+    if ((tile + 1) * SCAN_TILE >= n) {  // the last tile knows the grand total
+      const int64_t t = excl + total;
+      offsets[n] = t < capacity ? t : capacity;
+      totals[0] = t < capacity ? t : capacity;
+      totals[1] = t;
+    }
+  }
+  __syncthreads();
+  int64_t off = excl_s + local;
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; ++k) {
     if (base + k < n) offsets[base + k] = off < capacity ? off : capacity;
     off += c[k];
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    const int64_t t = *total_raw;
-    offsets[n] = t < capacity ? t : capacity;
-    totals[0] = t < capacity ? t : capacity;
-    totals[1] = t;
   }
 }
 
@@ -923,12 +954,11 @@ CEDNERF_EXPORT int cednerf_exclusive_scan_capped(const int32_t* counts, int64_t 
     return 0;
   }
   const int64_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-  int64_t* tile_sums = (int64_t*)workspace;
-  scan_tile_sums_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(counts, n, tile_sums);
-  scan_tile_offsets_kernel<<<1, SCAN_THREADS, 0, st>>>(tile_sums, tiles, totals + 1);
-  scan_apply_capped_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(counts, n, tile_sums, capacity, offsets, totals + 1,
-                                                                      totals);
-  return cednerf_check_launch("cednerf_exclusive_scan_capped", 3);
+  // one pass: ticket counter + one state word per tile (workspace holds 8 (tiles + 1) bytes), zeroed by a memset node
+  cudaMemsetAsync(workspace, 0, 8 * (size_t)(tiles + 1), st);
+  scan_capped_onepass_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(counts, n, capacity, offsets, totals,
+                                                                       (unsigned long long*)workspace);
+  return cednerf_check_launch("cednerf_exclusive_scan_capped", 1);
 }
 
 // ---- marching rounds of render_image_test kept on the device (cednerf/utils.py:224-318) ---------------------------
@@ -938,22 +968,7 @@ CEDNERF_EXPORT int cednerf_exclusive_scan_capped(const int32_t* counts, int64_t 
 namespace {
 __global__ void render_round_begin_kernel(int32_t* __restrict__ state, int64_t n_rays, int max_samples, int min_samples,
                                           const int64_t* __restrict__ prev_totals, int64_t* __restrict__ total) {
-  if (prev_totals && total) total[0] += prev_totals[0];
-  int n_alive = state[3];
-  state[3] = 0;
-  int k = 0;
-  if (n_alive <= 0 || state[2] >= max_samples) {
-    n_alive = 0;
-    state[5] = 1;
-  } else {
-    const int64_t q = n_rays / (int64_t)n_alive;            // the reference: k = max(min(n // n_alive, 64), min_samples)
-    k = (int)(q < 64 ? q : 64);
-    if (k < min_samples) k = min_samples;
-    state[2] += k;
-  }
-  state[0] = n_alive;
-  state[1] = k;
-  state[4] += 1;
+  cednerf_round_begin(state, n_rays, max_samples, min_samples, prev_totals, total);
 }
 }  // namespace
 

@@ -206,10 +206,9 @@ def _render_rounds_on_device(max_samples, field, rays, bits, aabbs, res, near, f
     max_rounds = (max_samples + min_samples - 1) // min_samples + 1
     import ctypes as _ct
 
-    for rnd in range(max_rounds):
+    call("cednerf_render_round_begin", ptr(state), n, int(max_samples), int(min_samples), None, ptr(total), stream())
+    for rnd in range(max_rounds):   # (every later round is begun by the compaction launch that ends its predecessor)
         cur, nxt = lists[rnd & 1], lists[(rnd + 1) & 1]
-        call("cednerf_render_round_begin", ptr(state), n, int(max_samples), int(min_samples),
-             ptr(totals) if rnd else None, ptr(total), stream())
         host = ring[rnd % len(ring)]
         host.copy_(state, non_blocking=True)
         ev = torch.cuda.Event()
@@ -230,7 +229,8 @@ def _render_rounds_on_device(max_samples, field, rays, bits, aabbs, res, near, f
              ptr(n_sm), bound, int(k_hint), float(early_stop_eps), ptr(rgb), ptr(opacity), ptr(depth), ptr(flags), stream())
         # ordered compaction of the surviving rays: the list stays in pixel order, so a warp's rays stay coherent
         call("cednerf_exclusive_scan_capped", ptr(flags), bound, n, ptr(pos), ptr(pos_tot), ptr(ws), stream())
-        call("cednerf_render_round_compact", ptr(flags), ptr(pos), ptr(cur), bound, ptr(state), ptr(nxt), stream())
+        call("cednerf_render_round_compact", ptr(flags), ptr(pos), ptr(cur), bound, ptr(state), ptr(nxt), n,
+             int(max_samples), int(min_samples), ptr(totals), ptr(total), stream())
         # look at the oldest state copies that have arrived; never run more than _ROUND_LAG rounds ahead of one
         stop = False
         while pending and (pending[0][0].query() or len(pending) > _ROUND_LAG):
@@ -244,8 +244,7 @@ def _render_rounds_on_device(max_samples, field, rays, bits, aabbs, res, near, f
             k_hint = max(k_hint, min(64, n // max(n_alive, 1)))
         if stop:
             break
-    # the rounds still in flight when the host saw the end did nothing (state[0] == 0); collect the total
-    call("cednerf_render_round_begin", ptr(state), n, int(max_samples), int(min_samples), ptr(totals), ptr(total), stream())
+    # the rounds still in flight when the host saw the end did nothing (state[0] == 0, totals == 0)
     return int(total.item())
 
 

@@ -283,7 +283,9 @@ int cednerf_render_round_composite(const float* t_starts, const float* t_ends, c
 /* ordered compaction of the flagged slots into the next round's list (positions = cednerf_exclusive_scan_capped of the
  * flags): neighbouring lanes keep marching neighbouring pixels.  state[3] <- number of rays kept. */
 int cednerf_render_round_compact(const int32_t* alive_flags, const int64_t* positions, const int32_t* alive,
-                                 int64_t n_bound, int32_t* round_state, int32_t* next_alive, void* stream);
+                                 int64_t n_bound, int32_t* round_state, int32_t* next_alive, int64_t n_rays,
+                                 int max_samples /*> 0: also begin the next round, as cednerf_render_round_begin*/,
+                                 int min_samples, const int64_t* round_totals, int64_t* total, void* stream);
 /* nerfacc.accumulate_along_rays / accumulate_along_rays_ — cednerf/render.py:158-169, cednerf/utils.py:282-299 */
 int cednerf_accumulate_fwd(const float* weights, const float* values /*nullable*/, int n_channels,
                            const int64_t* offsets, int64_t n_samples, int64_t n_rays, float* outputs, int inplace,

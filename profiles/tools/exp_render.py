@@ -28,3 +28,8 @@ for name,a,s,e in ins.rec:
     if name=='cednerf_march_round' and a[0]==0: rounds.append((a[3], round(s.elapsed_time(e),3)))
 for k,v in sorted(agg.items(), key=lambda kv:-kv[1][0]): print(f"{k:40s} {v[0]:8.3f} ms {v[1]:4d}")
 print('count pass per round (bound, ms):', rounds)
+U._DEVICE_ROUNDS=False
+ref=cb.render_image_test(1024,field,est,rays,render_bkgd=bk,timestamps=t,**rk)
+U._DEVICE_ROUNDS=True
+got=[cb.render_image_test(1024,field,est,rays,render_bkgd=bk,timestamps=t,**rk) for _ in range(3)]
+print('host-driven total',ref[3],'device rounds totals',[g[3] for g in got],'max |rgb diff|',[float((g[0]-ref[0]).abs().max()) for g in got], 'opacity diff', float((got[0][1]-ref[1]).abs().max()))
