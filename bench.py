@@ -62,6 +62,8 @@ def parse():
     ap.add_argument("--profile-steps", type=int, default=3, help="instrumented steps for the per-kernel breakdown")
     ap.add_argument("--render-frames", type=int, default=300,
                     help="frames of the video leg in total (subsampled from the 300-pose spiral; 0 = skip)")
+    ap.add_argument("--render-streams", type=int, default=3,
+                    help="frames of the video / frame legs whose marching rounds are interleaved on separate streams")
     ap.add_argument("--headline-only", action="store_true", help="skip the other configurations")
     ap.add_argument("--host-counts", action="store_true",
                     help="read the sample totals back to the host inside the step (the reference's behaviour) instead "
@@ -587,27 +589,35 @@ def render_leg(D, cb, workload, cfg, args, poses, times, opengl, bkgd, profile: 
     ring = [torch.empty(cfg.height, cfg.width, 3, dtype=torch.uint8).pin_memory() for _ in range(3)]
     copies = []
 
-    def render_one(k):
-        c2w, t = frames[k]   # pixel -> ray generation inside the timed region, one launch (gui.py:43-86 does it per frame)
-        rays = cb.utils.generate_rays(K, c2w, cfg.width, cfg.height, opengl)
-        rgb, _, _, n_s = cb.render_image_test(1024, field, est, rays, render_bkgd=bk, timestamps=t, **rk)
+    n_samples_box = [0]
+
+    def to_host(k, res):   # 8-bit frame -> pinned ring; the copy of frame k overlaps the rendering of the next frames
+        rgb, _, _, n_s = res
+        n_samples_box[0] += n_s
         if len(copies) >= len(ring):
             copies.pop(0).synchronize()
         ring[k % len(ring)].copy_((rgb.clamp(0.0, 1.0) * 255.0).to(torch.uint8), non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
         copies.append(ev)
-        return n_s
 
-    for k in range(min(2, len(frames))):
-        render_one(k)
+    def render_all(idx):
+        """Frames `idx` through render_images_test: pixel -> ray generation (one launch per frame, inside the timed region,
+        gui.py:43-86 does it per frame), the marching rounds of `--render-streams` frames interleaved, 8-bit frames to the host."""
+        n_samples_box[0] = 0
+        rays = [(lambda c=frames[k][0]: cb.utils.generate_rays(K, c, cfg.width, cfg.height, opengl)) for k in idx]
+        cb.utils.render_images_test(1024, field, est, rays, [frames[k][1] for k in idx], concurrency=args.render_streams,
+                                    on_frame=to_host, render_bkgd=bk, **rk)
+        while copies:
+            copies.pop(0).synchronize()   # every frame has reached the host before the clock stops
+        return n_samples_box[0]
+
+    render_all(list(range(min(2, len(frames)))))
     D.barrier()
     r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = _lib.launch_count()
     r0.record()
-    n_samples = sum(render_one(k) for k in range(len(frames)))
-    while copies:
-        copies.pop(0).synchronize()   # every frame has reached the host before the clock stops
+    n_samples = render_all(list(range(len(frames))))
     r1.record()
     D.barrier()
     ms = dp.max_over_ranks(r0.elapsed_time(r1), dev)
@@ -615,7 +625,7 @@ def render_leg(D, cb, workload, cfg, args, poses, times, opengl, bkgd, profile: 
     rays = cfg.width * cfg.height * len(poses)
     hbm_peak, _ = peaks()
     out = {"workload": f"{cfg.name}: {len(poses)} {cfg.width}x{cfg.height} frames, render_image_test(1024), "
-                       f"frames interleaved over {world} GPU(s), no collective",
+                       f"frames interleaved over {world} GPU(s), no collective; {args.render_streams} frame(s) in flight per GPU",
            "frames": len(poses), "scaling": "strong", "d2h_bytes_per_frame": cfg.width * cfg.height * 3, "rays_per_s": round(rays / (ms * 1e-3), 1),
            "samples_per_s": round(n_all / (ms * 1e-3), 1), "ms_per_frame_per_gpu": round(ms / max(len(mine), 1), 3),
            "samples_per_ray": round(n_all / rays, 3), "launches_per_frame": (_lib.launch_count() - l0) // max(len(mine), 1),
@@ -623,7 +633,8 @@ def render_leg(D, cb, workload, cfg, args, poses, times, opengl, bkgd, profile: 
            "pipeline_frac": round(n_all * 562 / (ms * 1e-3) / 1e9 / (hbm_peak * world), 4)}
     if profile and rank == 0 and frames:
         with Instrument(cb, _lib) as ins:
-            render_one(0)
+            cb.render_image_test(1024, field, est, cb.utils.generate_rays(K, frames[0][0], cfg.width, cfg.height, opengl),
+                                 render_bkgd=bk, timestamps=frames[0][1], **rk)
             torch.cuda.synchronize()
         agg = ins.aggregate()
         out["breakdown_ms_per_frame"] = {k: [round(v["ms"], 3), v["launches"]] for k, v in
@@ -707,7 +718,7 @@ def run_ours(args):
             line["render"] = video_leg(args.profile_steps > 0)
             line["config"]["render"] = {k: line["render"][k] for k in ("frames", "rays_per_s", "samples_per_s",
                                                                        "ms_per_frame_per_gpu", "pipeline_frac")}
-        r = dnerf_leg(8 * world, False)
+        r = dnerf_leg(16 * world, False)
         others["dnerf"] = {k: r[k] for k in ("frames", "rays_per_s", "samples_per_s", "ms_per_frame_per_gpu",
                                              "samples_per_ray", "pipeline_frac")}
         h = train_leg(D, cb, workload, workload.HYPERNERF, args, args.rays, 10, 3, False)

@@ -19,7 +19,7 @@ from . import encoder, hash_encoder, losses, model, nerfacc, ops, optim, render,
 from .model import DNGPradianceField  # noqa: E402
 from .nerfacc import OccGridEstimator  # noqa: E402
 from .render import rendering  # noqa: E402
-from .utils import Rays, render_image, render_image_test  # noqa: E402
+from .utils import Rays, render_image, render_image_test, render_images_test  # noqa: E402
 
-__all__ = ["DNGPradianceField", "OccGridEstimator", "rendering", "render_image", "render_image_test", "Rays",
+__all__ = ["DNGPradianceField", "OccGridEstimator", "rendering", "render_image", "render_image_test", "render_images_test", "Rays",
            "nerfacc", "tcnn", "hash_encoder", "encoder", "model", "render", "utils", "ops", "optim", "losses"]

@@ -160,15 +160,18 @@ _DEVICE_ROUNDS = True   # False: the host-driven rounds below (one host read per
 _ROUND_LAG = 4          # rounds the host may run ahead of the newest alive count it has seen
 
 
-def _render_rounds_on_device(max_samples, field, rays, bits, aabbs, res, near, far_plane, step, cone, early_stop_eps,
-                             timestamps, t_sorted, t_indices, hits, min_samples, rgb, opacity, depth) -> int:
+def _render_rounds_gen(max_samples, field, rays, bits, aabbs, res, near, far_plane, step, cone, early_stop_eps,
+                       timestamps, t_sorted, t_indices, hits, min_samples, rgb, opacity, depth):
     """The marching rounds of cednerf/utils.py:224-304 with the alive-ray list, the per-round k and the termination test
     on the device (csrc/march.cu: cednerf_render_round_begin / cednerf_march_round / cednerf_march_fill_runs_round,
     csrc/composite.cu: cednerf_render_round_composite).  The host enqueues rounds and reads a copy of the round state
     that is up to _ROUND_LAG rounds old: it tells it when every ray is done and how far the launches can shrink
     (the alive count never grows).  Rays are marched in alive-list order; the list is the ORDERED compaction of the
     survivors, so neighbouring lanes keep neighbouring pixels and a round's warps are dense however few rays survive;
-    per ray the samples, their order and the arithmetic are those of the host-driven loop."""
+    per ray the samples, their order and the arithmetic are those of the host-driven loop.
+
+    A generator: it yields after enqueuing each round (and while it waits for the final total), so that a scheduler can
+    interleave the rounds of several frames on several streams (render_images_test); it returns the sample total."""
     from ._lib import call, ptr, stream
 
     n, dev = rays.origins.shape[0], rays.origins.device
@@ -244,8 +247,15 @@ def _render_rounds_on_device(max_samples, field, rays, bits, aabbs, res, near, f
             k_hint = max(k_hint, min(64, n // max(n_alive, 1)))
         if stop:
             break
+        yield
     # the rounds still in flight when the host saw the end did nothing (state[0] == 0, totals == 0)
-    return int(total.item())
+    total_host = torch.empty(1, dtype=I64).pin_memory()
+    total_host.copy_(total, non_blocking=True)
+    done_ev = torch.cuda.Event()
+    done_ev.record()
+    while not done_ev.query():
+        yield
+    return int(total_host[0])
 
 
 def _lib_scan_ws(n):
@@ -259,6 +269,63 @@ def render_image_test(max_samples, radiance_field, estimator, rays, near_plane=0
                       render_step_size=1e-3, render_bkgd=None, cone_angle=0.0, alpha_thre=0.0, early_stop_eps=1e-4,
                       timestamps=None):
     """Iterative early-terminating marcher of cednerf/utils.py:153-318 -> (rgb, acc, depth, n_samples)."""
+    gen = _render_image_test_gen(max_samples, radiance_field, estimator, rays, near_plane, far_plane, render_step_size,
+                                 render_bkgd, cone_angle, alpha_thre, early_stop_eps, timestamps)
+    while True:
+        try:
+            next(gen)
+        except StopIteration as fin:
+            return fin.value
+
+
+@torch.no_grad()
+def render_images_test(max_samples, radiance_field, estimator, rays_list, timestamps_list, concurrency: int = 2,
+                       on_frame=None, **kwargs):
+    """render_image_test for several independent frames (a video: datasets/utils.py:67-112 poses, one timestamp each),
+    with the marching rounds of up to `concurrency` frames interleaved on separate CUDA streams: a round's count pass
+    ends with a few rays walking long stretches of empty space while most SMs idle, and the field kernel of another frame
+    fills them.  rays_list: Rays, or callables returning Rays (called inside the frame's stream, e.g. generate_rays).
+    on_frame(index, (rgb, acc, depth, n_samples)): called as each frame completes (the results are then not kept).
+    -> list of (rgb, acc, depth, n_samples), frame by frame identical to render_image_test."""
+    n_frames = len(rays_list)
+    results = [None] * n_frames
+    main = torch.cuda.current_stream()
+    streams = [torch.cuda.Stream() for _ in range(max(1, min(int(concurrency), n_frames)))]
+    free, active, nxt = list(streams), [], 0
+    while active or nxt < n_frames:
+        while free and nxt < n_frames:
+            st = free.pop()
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                r = rays_list[nxt]
+                r = r() if callable(r) else r
+                gen = _render_image_test_gen(max_samples, radiance_field, estimator, r, timestamps=timestamps_list[nxt],
+                                             **kwargs)
+            active.append((gen, st, nxt))
+            nxt += 1
+        for entry in list(active):
+            gen, st, idx = entry
+            with torch.cuda.stream(st):
+                try:
+                    next(gen)
+                except StopIteration as fin:
+                    main.wait_stream(st)
+                    for t in fin.value[:3]:
+                        t.record_stream(main)
+                    if on_frame is None:
+                        results[idx] = fin.value
+                    else:
+                        with torch.cuda.stream(main):
+                            on_frame(idx, fin.value)
+                    active.remove(entry)
+                    free.append(st)
+    return results
+
+
+def _render_image_test_gen(max_samples, radiance_field, estimator, rays, near_plane=0.0, far_plane=1e10,
+                           render_step_size=1e-3, render_bkgd=None, cone_angle=0.0, alpha_thre=0.0, early_stop_eps=1e-4,
+                           timestamps=None):
+    """render_image_test as a generator (yields between marching rounds on the device-resident path)."""
     shape = rays.origins.shape
     rays = Rays(rays.origins.reshape(-1, 3), rays.viewdirs.reshape(-1, 3))
     n, dev = rays.origins.shape[0], rays.origins.device
@@ -275,9 +342,9 @@ def render_image_test(max_samples, radiance_field, estimator, rays, near_plane=0
     fuse = (getattr(radiance_field, "fused_supported", lambda: False)() and not radiance_field.training
             and timestamps is not None and timestamps.numel() == 1 and render_step_size > 0 and n < 2 ** 31)
     if fuse and _DEVICE_ROUNDS:
-        total = _render_rounds_on_device(max_samples, radiance_field, rays, bits, estimator.aabbs, res, near, float(far_plane),
-                                         render_step_size, cone_angle, early_stop_eps, timestamps, t_sorted, t_indices, hits,
-                                         min_samples, rgb, opacity, depth)
+        total = yield from _render_rounds_gen(max_samples, radiance_field, rays, bits, estimator.aabbs, res, near,
+                                              float(far_plane), render_step_size, cone_angle, early_stop_eps, timestamps,
+                                              t_sorted, t_indices, hits, min_samples, rgb, opacity, depth)
         rgb = rgb + render_bkgd * (1.0 - opacity)
         depth = depth / opacity.clamp_min(torch.finfo(torch.float32).eps)
         return rgb.view(*shape[:-1], -1), opacity.view(*shape[:-1], -1), depth.view(*shape[:-1], -1), total

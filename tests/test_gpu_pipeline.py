@@ -391,3 +391,32 @@ def test_fused_occupancy_update_matches_the_op_by_op_update(cb):
     # the reference's calling convention still works with the object
     x = torch.rand(100, 3, device=DEV)
     assert fused_fn(x).shape == (100, 1)
+
+
+def test_interleaved_frames_match_frame_by_frame_rendering(cb):
+    """render_images_test (marching rounds of several frames interleaved on separate streams) returns, frame by frame,
+    what render_image_test returns."""
+    from cednerf_b200 import workload as w
+
+    cfg = w.TINY
+    rk = w.render_kwargs(cfg)
+    est, field = w.build_scene(cfg, DEV, cb, seed=42)
+    est.eval(), field.eval()
+    poses = w.spiral_poses(cfg, 5)
+    K = [[cfg.focal, 0.0, cfg.width / 2], [0.0, cfg.focal, cfg.height / 2], [0.0, 0.0, 1.0]]
+    bk = torch.tensor([0.2, 0.4, 0.6], device=DEV)
+    ts = [torch.tensor([[k / 5.0]], device=DEV) for k in range(5)]
+    want = [cb.render_image_test(1024, field, est, cb.utils.generate_rays(K, poses[k].to(DEV), cfg.width, cfg.height),
+                                 render_bkgd=bk, timestamps=ts[k], **rk) for k in range(5)]
+    rays = [(lambda k=k: cb.utils.generate_rays(K, poses[k].to(DEV), cfg.width, cfg.height)) for k in range(5)]
+    for conc in (1, 2, 3):
+        got = cb.render_images_test(1024, field, est, rays, ts, concurrency=conc, render_bkgd=bk, **rk)
+        torch.cuda.synchronize()
+        for k in range(5):
+            assert got[k][3] == want[k][3] and got[k][3] > 0
+            for i in range(3):
+                assert torch.equal(got[k][i], want[k][i]), (conc, k, i)
+    seen = []
+    cb.render_images_test(1024, field, est, rays, ts, concurrency=2, render_bkgd=bk,
+                          on_frame=lambda idx, res: seen.append((idx, res[3])), **rk)
+    assert sorted(seen) == [(k, want[k][3]) for k in range(5)]
