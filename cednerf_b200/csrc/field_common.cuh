@@ -23,8 +23,14 @@ __device__ __forceinline__ void group_sync(int group) { asm volatile("bar.sync %
 // The last layer's accumulator is left in TMEM columns [0, N_last) of this group's TMEM slice.
 __device__ __forceinline__ void run_chain(const CednerfMlpDesc& d, const uint8_t* wimg, uint8_t* abuf, uint32_t tmem_grp,
                                           uint32_t tmem_warp, uint64_t* bar, uint32_t& phase, int gtid, int group,
-                                          __half* save = nullptr, int64_t save_layer_stride = 0, int64_t save_row0 = 0,
+                                          uint8_t* save = nullptr, int64_t save_layer_stride = 0, int64_t save_row0 = 0,
                                           int save_rows = 0, uint8_t* save_in = nullptr) {
+  // `save` (training forward): the post-ReLU activation tiles are kept for the backward pass AS THEY SIT IN SHARED
+  // MEMORY - the 16 KB swizzled image of tile t, layer l at save + (l * save_layer_stride + t) * 16384 with
+  // save_layer_stride = number of tiles and t = save_row0 / 128 - so that one elected thread stores a tile with one TMA
+  // bulk copy (cp.async.bulk.global.shared::cta, UBLKCP) and the backward fetches it with one bulk load straight into
+  // its operand buffer: no per-thread address arithmetic, no 8 x (LDS + STG) per thread and layer.  The buffer is
+  // private to the library (cednerf_field_saved_bytes), so its layout is ours to choose.
   const int L = d.n_layers;
   for (int l = 0; l < L; ++l) {
     const int K = d.dim_in[l], N = d.dim_out[l];
@@ -44,17 +50,14 @@ __device__ __forceinline__ void run_chain(const CednerfMlpDesc& d, const uint8_t
         if (r < save_rows) dst[q] = *reinterpret_cast<const uint4*>(abuf + swz(r, c));
       }
     }
-    if (save && l > 0) {
-      // post-ReLU activations of the previous layer, kept for the backward pass: the tile this layer's MMA is reading
-      // is copied out cooperatively while it runs - consecutive threads write consecutive 16-byte chunks of the
-      // row-major [rows, 64] fp16 matrix (512 contiguous bytes per warp instruction; one 128-byte row per thread made
-      // every store instruction touch 32 half-filled sectors).  Nobody overwrites the tile before the barrier below.
-      uint4* dst = reinterpret_cast<uint4*>(save + (l - 1) * save_layer_stride + save_row0 * 64);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int q = i * MLP_TILE + gtid, r = q >> 3, c = q & 7;
-        if (r < save_rows) dst[q] = *reinterpret_cast<const uint4*>(abuf + swz(r, c));
-      }
+    if (save && l > 0 && gtid == 0) {
+      // the tile this layer's MMA is reading (post-ReLU activations of the previous layer) leaves by TMA while the MMA
+      // runs; the store has finished READING shared memory before anyone overwrites the tile (wait_group.read below)
+      uint8_t* dst = save + ((int64_t)(l - 1) * save_layer_stride + (save_row0 >> 7)) * MLP_TILE_BYTES;
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(abuf)),
+                   "r"((uint32_t)MLP_TILE_BYTES)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
     // one warp of the group polls the mbarrier; the other three block on the group's named barrier, which costs no
     // issue slots (four polling warps per tile were 14 % of the kernel's executed instructions)
@@ -62,6 +65,7 @@ __device__ __forceinline__ void run_chain(const CednerfMlpDesc& d, const uint8_t
       mbar_wait(bar, phase);
       tc_fence_after();
       tc_fence_before();
+      if (save && l > 0 && gtid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     group_sync(group);
     phase ^= 1;

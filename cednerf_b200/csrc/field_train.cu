@@ -18,19 +18,23 @@
 namespace {
 
 struct SavedLayout {
-  int64_t h1, o1, in2, h2, o2, h3, h4, o4, xn, total;
+  int64_t h1, o1, in2, h2, o2, h3, h4, o4, xn, total, tiles;
 };
 
 __host__ __device__ inline SavedLayout saved_layout(const CednerfFieldDesc& d, int64_t n) {
   SavedLayout s;
   int64_t off = 0;
-  s.h1 = off, off += (int64_t)(d.f1.n_layers - 1) * n * 128;
+  // hidden activations: tile-blocked, every 128-sample tile as its 16 KB swizzled shared-memory image (one TMA bulk
+  // copy out in the forward, one in in the backward), [layer][tile]; everything else row-major per sample
+  const int64_t tiles = (n + MLP_TILE - 1) / MLP_TILE;
+  s.tiles = tiles;
+  s.h1 = off, off += (int64_t)(d.f1.n_layers - 1) * tiles * MLP_TILE_BYTES;
   s.o1 = off, off += n * 32;
   s.in2 = off, off += n * d.f2.dim_in[0] * 2;
-  s.h2 = off, off += (int64_t)(d.f2.n_layers - 1) * n * 128;
+  s.h2 = off, off += (int64_t)(d.f2.n_layers - 1) * tiles * MLP_TILE_BYTES;
   s.o2 = off, off += n * 32;
-  s.h3 = off, off += (int64_t)(d.f3.n_layers - 1) * n * 128;
-  s.h4 = off, off += d.f4.n_layers > 0 ? (int64_t)(d.f4.n_layers - 1) * n * 128 : 0;
+  s.h3 = off, off += (int64_t)(d.f3.n_layers - 1) * tiles * MLP_TILE_BYTES;
+  s.h4 = off, off += d.f4.n_layers > 0 ? (int64_t)(d.f4.n_layers - 1) * tiles * MLP_TILE_BYTES : 0;
   s.o4 = off, off += d.f4.n_layers > 0 ? n * 64 : 0;
   s.xn = off, off += (n * 12 + 15) / 16 * 16;
   s.total = off;
@@ -161,8 +165,8 @@ __global__ void __launch_bounds__(768, 1) field_train_fwd_kernel(TrainArgs a) {
     fence_proxy_async();
     tc_fence_before();
     group_sync(group);
-    run_chain(d.f1, w1, abuf, tmem_base, tmem_warp, bar, phase, gtid, group, reinterpret_cast<__half*>(a.saved + sl.h1),
-              n * 64, tile * MLP_TILE, rows_valid);
+    run_chain(d.f1, w1, abuf, tmem_base, tmem_warp, bar, phase, gtid, group, a.saved + sl.h1,
+              sl.tiles, tile * MLP_TILE, rows_valid);
     float xn[3], mv[3], mvnorm;
     bool selector;
     {
@@ -224,8 +228,8 @@ __global__ void __launch_bounds__(768, 1) field_train_fwd_kernel(TrainArgs a) {
     tc_fence_before();
     group_sync(group);
     // (the density net's input rows are kept too: weight gradient of its first layer, huber target of the predictor)
-    run_chain(d.f2, w2, abuf, tmem_base, tmem_warp, bar, phase, gtid, group, reinterpret_cast<__half*>(a.saved + sl.h2),
-              n * 64, tile * MLP_TILE, rows_valid, a.saved + sl.in2);
+    run_chain(d.f2, w2, abuf, tmem_base, tmem_warp, bar, phase, gtid, group, a.saved + sl.h2,
+              sl.tiles, tile * MLP_TILE, rows_valid, a.saved + sl.in2);
     {
       uint32_t o2[16];
       tmem_ld16(tmem_warp, o2);
@@ -249,8 +253,8 @@ __global__ void __launch_bounds__(768, 1) field_train_fwd_kernel(TrainArgs a) {
     fence_proxy_async();
     tc_fence_before();
     group_sync(group);
-    run_chain(d.f3, w3, abuf, tmem_base, tmem_warp, bar, phase, gtid, group, reinterpret_cast<__half*>(a.saved + sl.h3),
-              n * 64, tile * MLP_TILE, rows_valid);
+    run_chain(d.f3, w3, abuf, tmem_base, tmem_warp, bar, phase, gtid, group, a.saved + sl.h3,
+              sl.tiles, tile * MLP_TILE, rows_valid);
     {
       uint32_t r[16];
       tmem_ld16(tmem_warp, r);
@@ -266,8 +270,8 @@ __global__ void __launch_bounds__(768, 1) field_train_fwd_kernel(TrainArgs a) {
       fence_proxy_async();
       tc_fence_before();
       group_sync(group);
-      run_chain(d.f4, w4, abuf, tmem_base, tmem_warp, bar, phase, gtid, group, reinterpret_cast<__half*>(a.saved + sl.h4),
-                n * 64, tile * MLP_TILE, rows_valid);
+      run_chain(d.f4, w4, abuf, tmem_base, tmem_warp, bar, phase, gtid, group, a.saved + sl.h4,
+                sl.tiles, tile * MLP_TILE, rows_valid);
 #pragma unroll
       for (int cb = 0; cb < 2; ++cb) {
         uint32_t r[16];
@@ -494,18 +498,39 @@ __global__ void __launch_bounds__(BWD_GROUPS * MLP_TILE, 1) field_bwd_kernel(Tra
   const SavedLayout sl = saved_layout(a.d, n);
   const BwdWorkLayout wl = bwd_layout(a.d, n);
   const uint8_t* image = a.img[NET - 1];
-  const __half* hidden = reinterpret_cast<const __half*>(
-      a.saved + (NET == 1 ? sl.h1 : (NET == 2 ? sl.h2 : (NET == 3 ? sl.h3 : sl.h4))));
+  const uint8_t* hidden = a.saved + (NET == 1 ? sl.h1 : (NET == 2 ? sl.h2 : (NET == 3 ? sl.h3 : sl.h4)));
+  __shared__ uint64_t lbars[BWD_GROUPS];  // completion of the TMA loads of this group's activation tiles
+  uint64_t* lbar = &lbars[group];
+  uint32_t lphase = 0;
+  // one elected thread fetches the saved 16 KB tile image (layer, tile) into an operand buffer with one bulk copy
+  auto fetch_tile = [&](uint8_t* dst, int layer, int64_t tile_idx) {
+    if (gtid == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(lbar)), "r"((uint32_t)MLP_TILE_BYTES)
+                   : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                   "l"(hidden + ((int64_t)layer * sl.tiles + tile_idx) * MLP_TILE_BYTES), "r"((uint32_t)MLP_TILE_BYTES),
+                   "r"(smem_u32(lbar))
+                   : "memory");
+    }
+  };
+  auto await_tile = [&]() {  // every thread of the group: the fetched tile is in shared memory
+    mbar_wait(lbar, lphase);
+    lphase ^= 1;
+  };
   float* d_params = a.d_params[NET - 1];
   const int L = d.n_layers;
   for (int q = tid; q < d.image_bytes / 16; q += blockDim.x)
     reinterpret_cast<uint4*>(wsm)[q] = __ldg(reinterpret_cast<const uint4*>(image) + q);
   if (warp == 0) tmem_alloc(&tmem_base_s, a.tmem_cols);
-  if (gtid == 0) mbar_init(bar, 1);
+  if (gtid == 0) {
+    mbar_init(bar, 1);
+    mbar_init(lbar, 1);
+  }
   if (tid == 0) fence_barrier_init();
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
+  if (gtid == 0) fence_barrier_init();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   const uint32_t tmem_grp = tmem_base + 64u * (uint32_t)group;                    // dgrad accumulator of this group
@@ -567,10 +592,10 @@ __global__ void __launch_bounds__(BWD_GROUPS * MLP_TILE, 1) field_bwd_kernel(Tra
     const int rows_valid = (int)((nl - row0) < MLP_TILE ? (nl - row0) : MLP_TILE);
     const int64_t s = row0 + gtid;
     const bool ok = gtid < rows_valid;
-    if (L > 1) load_tile_async(ibuf[0], hidden + ((int64_t)(L - 2) * n + row0) * 64, 64, rows_valid, gtid, MLP_TILE);
+    if (L > 1) fetch_tile(ibuf[0], L - 2, tile);
     else make_input<NET>(a, sl, ibuf[0], gtid, s, ok);
     make_dout<NET>(a, sl, wl, gbuf, gtid, s, ok);
-    cp_async_wait_all();
+    if (L > 1) await_tile();
     fence_proxy_async();
     tc_fence_before();
     group_sync(group);
@@ -597,7 +622,7 @@ __global__ void __launch_bounds__(BWD_GROUPS * MLP_TILE, 1) field_bwd_kernel(Tra
         umma_commit(bar);
       }
       if (l > 0) {
-        if (l > 1) load_tile_async(ibuf[cur ^ 1], hidden + ((int64_t)(l - 2) * n + row0) * 64, 64, rows_valid, gtid, MLP_TILE);
+        if (l > 1) fetch_tile(ibuf[cur ^ 1], l - 2, tile);
         else make_input<NET>(a, sl, ibuf[cur ^ 1], gtid, s, ok);
       }
       if ((gtid >> 5) == 0) {  // one polling warp per group, the others block on the named barrier
@@ -685,7 +710,7 @@ __global__ void __launch_bounds__(BWD_GROUPS * MLP_TILE, 1) field_bwd_kernel(Tra
           }
         }
       }
-      cp_async_wait_all();  // the prefetched next-layer tile has landed
+      if (l > 1) await_tile();  // the prefetched next-layer tile has landed
       fence_proxy_async();
       tc_fence_before();
       group_sync(group);
