@@ -12,7 +12,8 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcednerf_b200.so")
+# CEDNERF_B200_LIB: an instrumented build of the same library (make -C cednerf_b200/csrc debug), for profiles/tools only
+LIB_PATH = os.environ.get("CEDNERF_B200_LIB") or os.path.join(_HERE, "libcednerf_b200.so")
 
 MAX_LEVELS = 32
 MLP_MAX_LAYERS = 5

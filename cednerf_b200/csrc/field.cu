@@ -49,6 +49,22 @@ struct FieldFwdArgs {
 
 #define FIELD_MAX_GROUPS 8
 
+// -DFIELD_PHASE_CLOCKS (the libcednerf_b200_dbg.so of `make debug`, profiles/tools/exp_field_fwd.py): the first thread of
+// every warp-group adds the cycles each phase of a tile took to g_phase_clocks; slot 7 counts tiles.
+#ifdef FIELD_PHASE_CLOCKS
+__device__ unsigned long long g_phase_clocks[8];
+#define PHASE_MARK(i)                                                      \
+  do {                                                                     \
+    if (gtid == 0) {                                                       \
+      const long long now_ = clock64();                                    \
+      atomicAdd(&g_phase_clocks[i], (unsigned long long)(now_ - phase_t)); \
+      phase_t = now_;                                                      \
+    }                                                                      \
+  } while (0)
+#else
+#define PHASE_MARK(i) do {} while (0)
+#endif
+
 __global__ void __launch_bounds__(896, 1) field_fwd_kernel(FieldFwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -98,6 +114,10 @@ __global__ void __launch_bounds__(896, 1) field_fwd_kernel(FieldFwdArgs a) {
   for (int64_t tile = blockIdx.x + (int64_t)gridDim.x * group; tile < n_tiles; tile += (int64_t)gridDim.x * n_groups) {
     const int64_t s = tile * MLP_TILE + gtid;
     const bool ok = s < n_live;
+#ifdef FIELD_PHASE_CLOCKS
+    long long phase_t = clock64();
+    if (gtid == 0) atomicAdd(&g_phase_clocks[7], 1ull);
+#endif
     // ---- the sample: position, time, direction (cednerf/utils.py:74-104) -------------------------------------
     float x[3] = {0.f, 0.f, 0.f}, tv = 0.f;
     if (ok) {
@@ -131,7 +151,9 @@ __global__ void __launch_bounds__(896, 1) field_fwd_kernel(FieldFwdArgs a) {
     fence_proxy_async();
     tc_fence_before();
     group_sync(group);
+    PHASE_MARK(0);  // sample + Frequency row
     run_chain(d.f1, w1, abuf0, tmem_base, tmem_warp, bar, phase, gtid, group);
+    PHASE_MARK(1);  // deformation net
     float xn[3], mvnorm;
     bool selector = true;
     {
@@ -149,6 +171,7 @@ __global__ void __launch_bounds__(896, 1) field_fwd_kernel(FieldFwdArgs a) {
       }
       mvnorm = sqrtf(mv[0] * mv[0] + mv[1] * mv[1] + mv[2] * mv[2]);
     }
+    PHASE_MARK(2);  // move, normalise, selector
     // ---- density net input: [hash 2L | time 9 | 1.0 padding] (model.py:384-403) -------------------------------
     float temb[9];
     {
@@ -175,6 +198,7 @@ __global__ void __launch_bounds__(896, 1) field_fwd_kernel(FieldFwdArgs a) {
           put_word(l0, f1w[0]);
         }
       }
+      PHASE_MARK(3);  // hash gathers + blends
       if (d.time_mode) time_embedding(tv, mvnorm, d.time_mode, temb);  // after the gathers: keeps registers free
       int w = L;
       if (d.time_mode && d.time_before_sigma) {
@@ -189,7 +213,9 @@ __global__ void __launch_bounds__(896, 1) field_fwd_kernel(FieldFwdArgs a) {
     fence_proxy_async();
     tc_fence_before();
     group_sync(group);
+    PHASE_MARK(4);  // time embedding, padding, fence + barrier
     run_chain(d.f2, w2, abuf0, tmem_base, tmem_warp, bar, phase, gtid, group);
+    PHASE_MARK(5);  // density net
     uint32_t o2[16];
     tmem_ld16(tmem_warp, o2);
     tmem_ld_wait();
@@ -210,6 +236,7 @@ __global__ void __launch_bounds__(896, 1) field_fwd_kernel(FieldFwdArgs a) {
     if (!want_rgb) {
       tc_fence_before();
       group_sync(group);
+      PHASE_MARK(6);  // sigma out + closing barrier
       continue;
     }
     // ---- colour net input: [SH4(dir) | 15 geometry features (| time 9) | 1.0 padding] (model.py:447-466) --------
@@ -373,3 +400,12 @@ CEDNERF_EXPORT int cednerf_occ_update_level(const int64_t* cells, int64_t n, con
   }
   return cednerf_check_launch("cednerf_occ_update_level", launches);
 }
+
+#ifdef FIELD_PHASE_CLOCKS
+// debug build only: copy the accumulated phase clocks to `out` (8 x uint64 on the host) and clear them
+CEDNERF_EXPORT int cednerf_debug_phase_clocks(unsigned long long* out) {
+  unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (cudaMemcpyFromSymbol(out, g_phase_clocks, sizeof(zero)) != cudaSuccess) return 1;
+  return cudaMemcpyToSymbol(g_phase_clocks, zero, sizeof(zero)) != cudaSuccess;
+}
+#endif

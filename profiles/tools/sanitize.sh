@@ -9,7 +9,7 @@ for tool in memcheck racecheck initcheck synccheck; do
   extra=""
   [ "$tool" = initcheck ] && extra="--track-unused-memory no"
   [ "$tool" = racecheck ] && extra="--racecheck-report all"
-  timeout 900 compute-sanitizer --tool $tool $extra --print-limit 40 --launch-timeout 0 \
+  timeout ${SAN_TIMEOUT:-900} compute-sanitizer --tool $tool $extra --print-limit 40 --launch-timeout 0 \
     python -c "import __graft_entry__ as g; g.smoke()" > "$out/sanitizer_$tool.log" 2>&1
   echo "exit code $?" >> "$out/sanitizer_$tool.log"
   tail -4 "$out/sanitizer_$tool.log"
