@@ -91,22 +91,6 @@ hashgrid_bwd_kernel(const float* __restrict__ x, int x_stride, int64_t n, const 
   for (int k = 0; k < 8; ++k)
     idx[k] = off + corner_index(c.g[0] + (k & 1), c.g[1] + ((k >> 1) & 1), c.g[2] + ((k >> 2) & 1), res, size, hashed);
 
-  if (FOUR_D) {
-    if (!active || (d0 == 0.f && d1 == 0.f)) return;
-    int kf;
-    float tau;
-    keyframe(xs[3], taichi_compat, kf, tau);
-    const float om = 1.f - tau;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float w = corner_weight(c, k);
-      float2* dst = reinterpret_cast<float2*>(g_table + (size_t)idx[k] * 8 + 2 * kf);
-      atomicAdd(dst, make_float2(w * d0 * om, w * d1 * om));
-      atomicAdd(dst + 1, make_float2(w * d0 * tau, w * d1 * tau));
-    }
-    return;
-  }
-
   float gx[3] = {0.f, 0.f, 0.f};
   if (g_x) {
     __half2 v[8];
@@ -183,13 +167,19 @@ struct LevelList {
   int id[CEDNERF_MAX_LEVELS];
 };
 
-template <typename GradT, bool LEVEL_MAJOR, bool CACHED>
+// FOUR_D (xyz + t key-frame table, 8 floats per entry: 4 key-frames x 2 features, hash_encoder_inter.py:202-275): a corner
+// receives (w dy om, w dy tau) at key-frames k and k + 1, i.e. FOUR CONSECUTIVE floats at float offset 2k of its entry - one
+// 16-byte reduction when k is even, two 8-byte ones when k = 1.  Runs additionally break where the key-frame changes
+// (samples of one ray share their timestamp, so in practice they do not).
+template <typename GradT, bool LEVEL_MAJOR, bool CACHED, bool FOUR_D = false>
 __global__ void __launch_bounds__(256)
 hashgrid_bwd_table_kernel(const float* __restrict__ x, int x_stride, int64_t n, CednerfGridLevels lv, LevelList list,
                           const GradT* __restrict__ dy, int dy_stride, float* __restrict__ g_table, int64_t chunk,
-                          const int64_t* __restrict__ n_dev) {
-  __shared__ uint32_t tags[CACHED ? TG_SLOTS : 1];
-  __shared__ float vals[CACHED ? 2 * TG_SLOTS : 1];
+                          const int64_t* __restrict__ n_dev, int taichi_compat = 0) {
+  constexpr int EW = FOUR_D ? 8 : 2;                          // floats per table entry
+  constexpr int SLOTS = FOUR_D ? TG_SLOTS / 2 : TG_SLOTS;     // 4-D: 1024 slots x 32 B = 32 KB of shared memory
+  __shared__ uint32_t tags[CACHED ? SLOTS : 1];
+  __shared__ float vals[CACHED ? EW * SLOTS : 1];
   // n: capacity of the sample arrays (and the level stride of a level-major dy); n_dev (nullable): live sample count
   int64_t n_live = n;
   if (n_dev) {
@@ -204,13 +194,34 @@ hashgrid_bwd_table_kernel(const float* __restrict__ x, int x_stride, int64_t n, 
   const float scale = lv.scale[l];
   float2* t2 = reinterpret_cast<float2*>(g_table) + off;
   if (CACHED) {
-    for (int q = threadIdx.x; q < TG_SLOTS; q += blockDim.x) tags[q] = TG_EMPTY, vals[2 * q] = 0.f, vals[2 * q + 1] = 0.f;
+    for (int q = threadIdx.x; q < SLOTS; q += blockDim.x) tags[q] = TG_EMPTY;
+    for (int q = threadIdx.x; q < EW * SLOTS; q += blockDim.x) vals[q] = 0.f;
     __syncthreads();
   }
+  // 4-D: four floats at float offset 2 kf of entry i
+  auto add4 = [&](uint32_t i, int kf, const float* v) {
+    if (v[0] == 0.f && v[1] == 0.f && v[2] == 0.f && v[3] == 0.f) return;
+    if (CACHED) {
+      const uint32_t slot = i & (SLOTS - 1);
+      const uint32_t old = atomicCAS(&tags[slot], TG_EMPTY, i);
+      if (old == TG_EMPTY || old == i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) atomicAdd(&vals[EW * slot + 2 * kf + j], v[j]);
+        return;
+      }
+    }
+    float* dst = g_table + ((size_t)off + i) * 8 + 2 * kf;
+    if ((kf & 1) == 0) {
+      atomicAdd(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
+    } else {
+      atomicAdd(reinterpret_cast<float2*>(dst), make_float2(v[0], v[1]));
+      atomicAdd(reinterpret_cast<float2*>(dst) + 1, make_float2(v[2], v[3]));
+    }
+  };
   auto add = [&](uint32_t i, float a, float b) {  // i: index inside the level
     if (a == 0.f && b == 0.f) return;
     if (CACHED) {
-      const uint32_t slot = i & (TG_SLOTS - 1);
+      const uint32_t slot = i & (SLOTS - 1);
       const uint32_t old = atomicCAS(&tags[slot], TG_EMPTY, i);
       if (old == TG_EMPTY || old == i) {
         atomicAdd(&vals[2 * slot], a);
@@ -239,7 +250,14 @@ hashgrid_bwd_table_kernel(const float* __restrict__ x, int x_stride, int64_t n, 
     // run structure: a lane starts a run when its cell differs from the previous lane's
     const uint32_t px = __shfl_up_sync(0xffffffffu, c.g[0], 1), py = __shfl_up_sync(0xffffffffu, c.g[1], 1),
                    pz = __shfl_up_sync(0xffffffffu, c.g[2], 1);
-    const bool head = lane == 0 || px != c.g[0] || py != c.g[1] || pz != c.g[2];
+    int kf = 0;
+    float tau = 0.f, om = 1.f;
+    if (FOUR_D) {
+      keyframe(x[s * x_stride + 3], taichi_compat, kf, tau);
+      om = 1.f - tau;
+    }
+    const int pk = __shfl_up_sync(0xffffffffu, kf, 1);
+    const bool head = lane == 0 || px != c.g[0] || py != c.g[1] || pz != c.g[2] || (FOUR_D && pk != kf);
     const unsigned heads = __ballot_sync(0xffffffffu, head);
     const int run_start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));  // highest head at or below this lane
     const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
@@ -266,6 +284,27 @@ hashgrid_bwd_table_kernel(const float* __restrict__ x, int x_stride, int64_t n, 
       hy[0] = 0u, hy[1] = res, hz[0] = 0u, hz[1] = r2;
       plain = x0 < size - (1u + res + r2);
     }
+    if constexpr (FOUR_D) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float v[4];
+        v[0] = w8[k] * d0 * om, v[1] = w8[k] * d1 * om, v[2] = w8[k] * d0 * tau, v[3] = w8[k] * d1 * tau;
+        for (int o = 1; o < max_len; o <<= 1) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float u = __shfl_up_sync(0xffffffffu, v[j], o);
+            if (lane - o >= run_start) v[j] += u;
+          }
+        }
+        if (tail) {
+          uint32_t i;
+          if (hashed) i = ((k & 1) ? x1 : x0) ^ hy[(k >> 1) & 1] ^ hz[k >> 2];
+          else if (plain) i = ((k & 1) ? x1 : x0) + hy[(k >> 1) & 1] + hz[k >> 2];
+          else i = corner_index(c.g[0] + (k & 1), c.g[1] + ((k >> 1) & 1), c.g[2] + (k >> 2), res, size, false);
+          add4(i, kf, v);
+        }
+      }
+    } else {
 #pragma unroll
     for (int kp = 0; kp < 4; ++kp) {
       float v[4];
@@ -301,21 +340,33 @@ hashgrid_bwd_table_kernel(const float* __restrict__ x, int x_stride, int64_t n, 
         }
       }
     }
+    }  // 3-D
   }
   if (CACHED) {
     __syncthreads();
-    for (int q = threadIdx.x; q < TG_SLOTS; q += blockDim.x) {
+    for (int q = threadIdx.x; q < SLOTS; q += blockDim.x) {
       const uint32_t i = tags[q];
-      const float a = vals[2 * q], b = vals[2 * q + 1];
-      if (i != TG_EMPTY && (a != 0.f || b != 0.f)) atomicAdd(t2 + i, make_float2(a, b));
+      if (i == TG_EMPTY) continue;
+      if (FOUR_D) {
+        float4* dst = reinterpret_cast<float4*>(g_table + ((size_t)off + i) * 8);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float4 val = make_float4(vals[EW * q + 4 * h], vals[EW * q + 4 * h + 1], vals[EW * q + 4 * h + 2],
+                                         vals[EW * q + 4 * h + 3]);
+          if (val.x != 0.f || val.y != 0.f || val.z != 0.f || val.w != 0.f) atomicAdd(dst + h, val);
+        }
+      } else {
+        const float a = vals[2 * q], b = vals[2 * q + 1];
+        if (a != 0.f || b != 0.f) atomicAdd(t2 + i, make_float2(a, b));
+      }
     }
   }
 }
 
 // small dense levels -> cached pass (long chunks), the others -> direct pass (one block of 256 samples per CTA)
-template <typename GradT, bool LEVEL_MAJOR>
+template <typename GradT, bool LEVEL_MAJOR, bool FOUR_D = false>
 int launch_table_gradient(const float* x, int x_stride, int64_t n, const CednerfGridLevels& lv, const GradT* dy, int dy_stride,
-                          float* g_table, cudaStream_t st, const int64_t* n_dev = nullptr) {
+                          float* g_table, cudaStream_t st, const int64_t* n_dev = nullptr, int taichi_compat = 0) {
   LevelList cached{}, direct{};
   for (int l = 0; l < lv.n_levels; ++l) {
     // the cache pays where a level has few entries (heavy per-address contention in L2); from 2^20 entries on - hashed
@@ -329,12 +380,14 @@ int launch_table_gradient(const float* x, int x_stride, int64_t n, const Cednerf
     int64_t chunk = ((n + want_ctas - 1) / want_ctas + 255) / 256 * 256;
     if (chunk < 2048) chunk = 2048;
     dim3 grid((unsigned)((n + chunk - 1) / chunk), cached.n);
-    hashgrid_bwd_table_kernel<GradT, LEVEL_MAJOR, true><<<grid, 256, 0, st>>>(x, x_stride, n, lv, cached, dy, dy_stride, g_table, chunk, n_dev);
+    hashgrid_bwd_table_kernel<GradT, LEVEL_MAJOR, true, FOUR_D><<<grid, 256, 0, st>>>(x, x_stride, n, lv, cached, dy, dy_stride,
+                                                                                 g_table, chunk, n_dev, taichi_compat);
     ++launches;
   }
   if (direct.n) {
     dim3 grid(cednerf_blocks(n, 256), direct.n);
-    hashgrid_bwd_table_kernel<GradT, LEVEL_MAJOR, false><<<grid, 256, 0, st>>>(x, x_stride, n, lv, direct, dy, dy_stride, g_table, 256, n_dev);
+    hashgrid_bwd_table_kernel<GradT, LEVEL_MAJOR, false, FOUR_D><<<grid, 256, 0, st>>>(x, x_stride, n, lv, direct, dy, dy_stride,
+                                                                                  g_table, 256, n_dev, taichi_compat);
     ++launches;
   }
   return launches;
@@ -448,14 +501,14 @@ CEDNERF_EXPORT int cednerf_hashgrid4d_bwd(const float* xyzt, int x_stride, int64
   CEDNERF_REQUIRE(check_levels(levels), "bad level table");
   CEDNERF_REQUIRE(n >= 0 && x_stride >= 4 && dy_stride >= 2 * levels->n_levels && g_table, "bad sizes");
   if (n == 0) return 0;
-  dim3 grid(cednerf_blocks(n * levels->n_levels, 256));
-  if (dy_is_f16)
-    hashgrid_bwd_kernel<true, __half><<<grid, 256, 0, (cudaStream_t)stream>>>(
-        xyzt, x_stride, n, nullptr, *levels, (const __half*)dy, dy_stride, g_table, nullptr, taichi_compat);
-  else
-    hashgrid_bwd_kernel<true, float><<<grid, 256, 0, (cudaStream_t)stream>>>(
-        xyzt, x_stride, n, nullptr, *levels, (const float*)dy, dy_stride, g_table, nullptr, taichi_compat);
-  return cednerf_check_launch("cednerf_hashgrid4d_bwd");
+  CEDNERF_REQUIRE(((uintptr_t)g_table & 15) == 0, "4-D gradient table must be 16-byte aligned");
+  // level-major walk with run merging and the shared-memory cache for the small dense levels, as the 3-D table gradient
+  const int launches =
+      dy_is_f16 ? launch_table_gradient<__half, false, true>(xyzt, x_stride, n, *levels, (const __half*)dy, dy_stride, g_table,
+                                                             (cudaStream_t)stream, nullptr, taichi_compat)
+                : launch_table_gradient<float, false, true>(xyzt, x_stride, n, *levels, (const float*)dy, dy_stride, g_table,
+                                                            (cudaStream_t)stream, nullptr, taichi_compat);
+  return cednerf_check_launch("cednerf_hashgrid4d_bwd", launches);
 }
 
 // fp32 master parameters -> fp16 working copy (the reference does this cast on every forward,
