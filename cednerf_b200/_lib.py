@@ -123,6 +123,9 @@ _SIGNATURES = {
     "cednerf_generate_rays": "ppppiffffiilpppp",
     "cednerf_distortion_fwd": "pppplpppp",
     "cednerf_distortion_bwd": "pppplpppp",
+    "cednerf_importance_keys": "ppplpp",
+    "cednerf_topk_select": "pllpppp",
+    "cednerf_importance_batch": "pliiippiffffipppppppp",
     "cednerf_nonfinite_check": "App",
     "cednerf_training_loss_fwd": "ppplppplpiffpppp",
     "cednerf_training_loss_bwd": "pppplpppliffpppppp",
@@ -162,6 +165,8 @@ def load() -> ctypes.CDLL:
         getattr(lib, name).restype = ctypes.c_int64
         getattr(lib, name).argtypes = [ctypes.POINTER(FieldDesc), ctypes.c_int64]
     lib.cednerf_scan_workspace_bytes.argtypes = [ctypes.c_int64]
+    lib.cednerf_topk_workspace_bytes.restype = ctypes.c_int64
+    lib.cednerf_topk_workspace_bytes.argtypes = [ctypes.c_int64]
     for name, sig in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = ctypes.c_int
@@ -173,7 +178,7 @@ def load() -> ctypes.CDLL:
 def exported_symbols():
     return sorted(list(_SIGNATURES) + ["cednerf_last_error", "cednerf_abi_version", "cednerf_check_device",
                                        "cednerf_scan_workspace_bytes", "cednerf_launch_count", "cednerf_field_saved_bytes",
-                                       "cednerf_field_bwd_workspace_bytes", "cednerf_dp_ctrl_bytes"])
+                                       "cednerf_field_bwd_workspace_bytes", "cednerf_dp_ctrl_bytes", "cednerf_topk_workspace_bytes"])
 
 
 def ptr(t: Optional[torch.Tensor]):

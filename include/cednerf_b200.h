@@ -415,6 +415,29 @@ int cednerf_distortion_fwd(const float* weights, const float* t_starts, const fl
 int cednerf_distortion_bwd(const float* weights, const float* t_starts, const float* t_ends, const int64_t* offsets,
                            int64_t n_rays, const float* g_loss, const float* inv_rays, float* g_weights, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Importance-sampled training batches: the training branch of SubjectLoader.fetch_data,
+ * datasets/dnerf_3d_video_IS.py:401-445 (torch.multinomial over the ISG / IST weights of a uniform random subset) and
+ * :447-497 (s x s pixel expansion, colour gather, ray generation).  torch.multinomial without replacement is a top-k of
+ * weights / Exp(1) noise; the three calls below are that top-k and the batch assembly, with no host read.
+ * keys[i] = bits of weights[subset ? subset[i] : i] / exp_noise[i] (0 for non-positive weights). */
+int cednerf_importance_keys(const float* weights, const int64_t* subset /*nullable*/, const float* exp_noise, int64_t n,
+                            uint32_t* keys, void* stream);
+int64_t cednerf_topk_workspace_bytes(int64_t n);
+/* out [k]: the positions (mapped through `subset` when given) of the k largest keys, in ascending position order; ties at
+ * the threshold go to the lowest positions.  The int32 at byte 16 of the workspace is set to 1 when the k-th largest key
+ * is zero (fewer than k positive weights: torch.multinomial raises there). */
+int cednerf_topk_select(const uint32_t* keys, int64_t n, int64_t k, const int64_t* subset /*nullable*/, int64_t* out,
+                        void* workspace, void* stream);
+/* Ray j = sub * k + i (sub = ah * s + aw) is pixel (xsub * s + aw, ysub * s + ah) of image cells[i] / (hsub * wsub) with
+ * hsub = height / s, wsub = width / s: rgb = images[image, y, x] / 255, the ray of cednerf_generate_rays, the image's
+ * timestamp.  images uint8 [n_images, height, width, 3]; c2w [n_images, c2w_rows, 4]; timestamps [n_images];
+ * image_id_out / pixel_index_out nullable. */
+int cednerf_importance_batch(const int64_t* cells, int64_t k, int subsample, int width, int height, const uint8_t* images,
+                             const float* c2w, int c2w_rows, float fx, float fy, float cx, float cy, int opengl,
+                             const float* timestamps, float* origins, float* viewdirs, float* rgb, float* timestamps_out,
+                             int64_t* image_id_out, int64_t* pixel_index_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -134,3 +134,33 @@ def test_distortion_restatement_against_its_definition():
     (gb,) = torch.autograd.grad(b, w2)
     torch.testing.assert_close(a, b, rtol=1e-12, atol=1e-14)
     torch.testing.assert_close(ga, gb, rtol=1e-10, atol=1e-13)
+
+
+def test_multinomial_restatement_is_torch_multinomial():
+    """oracle/dataset_ref.py states torch.multinomial(w, k) without replacement as topk(w / Exp(1) draws, k): pinned here
+    to torch.multinomial ITSELF under the same generator state (ATen's implementation runs on the CPU in this container),
+    and the fetch_data restatement to the reference's index arithmetic on a hand-checked case."""
+    from oracle import dataset_ref as dr
+
+    for seed, n, k in ((0, 1000, 64), (1, 50000, 4096), (2, 17, 17)):
+        w = torch.rand(n, generator=torch.Generator().manual_seed(100 + seed)) ** 4
+        w[::7] = 0.0 if k < n else w[::7]
+        want = torch.multinomial(w, k, generator=torch.Generator().manual_seed(seed))
+        noise = torch.empty_like(w).exponential_(1, generator=torch.Generator().manual_seed(seed))
+        got = dr.multinomial_without_replacement(w, k, noise)
+        assert torch.equal(got, want)
+    # cell -> pixel expansion (dnerf_3d_video_IS.py:424-441): cell 5 of a 2-image set of 4 x 6 frames subsampled by 2
+    # (hsub 2, wsub 3) is image 0, ysub 1, xsub 2 -> pixels (x, y) = (4, 2), (5, 2), (4, 3), (5, 3)
+    images = torch.arange(2 * 4 * 6 * 3, dtype=torch.int64).remainder(251).to(torch.uint8).view(2, 4, 6, 3)
+    c2w = torch.eye(4)[None, :3].repeat(2, 1, 1)
+    K = torch.tensor([[5.0, 0, 3.0], [0, 5.0, 2.0], [0, 0, 1.0]])
+    w = torch.zeros(2 * 2 * 3)
+    w[5] = 1.0
+    out = dr.fetch_data_train(images, c2w, K, torch.tensor([[0.25], [0.75]]), w, 2, 4, 6, 4, False, None, torch.ones(12))
+    assert out["cells"].tolist() == [5] and out["idx"].tolist() == [0, 0, 0, 0]
+    want_px = [(4, 2), (5, 2), (4, 3), (5, 3)]
+    for j, (x, y) in enumerate(want_px):
+        assert torch.equal(out["rgb"][j], images[0, y, x] / 255.0)
+        d = torch.tensor([(x - 3.0 + 0.5) / 5.0, (y - 2.0 + 0.5) / 5.0, 1.0])
+        torch.testing.assert_close(out["viewdirs"][j], d / d.norm(), rtol=0, atol=1e-7)
+    assert torch.equal(out["timestamps"], torch.full((4, 1), 0.25))
