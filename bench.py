@@ -351,7 +351,10 @@ def roofline_of(agg, n_iter, total_ms):
             "frac": round(achieved / hbm_peak, 4), "traffic": traffic, "peak_source": src,
             "avg_launch_ms": round(d["ms"] / d["launches"], 4), "bytes_per_launch": d["bytes"] // d["launches"],
             "share_of_step": round(d["ms"] / n_iter / total_ms, 3),
-            "step_bytes": int(step_bytes), "step_frac": round(step_bytes / (total_ms * 1e-3) / 1e9 / hbm_peak, 4)}
+            "step_bytes": int(step_bytes), "step_frac": round(step_bytes / (total_ms * 1e-3) / 1e9 / hbm_peak, 4),
+            "limiter": ("the 96 MB fp16 table is L2-resident (DRAM 2 %): the kernel is paced by instruction issue and the L1 "
+                        "tag stage of its divergent gathers, so the HBM fraction is a lower bound on how well it uses what "
+                        "binds it (profiles/r2o_field_fwd_phase_experiments.md)") if top == "cednerf_field_fwd" else None}
 
 
 class Dist:
@@ -642,6 +645,56 @@ def render_leg(D, cb, workload, cfg, args, poses, times, opengl, bkgd, profile: 
     return out
 
 
+def encoder4d_leg(cb, workload, dev, log2_samples=22):
+    """North-star kernel (2) on its own: the 4-D (xyz + t key-frame) hash encoder of hash_encoder_inter.py:279-430 at full
+    size (16 levels, 2^21 entries x 8 fp16 per hashed level: a 383 MB table, NOT L2-resident) on the packed samples of a
+    DyNeRF-shaped batch.  Algorithmic bytes per sample: forward 16 x 8 x 16 B + 16 B + 64 B, backward 64 B
+    + 16 B + 16 x 8 x 16 B of fp32 gradient; fraction of the measured HBM copy bandwidth."""
+    cfg = workload.DYNERF
+    rk = workload.render_kwargs(cfg)
+    enc = cb.hash_encoder.HashEncoder4D(max_params=2 ** 21, levels=16, base_res=16.0, max_res=2048.0, seed=3).to(dev)
+    est, _ = workload.build_scene(cfg, dev, cb, seed=42)
+    est.train()
+    b = {k: v.to(dev) for k, v in workload.draw_batch(cfg, 262144, torch.Generator().manual_seed(1000)).items()}
+    with torch.no_grad():
+        ridx, t0, t1 = est.sampling(b["origins"], b["viewdirs"], stratified=True, jitter=b["jitter"], **rk)
+    n = min(2 ** log2_samples, ridx.numel())
+    x = b["origins"][ridx[:n]] + b["viewdirs"][ridx[:n]] * ((t0[:n] + t1[:n]) / 2)[:, None]
+    lo, hi = (torch.tensor(cfg.roi_aabb[k:k + 3], device=dev) for k in (0, 3))
+    pts = torch.cat([((x - lo) / (hi - lo)).clamp(0, 1), b["timestamps"][ridx[:n]]], -1).contiguous()
+    dy = torch.randn(n, 32, device=dev).half()
+    peak = peaks()[0]
+
+    def timed(fn, k):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / k
+
+    with torch.no_grad():
+        fwd = timed(lambda: enc(pts), 10)
+    y = enc(pts)
+
+    def bwd():
+        enc.hash_table.grad = None
+        y.backward(dy, retain_graph=True)
+
+    zero = timed(lambda: torch.zeros_like(enc.hash_table), 5)
+    tot = timed(bwd, 5)
+    fb, bb = 2128.0 * n, 2128.0 * n
+    return {"workload": "4-D hash encoder, 16 levels x 2^21 x 8 fp16 (383 MB table), packed samples of a DyNeRF-shaped batch",
+            "samples": n, "fwd_ms": round(fwd, 4), "fwd_gbs": round(fb / fwd / 1e6, 1), "fwd_frac": round(fb / fwd / 1e6 / peak, 4),
+            "bwd_ms": round(tot - zero, 4), "bwd_gbs": round(bb / (tot - zero) / 1e6, 1),
+            "bwd_frac": round(bb / (tot - zero) / 1e6 / peak, 4), "bound": "hbm", "peak_gbs": peak,
+            "bytes_per_sample": 2128}
+
+
 def run_ours(args):
     import cednerf_b200 as cb
     from cednerf_b200 import workload
@@ -725,6 +778,8 @@ def run_ours(args):
         others["hypernerf"] = {"rays_per_s": round(h["rays"] / (h["ms"] * 1e-3), 1), "ms_per_step": round(h["ms"], 4),
                                "samples_per_s": round(h["samples"] / (h["ms"] * 1e-3), 1),
                                "samples_per_ray": round(h["samples"] / h["rays"], 3), "rays_per_gpu": args.rays}
+        if world == 1:  # north-star kernel (2) at full size, on its own (it is not on the canonical recipes' path)
+            others["encoder4d"] = encoder4d_leg(cb, workload, D.dev)
         if world > 1:   # configs[4]: 2^20 rays per step split over the ranks
             s = train_leg(D, cb, workload, workload.DYNERF, args, 2 ** 20 // world, 10, 3, False)
             others["dynerf_2p20"] = {"rays_per_s": round(s["rays"] / (s["ms"] * 1e-3), 1), "ms_per_step": round(s["ms"], 4),

@@ -447,6 +447,14 @@ class OccGridEstimator(torch.nn.Module):
             x = self.aabbs[l, :3] + x * (self.aabbs[l, 3:] - self.aabbs[l, :3])
             occ = occ_eval_fn(x).squeeze(-1).float()
             cell = l * cpl + idx
+            if getattr(self, "duplicate_rule", "last") == "max":
+                # a cell drawn several times (uniform + occupied draws after the warm-up): nerfacc's indexed assignment
+                # keeps ONE of the candidates, which one is undefined on CUDA; "max" is the deterministic choice the
+                # product makes (the largest candidate), "last" what index_put does on the CPU
+                uniq = torch.unique(cell)
+                cand = torch.full_like(self.occs, -1.0).scatter_reduce(0, cell, occ, "amax", include_self=True)
+                self.occs[uniq] = torch.maximum(self.occs[uniq] * ema_decay, cand[uniq])
+                continue
             self.occs[cell] = torch.maximum(self.occs[cell] * ema_decay, occ)
         thre = torch.clamp(self.occs[self.occs >= 0].mean(), max=occ_thre)
         self.binaries = (self.occs > thre).view(self.binaries.shape)

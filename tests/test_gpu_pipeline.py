@@ -172,7 +172,7 @@ def test_estimator_update_matches_oracle(cb, golden):
         # same starting state on both sides (the rule for duplicate cells differs, see below)
         est.occs.copy_(est_ref.occs.to(DEV))
         est.binaries = est_ref.binaries.to(DEV)
-        before = est_ref.occs.clone()
+        before, binaries_before = est_ref.occs.clone(), est_ref.binaries.clone()
         est_ref.update_every_n_steps(step, occ_fn, occ_thre=1e-2, rng=nf.HostRng(step))
         est.update_every_n_steps(step, occ_fn, occ_thre=1e-2, rng=nf.HostRng(step, device=DEV))
         got, want = est.occs.cpu(), est_ref.occs
@@ -180,6 +180,13 @@ def test_estimator_update_matches_oracle(cb, golden):
             torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-8)
             assert int((est.binaries.cpu() != est_ref.binaries).sum()) <= 2  # threshold ties only
         else:
+            # the same update with the oracle resolving duplicate cells the way the product does (largest candidate):
+            # every cell agrees, as in the warm-up
+            est_max = nf.OccGridEstimator([-1.0, -1.0, -1.0, 1.0, 1.0, 1.0], resolution=16, levels=2).train()
+            est_max.occs, est_max.binaries, est_max.duplicate_rule = before.clone(), binaries_before.clone(), "max"
+            est_max.update_every_n_steps(step, occ_fn, occ_thre=1e-2, rng=nf.HostRng(step))
+            torch.testing.assert_close(got, est_max.occs, rtol=1e-5, atol=1e-8)
+            assert int((est.binaries.cpu() != est_max.binaries).sum()) <= 2
             # cells drawn more than once: the oracle keeps the last candidate (CPU index_put), the product the
             # largest (nerfacc on CUDA: undefined).  Both are candidates, so got >= want, and most cells agree.
             assert bool((got >= want - 1e-7).all()) and bool((got >= before * 0.95 - 1e-7).all())
