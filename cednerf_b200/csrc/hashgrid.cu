@@ -12,10 +12,9 @@
 
 namespace {
 
-template <bool FOUR_D>
 __global__ void __launch_bounds__(256)
 hashgrid_fwd_kernel(const float* __restrict__ x, int x_stride, int64_t n, const __half* __restrict__ table,
-                    CednerfGridLevels lv, __half* __restrict__ out, int out_stride, int taichi_compat) {
+                    CednerfGridLevels lv, __half* __restrict__ out, int out_stride) {
   const int L = lv.n_levels;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t s = tid / L;
@@ -29,7 +28,7 @@ hashgrid_fwd_kernel(const float* __restrict__ x, int x_stride, int64_t n, const 
   float wgt[8];
   cell_corners(c, res, size, off, hashed, idx, wgt);
   float a0 = 0.f, a1 = 0.f;
-  if (!FOUR_D) {
+  {
     __half2 v[8];
     const __half2* t2 = reinterpret_cast<const __half2*>(table);
 #pragma unroll
@@ -40,27 +39,72 @@ hashgrid_fwd_kernel(const float* __restrict__ x, int x_stride, int64_t n, const 
       a0 = __fadd_rn(a0, __fmul_rn(wgt[k], f.x));
       a1 = __fadd_rn(a1, __fmul_rn(wgt[k], f.y));
     }
-  } else {
-    int kf;
-    float tau;
-    keyframe(xs[3], taichi_compat, kf, tau);
-    const float om = __fsub_rn(1.f, tau);
-    uint4 v[8];
-    const uint4* t8 = reinterpret_cast<const uint4*>(table);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = __ldg(t8 + idx[k]);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const uint32_t words[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
-      const uint32_t lo_w = words[kf], hi_w = words[kf + 1];
-      const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&lo_w));
-      const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&hi_w));
-      const float w = wgt[k];
-      a0 = __fadd_rn(a0, __fmul_rn(w, __fadd_rn(__fmul_rn(lo.x, om), __fmul_rn(hi.x, tau))));
-      a1 = __fadd_rn(a1, __fmul_rn(w, __fadd_rn(__fmul_rn(lo.y, om), __fmul_rn(hi.y, tau))));
-    }
   }
   *reinterpret_cast<__half2*>(out + s * out_stride + 2 * l) = __floats2half2_rn(a0, a1);
+}
+
+// 4-D forward, one thread per SAMPLE walking the levels (the stand-alone 3-D forward above keeps a thread per (sample,
+// level)): the lanes of a warp are 32 consecutive samples - neighbours on a ray - so a level's eight 16-byte gathers
+// touch one or two sectors per warp at the coarse and middle levels instead of 32 (with level-fastest lanes every lane of
+// a gather sat in a different level, i.e. a different sector: the L1 data stage ran at 66 % with DRAM at 52 %), and a
+// sample's 32 features leave as four 16-byte stores.  Two levels (16 gathers of 16 bytes) in flight per thread.  Same
+// arithmetic per (sample, level), operation by operation, as the kernel above: bit-identical features.
+template <int LG>
+__global__ void __launch_bounds__(256)
+hashgrid4d_fwd_sample_kernel(const float* __restrict__ x, int x_stride, int64_t n, const __half* __restrict__ table,
+                             CednerfGridLevels lv, __half* __restrict__ out, int out_stride, int taichi_compat) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const float xs[4] = {x[s * x_stride], x[s * x_stride + 1], x[s * x_stride + 2], x[s * x_stride + 3]};
+  int kf;
+  float tau;
+  keyframe(xs[3], taichi_compat, kf, tau);
+  const float om = __fsub_rn(1.f, tau);
+  const uint4* t8 = reinterpret_cast<const uint4*>(table);
+  const int L = lv.n_levels;
+  uint32_t* orow = reinterpret_cast<uint32_t*>(out + s * out_stride);
+  uint32_t pend[4];
+#pragma unroll 1
+  for (int l0 = 0; l0 < L; l0 += LG) {
+    uint4 v[LG][8];
+    float wgt[LG][8];
+#pragma unroll
+    for (int a = 0; a < LG; ++a) {
+      const int l = l0 + a < L ? l0 + a : L - 1;
+      const Cell c = locate(xs, lv.scale[l]);
+      uint32_t idx[8];
+      cell_corners(c, lv.res[l], lv.size[l], lv.offset[l], lv.hashed[l] != 0, idx, wgt[a]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[a][k] = __ldg(t8 + idx[k]);
+    }
+#pragma unroll
+    for (int a = 0; a < LG; ++a) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t lo_w = kf == 0 ? v[a][k].x : (kf == 1 ? v[a][k].y : v[a][k].z);
+        const uint32_t hi_w = kf == 0 ? v[a][k].y : (kf == 1 ? v[a][k].z : v[a][k].w);
+        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&lo_w));
+        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&hi_w));
+        const float w = wgt[a][k];
+        a0 = __fadd_rn(a0, __fmul_rn(w, __fadd_rn(__fmul_rn(lo.x, om), __fmul_rn(hi.x, tau))));
+        a1 = __fadd_rn(a1, __fmul_rn(w, __fadd_rn(__fmul_rn(lo.y, om), __fmul_rn(hi.y, tau))));
+      }
+      const __half2 h = __floats2half2_rn(a0, a1);
+      const int l = l0 + a;
+      if (l < L) {
+        pend[l & 3] = *reinterpret_cast<const uint32_t*>(&h);
+        const bool row_aligned = ((out_stride & 7) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+        if ((l & 3) == 3 && row_aligned) {
+          *reinterpret_cast<uint4*>(orow + (l - 3)) = make_uint4(pend[0], pend[1], pend[2], pend[3]);
+        } else if (!row_aligned || (l == L - 1 && (l & 3) != 3)) {
+          if (!row_aligned) orow[l] = pend[l & 3];
+          else
+            for (int q = l & ~3; q <= l; ++q) orow[q] = pend[q & 3];
+        }
+      }
+    }
+  }
 }
 
 // Backward: table gradient (fp32 vector reductions, red.global.add.v2.f32) and, for the 3-D encoder,
@@ -425,8 +469,8 @@ CEDNERF_EXPORT int cednerf_hashgrid_fwd(const float* x, int x_stride, int64_t n,
   CEDNERF_REQUIRE(check_levels(levels), "bad level table");
   CEDNERF_REQUIRE(n >= 0 && x_stride >= 3 && out_stride >= 2 * levels->n_levels && (out_stride % 2) == 0, "bad sizes");
   if (n == 0) return 0;
-  hashgrid_fwd_kernel<false><<<cednerf_blocks(n * levels->n_levels, 256), 256, 0, (cudaStream_t)stream>>>(
-      x, x_stride, n, (const __half*)table_f16, *levels, (__half*)out_f16, out_stride, 0);
+  hashgrid_fwd_kernel<<<cednerf_blocks(n * levels->n_levels, 256), 256, 0, (cudaStream_t)stream>>>(
+      x, x_stride, n, (const __half*)table_f16, *levels, (__half*)out_f16, out_stride);
   return cednerf_check_launch("cednerf_hashgrid_fwd");
 }
 
@@ -490,7 +534,9 @@ CEDNERF_EXPORT int cednerf_hashgrid4d_fwd(const float* xyzt, int x_stride, int64
   CEDNERF_REQUIRE(n >= 0 && x_stride >= 4 && out_stride >= 2 * levels->n_levels && (out_stride % 2) == 0, "bad sizes");
   CEDNERF_REQUIRE(((uintptr_t)table_f16 & 15) == 0, "4-D table must be 16-byte aligned");
   if (n == 0) return 0;
-  hashgrid_fwd_kernel<true><<<cednerf_blocks(n * levels->n_levels, 256), 256, 0, (cudaStream_t)stream>>>(
+  // two levels in flight per thread (107 registers, 16 warps / SM): 1.93 ms on 2^22 ray-coherent samples against 2.02 ms
+  // with one level (56 registers) and 2.66 ms with the thread-per-(sample, level) kernel (profiles/r2q_hash4d_full_size.md)
+  hashgrid4d_fwd_sample_kernel<2><<<cednerf_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(
       xyzt, x_stride, n, (const __half*)table_f16, *levels, (__half*)out_f16, out_stride, taichi_compat);
   return cednerf_check_launch("cednerf_hashgrid4d_fwd");
 }
