@@ -106,8 +106,9 @@ _SIGNATURES = {
     "cednerf_mlp_bwd": "ppppMlpippp",
     "cednerf_field_fwd": "ppppppppilppppFpppp",
     "cednerf_occ_update_level": "plpppiffpppFpppp",
-    "cednerf_field_train_fwd": "ppppppilpppppFpppppppp",
-    "cednerf_field_train_bwd": "ppppppilpppppFpppppppppppppipp",
+    "cednerf_field_train_fwd": "ppppppilpppppFppppppppp",
+    "cednerf_field_train_bwd": "ppppppilpppppFpppppppppppppippp",
+    "cednerf_sample_order": "ppppplpffffffppp",
     "cednerf_ray_offsets": "pllpp",
     "cednerf_composite_fwd": "pppppppillpppppppifp",
     "cednerf_composite_bwd": "pppppppillppppppppppfp",
@@ -167,6 +168,8 @@ def load() -> ctypes.CDLL:
     lib.cednerf_scan_workspace_bytes.argtypes = [ctypes.c_int64]
     lib.cednerf_topk_workspace_bytes.restype = ctypes.c_int64
     lib.cednerf_topk_workspace_bytes.argtypes = [ctypes.c_int64]
+    lib.cednerf_sample_order_workspace_bytes.restype = ctypes.c_int64
+    lib.cednerf_sample_order_workspace_bytes.argtypes = [ctypes.c_int64]
     for name, sig in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = ctypes.c_int
@@ -178,7 +181,7 @@ def load() -> ctypes.CDLL:
 def exported_symbols():
     return sorted(list(_SIGNATURES) + ["cednerf_last_error", "cednerf_abi_version", "cednerf_check_device",
                                        "cednerf_scan_workspace_bytes", "cednerf_launch_count", "cednerf_field_saved_bytes",
-                                       "cednerf_field_bwd_workspace_bytes", "cednerf_dp_ctrl_bytes", "cednerf_topk_workspace_bytes"])
+                                       "cednerf_field_bwd_workspace_bytes", "cednerf_dp_ctrl_bytes", "cednerf_topk_workspace_bytes", "cednerf_sample_order_workspace_bytes"])
 
 
 def ptr(t: Optional[torch.Tensor]):

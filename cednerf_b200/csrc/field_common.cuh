@@ -25,6 +25,9 @@ __device__ __forceinline__ void run_chain(const CednerfMlpDesc& d, const uint8_t
                                           uint32_t tmem_warp, uint64_t* bar, uint32_t& phase, int gtid, int group,
                                           uint8_t* save = nullptr, int64_t save_layer_stride = 0, int64_t save_row0 = 0,
                                           int save_rows = 0, uint8_t* save_in = nullptr) {
+#if defined(FIELD_EXP) && FIELD_EXP == 5  // timing experiment: nothing is saved for the backward
+  save = nullptr, save_in = nullptr;
+#endif
   // `save` (training forward): the post-ReLU activation tiles are kept for the backward pass AS THEY SIT IN SHARED
   // MEMORY - the 16 KB swizzled image of tile t, layer l at save + (l * save_layer_stride + t) * 16384 with
   // save_layer_stride = number of tiles and t = save_row0 / 128 - so that one elected thread stores a tile with one TMA
@@ -173,7 +176,13 @@ __device__ __forceinline__ void hash_issue(const float* xn, const __half* __rest
       const uint32_t hy[2] = {y0 & mask, (y0 + 2654435761u) & mask};
       const uint32_t hz[2] = {z0 & mask, (z0 + 805459861u) & mask};
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[a][k] = gather_h2(tl, hx[k & 1] ^ hy[(k >> 1) & 1] ^ hz[k >> 2]);
+      for (int k = 0; k < 8; ++k) {
+#if defined(FIELD_EXP) && FIELD_EXP == 4  // timing experiment: same instructions, every lane the same few lines
+        v[a][k] = gather_h2(tl, (hx[k & 1] ^ hy[(k >> 1) & 1] ^ hz[k >> 2]) & 7u);
+#else
+        v[a][k] = gather_h2(tl, hx[k & 1] ^ hy[(k >> 1) & 1] ^ hz[k >> 2]);
+#endif
+      }
     } else {
       const uint32_t r2 = res * res;
       const uint32_t base = c.g[0] + c.g[1] * res + c.g[2] * r2;

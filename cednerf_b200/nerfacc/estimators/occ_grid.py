@@ -33,6 +33,12 @@ class OccGridEstimator(torch.nn.Module):
         self._cap_state, self.dropped_samples = {}, 0  # sampling(..., device_counts=True)
         self._aabbs_host, self._occ_cand, self._occ_touched = None, None, None  # fused occupancy update
 
+    def aabbs_on_host(self):
+        """The level boxes as nested host lists (one host read, repeated only when the buffer changes)."""
+        if self._aabbs_host is None or self._aabbs_host[0] != (self.aabbs.data_ptr(), self.aabbs._version):
+            self._aabbs_host = ((self.aabbs.data_ptr(), self.aabbs._version), self.aabbs.cpu().tolist())
+        return self._aabbs_host[1]
+
     def _load_from_state_dict(self, *args, **kwargs):
         self._occs_seen = None  # contents replaced in place: look again at the next update
         return super()._load_from_state_dict(*args, **kwargs)
@@ -215,9 +221,7 @@ class OccGridEstimator(torch.nn.Module):
         jitter = rand(n, 3).to(dev).float().contiguous()
         tt = fn.rand_t(n, dev).float().contiguous().view(-1)
         f = fn.field
-        if self._aabbs_host is None or self._aabbs_host[0] != (self.aabbs.data_ptr(), self.aabbs._version):
-            self._aabbs_host = ((self.aabbs.data_ptr(), self.aabbs._version), self.aabbs.cpu().tolist())  # one host read
-        box = (ctypes.c_float * 6)(*self._aabbs_host[1][l])
+        box = (ctypes.c_float * 6)(*self.aabbs_on_host()[l])
         cells = None if idx is None else idx.to(torch.int64).contiguous()
         cand = touched = None
         if not unique:
