@@ -168,6 +168,8 @@ def load() -> ctypes.CDLL:
     lib.cednerf_scan_workspace_bytes.argtypes = [ctypes.c_int64]
     lib.cednerf_topk_workspace_bytes.restype = ctypes.c_int64
     lib.cednerf_topk_workspace_bytes.argtypes = [ctypes.c_int64]
+    lib.cednerf_distortion_workspace_bytes.restype = ctypes.c_int64
+    lib.cednerf_distortion_workspace_bytes.argtypes = []
     lib.cednerf_sample_order_workspace_bytes.restype = ctypes.c_int64
     lib.cednerf_sample_order_workspace_bytes.argtypes = [ctypes.c_int64]
     for name, sig in _SIGNATURES.items():
@@ -181,7 +183,7 @@ def load() -> ctypes.CDLL:
 def exported_symbols():
     return sorted(list(_SIGNATURES) + ["cednerf_last_error", "cednerf_abi_version", "cednerf_check_device",
                                        "cednerf_scan_workspace_bytes", "cednerf_launch_count", "cednerf_field_saved_bytes",
-                                       "cednerf_field_bwd_workspace_bytes", "cednerf_dp_ctrl_bytes", "cednerf_topk_workspace_bytes", "cednerf_sample_order_workspace_bytes"])
+                                       "cednerf_field_bwd_workspace_bytes", "cednerf_dp_ctrl_bytes", "cednerf_topk_workspace_bytes", "cednerf_sample_order_workspace_bytes", "cednerf_distortion_workspace_bytes"])
 
 
 def ptr(t: Optional[torch.Tensor]):

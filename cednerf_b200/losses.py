@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import torch
 
+from . import _lib
 from ._lib import call, ptr, stream
 from .ops import _f32c, _sempty, counts_of
 
@@ -92,7 +93,7 @@ class DistortionFunction(torch.autograd.Function):
     def forward(ctx, weights, t_starts, t_ends, offsets, n_rays):
         w, t0, t1 = _f32c(weights).view(-1), _f32c(t_starts).view(-1), _f32c(t_ends).view(-1)
         dev = w.device
-        work = torch.empty(2, dtype=F64, device=dev)
+        work = torch.empty(int(_lib.load().cednerf_distortion_workspace_bytes()) // 8, dtype=F64, device=dev)
         loss = torch.empty(1, dtype=F32, device=dev)
         inv = torch.empty(1, dtype=F32, device=dev)
         call("cednerf_distortion_fwd", ptr(w), ptr(t0), ptr(t1), ptr(offsets), int(n_rays), ptr(work), ptr(loss), ptr(inv),

@@ -421,7 +421,9 @@ int cednerf_generate_rays(const int64_t* px, const int64_t* py, const int64_t* c
                           float* viewdirs, float* directions, void* stream);
 /* Distortion loss (cednerf/losses.py:4-11 = torch_efficient_distloss.flatten_eff_distloss on weights, interval
  * mid-points and lengths) of packed samples: sum_rays sum_i [d_i w_i^2 / 3 + 2 w_i (m_i W_i - M_i)] / (max ray + 1).
- * work: 16 bytes; loss, inv_rays: one float each (inv_rays feeds the backward).  Gradient w.r.t. the weights only. */
+ * work: cednerf_distortion_workspace_bytes() (per-block fp64 partials: no atomics, deterministic); loss, inv_rays: one float
+ * each (inv_rays feeds the backward).  Gradient w.r.t. the weights only. */
+int64_t cednerf_distortion_workspace_bytes(void);
 int cednerf_distortion_fwd(const float* weights, const float* t_starts, const float* t_ends, const int64_t* offsets,
                            int64_t n_rays, void* work, float* loss, float* inv_rays, void* stream);
 int cednerf_distortion_bwd(const float* weights, const float* t_starts, const float* t_ends, const int64_t* offsets,
