@@ -40,6 +40,7 @@ struct FieldFwdArgs {
   const float* jitter;    // [n,3] in [0,1): position inside the cell
   float cell_lo[3], cell_hi[3];
   int cell_res;           // R; 0 = not in cell mode
+  int cell_morton;        // cells == null: walk the level's cells in Morton order (power-of-two R up to 1024)
   int cell_update;        // 1: occs[c] = max(occs[c] * decay, occ) (every cell at most once); 2: atomic max into cand[c]
   float occ_scale, occ_decay;
   float* occs;            // the level's R^3 values (mode 1) or zero-initialised candidates (mode 2)
@@ -48,6 +49,30 @@ struct FieldFwdArgs {
 };
 
 #define FIELD_MAX_GROUPS 8
+
+// Cell mode without a cell list (the warm-up update: every cell of the level once).  Thread s does not take cell s - 32
+// consecutive cell ids are a 32-cell column along z, a quarter of the grid's width, so the lanes of a warp sat in
+// different cells of every hash level - but the s-th cell of a Morton walk (power-of-two resolutions): a warp is a compact
+// 4 x 4 x 2 block of cells and its gathers coalesce like those of neighbouring ray samples.  The random draws stay
+// attached to the CELL (jitter / timestamp number c belongs to cell c, as in nerfacc's element-wise update), so every
+// cell is evaluated at exactly the same point as before.
+__device__ __forceinline__ uint32_t compact3(uint32_t v) {  // every third bit of v, packed
+  v &= 0x09249249u;
+  v = (v | (v >> 2)) & 0x030C30C3u;
+  v = (v | (v >> 4)) & 0x0300F00Fu;
+  v = (v | (v >> 8)) & 0x030000FFu;
+  v = (v | (v >> 16)) & 0x000003FFu;
+  return v;
+}
+__device__ __forceinline__ int64_t cell_of(const FieldFwdArgs& a, int64_t s) {
+  if (a.cells) return a.cells[s];
+  if (!a.cell_morton) return s;
+  const uint32_t m = (uint32_t)s;
+  const int64_t R = a.cell_res;
+  return ((int64_t)compact3(m >> 2) * R + compact3(m >> 1)) * R + compact3(m);  // x from bits 2, 5, ..: z fastest in the id
+}
+// index of sample s's random draws (jitter, timestamp): by position in the cell list, by cell id in the Morton walk
+__device__ __forceinline__ int64_t draw_of(const FieldFwdArgs& a, int64_t s) { return a.cells ? s : cell_of(a, s); }
 
 // -DFIELD_PHASE_CLOCKS (the libcednerf_b200_dbg.so of `make debug`, profiles/tools/exp_field_fwd.py): the first thread of
 // every warp-group adds the cycles each phase of a tile took to g_phase_clocks; slot 7 counts tiles.
@@ -130,16 +155,16 @@ __global__ void __launch_bounds__(896, 1) field_fwd_kernel(FieldFwdArgs a) {
         tv = a.t[r * a.t_stride];
       } else if (a.cell_res) {
         // x = aabb_lo + ((coord + jitter) / R) * (aabb_hi - aabb_lo): nerfacc's element-wise chain, op by op
-        const int64_t c = a.cells ? a.cells[s] : s;
+        const int64_t c = cell_of(a, s);
         const int R = a.cell_res;
         const int cz = (int)(c % R), cy = (int)((c / R) % R), cx = (int)(c / ((int64_t)R * R));
         const int cc[3] = {cx, cy, cz};
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-          const float u = __fdiv_rn(__fadd_rn((float)cc[k], a.jitter[3 * s + k]), (float)R);
+          const float u = __fdiv_rn(__fadd_rn((float)cc[k], a.jitter[3 * draw_of(a, s) + k]), (float)R);
           x[k] = __fadd_rn(a.cell_lo[k], __fmul_rn(u, __fsub_rn(a.cell_hi[k], a.cell_lo[k])));
         }
-        tv = a.t[s * a.t_stride];
+        tv = a.t[draw_of(a, s) * a.t_stride];
       } else {
 #pragma unroll
         for (int k = 0; k < 3; ++k) x[k] = a.x[3 * s + k];
@@ -223,7 +248,7 @@ __global__ void __launch_bounds__(896, 1) field_fwd_kernel(FieldFwdArgs a) {
       const float sg = selector ? expf(rnd16(o2[0]) - 1.f) : 0.f;  // trunc_exp(raw - 1) * selector (model.py:414-417)
       if (a.sigma) a.sigma[s] = sg;
       if (a.cell_res) {  // occ = sigma * step;  occs = max(occs * decay, occ)   (nerfacc _update, train_real.py:324-336)
-        const int64_t c = a.cells ? a.cells[s] : s;
+        const int64_t c = cell_of(a, s);
         const float occ = __fmul_rn(sg, a.occ_scale);
         if (a.cell_update == 1) {
           a.occs[c] = fmaxf(__fmul_rn(a.occs[c], a.occ_decay), occ);
@@ -385,6 +410,8 @@ CEDNERF_EXPORT int cednerf_occ_update_level(const int64_t* cells, int64_t n, con
   a.img1 = (const uint8_t*)image_deform, a.img2 = (const uint8_t*)image_density;
   a.table = (const __half*)table_f16, a.d = *desc;
   a.cells = cells, a.jitter = jitter, a.cell_res = resolution, a.cell_update = cand ? 2 : 1;
+  a.cell_morton = !cells && (resolution & (resolution - 1)) == 0 && resolution <= 1024 &&
+                  n == (int64_t)resolution * resolution * resolution;
   // level_aabb is a HOST array of 6 floats (the estimator's aabbs[level])
   for (int k = 0; k < 3; ++k) a.cell_lo[k] = level_aabb[k], a.cell_hi[k] = level_aabb[3 + k];
   a.occ_scale = step_scale, a.occ_decay = ema_decay, a.occs = cand ? cand : occs_level, a.touched = touched;

@@ -132,7 +132,13 @@ __device__ unsigned long long g_train_phase_clocks[12];
 #endif
 
 // =============================================================================================== forward
-__global__ void __launch_bounds__(768, 1) field_train_fwd_kernel(TrainArgs a) {
+#ifndef TRAIN_FWD_GROUPS
+#define TRAIN_FWD_GROUPS 6   // 128-sample tiles in flight per SM (one warp-group each)
+#endif
+#ifndef TRAIN_FWD_LG
+#define TRAIN_FWD_LG 4       // hash levels (8 gathers each) in flight per thread
+#endif
+__global__ void __launch_bounds__(TRAIN_FWD_GROUPS * 128, 1) field_train_fwd_kernel(TrainArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const CednerfFieldDesc& d = a.d;
@@ -229,12 +235,18 @@ __global__ void __launch_bounds__(768, 1) field_train_fwd_kernel(TrainArgs a) {
       auto put_word = [&](int w, uint32_t v) {
         *reinterpret_cast<uint32_t*>(abuf + swz(gtid, w >> 2) + ((w & 3) << 2)) = v;
       };
-      if ((L & 3) == 0) {
+      if ((L % TRAIN_FWD_LG) == 0 && (L & 3) == 0) {
 #pragma unroll 1
-        for (int l0 = 0; l0 < L; l0 += 4) {
-          uint32_t f4w[4];
-          hash_levels<4>(xn, a.table, d.levels, 0, f4w, l0);
-          *reinterpret_cast<uint4*>(abuf + swz(gtid, l0 >> 2)) = make_uint4(f4w[0], f4w[1], f4w[2], f4w[3]);
+        for (int l0 = 0; l0 < L; l0 += TRAIN_FWD_LG) {
+          uint32_t fw[TRAIN_FWD_LG];
+          hash_levels<TRAIN_FWD_LG>(xn, a.table, d.levels, 0, fw, l0);
+          if constexpr (TRAIN_FWD_LG >= 4) {
+#pragma unroll
+            for (int q = 0; q < TRAIN_FWD_LG / 4; ++q)
+              *reinterpret_cast<uint4*>(abuf + swz(gtid, (l0 >> 2) + q)) = make_uint4(fw[4 * q], fw[4 * q + 1], fw[4 * q + 2], fw[4 * q + 3]);
+          } else {
+            *reinterpret_cast<uint2*>(abuf + swz(gtid, l0 >> 2) + ((l0 & 2) << 2)) = make_uint2(fw[0], fw[1]);
+          }
         }
       } else {
 #pragma unroll 1
@@ -894,7 +906,7 @@ CEDNERF_EXPORT int cednerf_field_train_fwd(const int64_t* ray_indices, const flo
                   "bad arguments");
   CEDNERF_REQUIRE(desc->f4.n_layers == 0 || image_predict, "feature predictor image missing");
   if (n == 0) return 0;
-  const int n_groups = 6;  // one CTA per SM: six 128-sample tiles in flight (24 warps) share one copy of the weight images
+  const int n_groups = TRAIN_FWD_GROUPS;  // one CTA per SM: six 128-sample tiles in flight (24 warps) share one copy of the weight images
   const int smem = desc->f1.image_bytes + desc->f2.image_bytes + desc->f3.image_bytes +
                    (desc->f4.n_layers > 0 ? desc->f4.image_bytes : 0) + n_groups * MLP_TILE_BYTES + 2048;
   CEDNERF_REQUIRE(smem <= 224 * 1024, "networks too large for the fused kernel");
