@@ -90,7 +90,11 @@ __device__ unsigned long long g_phase_clocks[8];
 #define PHASE_MARK(i) do {} while (0)
 #endif
 
-__global__ void __launch_bounds__(896, 1) field_fwd_kernel(FieldFwdArgs a) {
+// GROUPS = 128-sample tiles in flight per SM (one warp-group each); the register budget follows (7: 72, 6: 80 per thread).
+// Measured on the 9.06 M-sample pre-pass (density only) 4 / 5 / 6 / 7 groups: 1.67 / 1.49 / 1.39 / 1.46 ms; on the rounds of
+// a 1352 x 1014 frame (density + colour) 9.8 / 8.8 / 8.2 / 7.8 ms: six for the density-only launches, seven with colour.
+template <int GROUPS>
+__global__ void __launch_bounds__(GROUPS * 128, 1) field_fwd_kernel(FieldFwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const CednerfFieldDesc& d = a.d;
@@ -352,13 +356,15 @@ CEDNERF_EXPORT int cednerf_field_fwd(const int64_t* ray_indices, const float* t_
   CEDNERF_REQUIRE((ray_indices && t_starts && t_ends && rays_o && rays_d) || (!ray_indices && x), "need packed samples or points");
   CEDNERF_REQUIRE(!rgb || ray_indices || dirs, "colour needs directions");
   if (n == 0) return 0;
-  // one CTA per SM with seven 128-sample tiles in flight (28 warps at 72 registers) sharing one copy of the weight
-  // images; measured 6 / 7 / 8 tiles: 1.83 / 1.78 / 1.85 ms on the 9.1 M-sample pre-pass (two CTAs of three: 1.91 ms)
-  const int n_groups = 7;
+  // one CTA per SM with six (density only) or seven (with colour) 128-sample tiles in flight sharing one copy of the
+  // weight images (see the kernel's header for the measurements)
+  const int n_groups = rgb ? 7 : 6;
   const int smem = desc->f1.image_bytes + desc->f2.image_bytes + (rgb ? desc->f3.image_bytes : 0) +
                    n_groups * MLP_TILE_BYTES + 2048;
-  static CednerfOncePerDevice configured;
-  if (int e = cednerf_opt_in_smem(field_fwd_kernel, 224 * 1024, configured, "cednerf_field_fwd")) return e;
+  static CednerfOncePerDevice configured7, configured6;
+  if (int e = rgb ? cednerf_opt_in_smem(field_fwd_kernel<7>, 224 * 1024, configured7, "cednerf_field_fwd")
+                  : cednerf_opt_in_smem(field_fwd_kernel<6>, 224 * 1024, configured6, "cednerf_field_fwd"))
+    return e;
   CEDNERF_REQUIRE(smem <= 224 * 1024, "networks too large for the fused kernel");
   FieldFwdArgs a{};
   a.ridx = ray_indices, a.t0 = t_starts, a.t1 = t_ends, a.rays_o = rays_o, a.rays_d = rays_d, a.x = x, a.dirs = dirs;
@@ -368,7 +374,9 @@ CEDNERF_EXPORT int cednerf_field_fwd(const int64_t* ray_indices, const float* t_
   const int64_t tiles = (n + MLP_TILE - 1) / MLP_TILE;
   const int64_t ctas = tiles;  // tiles go round-robin over CTAs first, then over the groups of a CTA
   const int64_t max_ctas = (int64_t)cednerf_num_sms();
-  field_fwd_kernel<<<(unsigned)(ctas < max_ctas ? ctas : max_ctas), n_groups * MLP_TILE, smem, (cudaStream_t)stream>>>(a);
+  const unsigned grid = (unsigned)(ctas < max_ctas ? ctas : max_ctas);
+  if (rgb) field_fwd_kernel<7><<<grid, 7 * MLP_TILE, smem, (cudaStream_t)stream>>>(a);
+  else field_fwd_kernel<6><<<grid, 6 * MLP_TILE, smem, (cudaStream_t)stream>>>(a);
   return cednerf_check_launch("cednerf_field_fwd");
 }
 
@@ -400,10 +408,10 @@ CEDNERF_EXPORT int cednerf_occ_update_level(const int64_t* cells, int64_t n, con
   CEDNERF_REQUIRE((cand == nullptr) == (touched == nullptr), "cand and touched go together");
   CEDNERF_REQUIRE(cells || n <= (int64_t)resolution * resolution * resolution, "more points than cells");
   if (n == 0) return 0;
-  const int n_groups = 7;
+  const int n_groups = 6;
   const int smem = desc->f1.image_bytes + desc->f2.image_bytes + n_groups * MLP_TILE_BYTES + 2048;
   static CednerfOncePerDevice configured;
-  if (int e = cednerf_opt_in_smem(field_fwd_kernel, 224 * 1024, configured, "cednerf_occ_update_level")) return e;
+  if (int e = cednerf_opt_in_smem(field_fwd_kernel<6>, 224 * 1024, configured, "cednerf_occ_update_level")) return e;
   CEDNERF_REQUIRE(smem <= 224 * 1024, "networks too large for the fused kernel");
   FieldFwdArgs a{};
   a.t = timestamps, a.t_stride = 1, a.n = n;
@@ -418,7 +426,7 @@ CEDNERF_EXPORT int cednerf_occ_update_level(const int64_t* cells, int64_t n, con
   const int64_t tiles = (n + MLP_TILE - 1) / MLP_TILE;
   const int64_t max_ctas = (int64_t)cednerf_num_sms();
   cudaStream_t st = (cudaStream_t)stream;
-  field_fwd_kernel<<<(unsigned)(tiles < max_ctas ? tiles : max_ctas), n_groups * MLP_TILE, smem, st>>>(a);
+  field_fwd_kernel<6><<<(unsigned)(tiles < max_ctas ? tiles : max_ctas), n_groups * MLP_TILE, smem, st>>>(a);
   int launches = 1;
   if (cand) {
     const int64_t n_cells = (int64_t)resolution * resolution * resolution;

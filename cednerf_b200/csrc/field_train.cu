@@ -133,7 +133,8 @@ __device__ unsigned long long g_train_phase_clocks[12];
 
 // =============================================================================================== forward
 #ifndef TRAIN_FWD_GROUPS
-#define TRAIN_FWD_GROUPS 6   // 128-sample tiles in flight per SM (one warp-group each)
+#define TRAIN_FWD_GROUPS 5   // 128-sample tiles in flight per SM (one warp-group each); measured 4 / 5 / 6 / 7: 0.60 / 0.57 /
+                             // 0.63 / 0.64 ms on the 1.01 M visible samples of the DyNeRF-shaped step (96 registers per thread at 5)
 #endif
 #ifndef TRAIN_FWD_LG
 #define TRAIN_FWD_LG 4       // hash levels (8 gathers each) in flight per thread
@@ -906,7 +907,7 @@ CEDNERF_EXPORT int cednerf_field_train_fwd(const int64_t* ray_indices, const flo
                   "bad arguments");
   CEDNERF_REQUIRE(desc->f4.n_layers == 0 || image_predict, "feature predictor image missing");
   if (n == 0) return 0;
-  const int n_groups = TRAIN_FWD_GROUPS;  // one CTA per SM: six 128-sample tiles in flight (24 warps) share one copy of the weight images
+  const int n_groups = TRAIN_FWD_GROUPS;  // one CTA per SM: the tiles in flight (one warp-group each) share one copy of the weight images
   const int smem = desc->f1.image_bytes + desc->f2.image_bytes + desc->f3.image_bytes +
                    (desc->f4.n_layers > 0 ? desc->f4.image_bytes : 0) + n_groups * MLP_TILE_BYTES + 2048;
   CEDNERF_REQUIRE(smem <= 224 * 1024, "networks too large for the fused kernel");

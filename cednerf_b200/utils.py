@@ -246,7 +246,9 @@ def _render_rounds_gen(max_samples, field, rays, bits, aabbs, res, near, far_pla
                 stop = True
                 break
             bound = min(bound, n_alive)                    # valid for every later round: the list only shrinks
-            k_hint = max(k_hint, min(64, n // max(n_alive, 1)))
+            # (k_hint stays at min_samples: it picks the lane-group width of the compositing kernel, i.e. the order in
+            # which a ray's samples are summed - following the host's LAGGED view of k made the last bits of a frame
+            # depend on timing; late rounds with large k have few rays left, so the narrow groups cost nothing)
         if stop:
             break
         yield
