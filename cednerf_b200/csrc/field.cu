@@ -93,6 +93,12 @@ __device__ unsigned long long g_phase_clocks[8];
 // GROUPS = 128-sample tiles in flight per SM (one warp-group each); the register budget follows (7: 72, 6: 80 per thread).
 // Measured on the 9.06 M-sample pre-pass (density only) 4 / 5 / 6 / 7 groups: 1.67 / 1.49 / 1.39 / 1.46 ms; on the rounds of
 // a 1352 x 1014 frame (density + colour) 9.8 / 8.8 / 8.2 / 7.8 ms: six for the density-only launches, seven with colour.
+#ifndef FIELD_FWD_LG
+#define FIELD_FWD_LG 2   // hash levels (8 gathers each) in flight per thread
+#endif
+#ifndef FIELD_FWD_SIGMA_GROUPS
+#define FIELD_FWD_SIGMA_GROUPS 6
+#endif
 template <int GROUPS>
 __global__ void __launch_bounds__(GROUPS * 128, 1) field_fwd_kernel(FieldFwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -212,7 +218,14 @@ __global__ void __launch_bounds__(GROUPS * 128, 1) field_fwd_kernel(FieldFwdArgs
       const int k2 = d.f2.dim_in[0];
       // runtime loops over level groups (not unrolled: the fully unrolled 16-level body was 340 KB of SASS and the
       // kernel spent 18 % of its stall samples waiting for instructions)
-      if ((L & 1) == 0) {
+      if (FIELD_FWD_LG == 4 && (L & 3) == 0) {
+#pragma unroll 1
+        for (int l0 = 0; l0 < L; l0 += 4) {  // 32 gathers in flight per thread; four levels = one 16-byte chunk of the row
+          uint32_t f4w[4];
+          hash_levels<4>(xn, a.table, d.levels, 0, f4w, l0);
+          *reinterpret_cast<uint4*>(abuf0 + swz(gtid, l0 >> 2)) = make_uint4(f4w[0], f4w[1], f4w[2], f4w[3]);
+        }
+      } else if ((L & 1) == 0) {
 #pragma unroll 1
         for (int l0 = 0; l0 < L; l0 += 2) {  // 16 gathers in flight per thread; two levels = 8 bytes of the row
           uint32_t f2w[2];
@@ -358,12 +371,12 @@ CEDNERF_EXPORT int cednerf_field_fwd(const int64_t* ray_indices, const float* t_
   if (n == 0) return 0;
   // one CTA per SM with six (density only) or seven (with colour) 128-sample tiles in flight sharing one copy of the
   // weight images (see the kernel's header for the measurements)
-  const int n_groups = rgb ? 7 : 6;
+  const int n_groups = rgb ? 7 : FIELD_FWD_SIGMA_GROUPS;
   const int smem = desc->f1.image_bytes + desc->f2.image_bytes + (rgb ? desc->f3.image_bytes : 0) +
                    n_groups * MLP_TILE_BYTES + 2048;
   static CednerfOncePerDevice configured7, configured6;
   if (int e = rgb ? cednerf_opt_in_smem(field_fwd_kernel<7>, 224 * 1024, configured7, "cednerf_field_fwd")
-                  : cednerf_opt_in_smem(field_fwd_kernel<6>, 224 * 1024, configured6, "cednerf_field_fwd"))
+                  : cednerf_opt_in_smem(field_fwd_kernel<FIELD_FWD_SIGMA_GROUPS>, 224 * 1024, configured6, "cednerf_field_fwd"))
     return e;
   CEDNERF_REQUIRE(smem <= 224 * 1024, "networks too large for the fused kernel");
   FieldFwdArgs a{};
@@ -376,7 +389,7 @@ CEDNERF_EXPORT int cednerf_field_fwd(const int64_t* ray_indices, const float* t_
   const int64_t max_ctas = (int64_t)cednerf_num_sms();
   const unsigned grid = (unsigned)(ctas < max_ctas ? ctas : max_ctas);
   if (rgb) field_fwd_kernel<7><<<grid, 7 * MLP_TILE, smem, (cudaStream_t)stream>>>(a);
-  else field_fwd_kernel<6><<<grid, 6 * MLP_TILE, smem, (cudaStream_t)stream>>>(a);
+  else field_fwd_kernel<FIELD_FWD_SIGMA_GROUPS><<<grid, FIELD_FWD_SIGMA_GROUPS * MLP_TILE, smem, (cudaStream_t)stream>>>(a);
   return cednerf_check_launch("cednerf_field_fwd");
 }
 
