@@ -275,12 +275,15 @@ __global__ void __launch_bounds__(128, MARCH_MIN_BLOCKS) march_kernel(MarchArgs 
     bool pend = false;
     int eb0 = -1, eb1 = -1, eb2 = -1;  // the 4^3 block known to be empty (-1: none)
     auto catch_up = [&](float t_target) { advance_to(t_last, t_target, cone, step_size); };
+    // the cell's bit index, kept incrementally (one add per DDA step; 32 bits: the entry point checks L res^3 < 2^31)
+    uint32_t cell = ((uint32_t)cur[0] * (uint32_t)res + (uint32_t)cur[1]) * (uint32_t)res + (uint32_t)cur[2] +
+                    (uint32_t)level * (uint32_t)cells_per_level;
+    const int dcell[3] = {stepi[0] * res * res, stepi[1] * res, stepi[2]};
     while (limit <= 0 || n_sm < limit) {
       const float t_trav = fminf(fminf(tdist[0], fminf(tdist[1], tdist[2])), this_tmax);
       bool occupied = false;
       if (!(a.coarse && (cur[0] >> 2) == eb0 && (cur[1] >> 2) == eb1 && (cur[2] >> 2) == eb2)) {
-        const int64_t cell = (int64_t)cur[0] * res * res + (int64_t)cur[1] * res + cur[2] + level * cells_per_level;
-        occupied = (__ldg(a.occ_bits + (cell >> 5)) >> (cell & 31)) & 1u;
+        occupied = (__ldg(a.occ_bits + (cell >> 5)) >> (cell & 31u)) & 1u;
         if (!occupied && a.coarse) {
           const int cres = res >> 2;
           const int64_t cb = ((int64_t)(cur[0] >> 2) * cres + (cur[1] >> 2)) * cres + (cur[2] >> 2) +
@@ -360,14 +363,17 @@ __global__ void __launch_bounds__(128, MARCH_MIN_BLOCKS) march_kernel(MarchArgs 
       if (ax == 0) {
         cur[0] += stepi[0];
         tdist[0] += delta[0];
+        cell += (uint32_t)dcell[0];
         done = cur[0] == overflow[0];
       } else if (ax == 1) {
         cur[1] += stepi[1];
         tdist[1] += delta[1];
+        cell += (uint32_t)dcell[1];
         done = cur[1] == overflow[1];
       } else {
         cur[2] += stepi[2];
         tdist[2] += delta[2];
+        cell += (uint32_t)dcell[2];
         done = cur[2] == overflow[2];
       }
       if (done) break;
@@ -872,6 +878,7 @@ CEDNERF_EXPORT int cednerf_march(int fill, const float* rays_o, const float* ray
                                  const uint32_t* occ_coarse, void* stream) {
   CEDNERF_REQUIRE(!run_t || (!fill && run_n && n_runs && run_cap > 0 && step_size > 0.0f),
                   "run recording: count pass, positive step size");
+  CEDNERF_REQUIRE((int64_t)n_levels * resolution * resolution * resolution < (1ll << 31), "occupancy grid too large");
   CEDNERF_REQUIRE(n_rays >= 0 && n_levels >= 1 && n_levels <= MARCH_MAX_LEVELS && resolution >= 1,
                   "bad sizes (levels <= 8)");
   CEDNERF_REQUIRE((t_sorted == nullptr) == (t_indices == nullptr) && (t_sorted == nullptr) == (hits == nullptr),
@@ -1001,6 +1008,7 @@ CEDNERF_EXPORT int cednerf_march_round(int fill, const float* rays_o, const floa
                                        const int64_t* offsets, float* t_starts, float* t_ends, int64_t* ray_indices,
                                        int32_t* n_samples, float* run_t, int32_t* run_n, int32_t* n_runs, int run_cap,
                                        const uint32_t* occ_coarse, void* stream) {
+  CEDNERF_REQUIRE((int64_t)n_levels * resolution * resolution * resolution < (1ll << 31), "occupancy grid too large");
   CEDNERF_REQUIRE(n_bound >= 0 && n_levels >= 1 && n_levels <= MARCH_MAX_LEVELS && resolution >= 1 && alive && state &&
                       near_term && t_sorted && t_indices && hits,
                   "bad arguments");
