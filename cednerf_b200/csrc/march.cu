@@ -97,10 +97,22 @@ __device__ __forceinline__ void advance_to(float& t_last, float t_target, float 
     if (t_last + dt * 0.5f >= t_target) return;
     t_last += dt;
   }
+  // four steps per trip: the step chain (one add and one multiply per step) runs ahead of the four stop tests, which hang
+  // off it side by side instead of sitting on it; the first test that holds names the value to keep (same operations,
+  // same roundings - the steps past the stop are computed and dropped)
+  float t = t_last;
   for (;;) {
-    const float dt = t_last * cone;
-    if (t_last + dt * 0.5f >= t_target) return;
-    t_last += dt;
+    const float d0 = t * cone;
+    const float t1 = t + d0, d1 = t1 * cone;
+    const float t2 = t1 + d1, d2 = t2 * cone;
+    const float t3 = t2 + d2, d3 = t3 * cone;
+    const bool e0 = t + d0 * 0.5f >= t_target, e1 = t1 + d1 * 0.5f >= t_target;
+    const bool e2 = t2 + d2 * 0.5f >= t_target, e3 = t3 + d3 * 0.5f >= t_target;
+    if (e0 | e1 | e2 | e3) {
+      t_last = e0 ? t : (e1 ? t1 : (e2 ? t2 : t3));
+      return;
+    }
+    t = t3 + d3;
   }
 }
 
