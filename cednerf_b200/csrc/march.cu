@@ -184,8 +184,8 @@ __global__ void sort_boundaries_kernel(const float* __restrict__ t_mins, const f
 }
 
 #ifndef MARCH_MIN_BLOCKS
-#define MARCH_MIN_BLOCKS 8
-#endif
+#define MARCH_MIN_BLOCKS 6   // resident CTAs of 128 rays per SM -> 78 registers; measured 5 / 6 / 7 / 8: 0.592 / 0.566 / 0.570 /
+#endif                       // 0.598 ms on the count pass of the DyNeRF-shaped batch (rounds of a frame: 7.09 / 7.20 / 7.23 / 7.37)
 template <bool FILL>
 __global__ void __launch_bounds__(128, MARCH_MIN_BLOCKS) march_kernel(MarchArgs a) {
   const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
