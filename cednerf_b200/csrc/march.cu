@@ -186,7 +186,9 @@ __global__ void sort_boundaries_kernel(const float* __restrict__ t_mins, const f
 #ifndef MARCH_MIN_BLOCKS
 #define MARCH_MIN_BLOCKS 6   // resident CTAs of 128 rays per SM -> 78 registers; measured 5 / 6 / 7 / 8: 0.592 / 0.566 / 0.570 /
 #endif                       // 0.598 ms on the count pass of the DyNeRF-shaped batch (rounds of a frame: 7.09 / 7.20 / 7.23 / 7.37)
-template <bool FILL>
+// COARSE: the 4^3-block bits are given (a.coarse != null).  A template parameter, not a run-time test: the block
+// coordinates and their three compares sat in the per-cell path of every launch, also of those without the bits.
+template <bool FILL, bool COARSE = false>
 __global__ void __launch_bounds__(128, MARCH_MIN_BLOCKS) march_kernel(MarchArgs a) {
   const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= a.n_rays) return;
@@ -294,9 +296,9 @@ __global__ void __launch_bounds__(128, MARCH_MIN_BLOCKS) march_kernel(MarchArgs 
     while (limit <= 0 || n_sm < limit) {
       const float t_trav = fminf(fminf(tdist[0], fminf(tdist[1], tdist[2])), this_tmax);
       bool occupied = false;
-      if (!(a.coarse && (cur[0] >> 2) == eb0 && (cur[1] >> 2) == eb1 && (cur[2] >> 2) == eb2)) {
+      if (!(COARSE && (cur[0] >> 2) == eb0 && (cur[1] >> 2) == eb1 && (cur[2] >> 2) == eb2)) {
         occupied = (__ldg(a.occ_bits + (cell >> 5)) >> (cell & 31u)) & 1u;
-        if (!occupied && a.coarse) {
+        if (COARSE && !occupied) {
           const int cres = res >> 2;
           const int64_t cb = ((int64_t)(cur[0] >> 2) * cres + (cur[1] >> 2)) * cres + (cur[2] >> 2) +
                              (int64_t)level * cres * cres * cres;
@@ -905,8 +907,13 @@ CEDNERF_EXPORT int cednerf_march(int fill, const float* rays_o, const float* ray
               n_intervals, n_samples, termination, run_t, run_n, n_runs, run_cap, ray_order, nullptr, nullptr, 0,
               (resolution % 4 == 0) ? occ_coarse : nullptr};
   const unsigned grid = cednerf_blocks(n_rays, 128);
-  if (fill) march_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
-  else march_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  if (a.coarse) {
+    if (fill) march_kernel<true, true><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+    else march_kernel<false, true><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  } else {
+    if (fill) march_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+    else march_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  }
   return cednerf_check_launch("cednerf_march");
 }
 
@@ -1039,8 +1046,13 @@ CEDNERF_EXPORT int cednerf_march_round(int fill, const float* rays_o, const floa
   a.order = alive, a.n_active_dev = state, a.limit_dev = state + 1, a.by_slot = 1;
   a.coarse = (resolution % 4 == 0) ? occ_coarse : nullptr;
   const unsigned grid = cednerf_blocks(n_bound, 128);
-  if (fill) march_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
-  else march_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  if (a.coarse) {
+    if (fill) march_kernel<true, true><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+    else march_kernel<false, true><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  } else {
+    if (fill) march_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+    else march_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  }
   return cednerf_check_launch("cednerf_march_round");
 }
 
