@@ -371,25 +371,21 @@ __global__ void __launch_bounds__(128, MARCH_MIN_BLOCKS) march_kernel(MarchArgs 
           if (t_next >= t_trav) break;
         }
       }
-      const int ax = (tdist[0] < tdist[1] && tdist[0] < tdist[2]) ? 0 : (tdist[1] < tdist[2] ? 1 : 2);
-      // register-friendly equivalent of cur[ax] += step[ax]; tdist[ax] += delta[ax]
-      bool done;
-      if (ax == 0) {
-        cur[0] += stepi[0];
-        tdist[0] += delta[0];
-        cell += (uint32_t)dcell[0];
-        done = cur[0] == overflow[0];
-      } else if (ax == 1) {
-        cur[1] += stepi[1];
-        tdist[1] += delta[1];
-        cell += (uint32_t)dcell[1];
-        done = cur[1] == overflow[1];
-      } else {
-        cur[2] += stepi[2];
-        tdist[2] += delta[2];
-        cell += (uint32_t)dcell[2];
-        done = cur[2] == overflow[2];
-      }
+      // advance along the axis whose plane comes first - written with selects, not a three-way branch: the lanes of a
+      // warp pick different axes at every step, and a branch runs the three arms one after the other.  (The add for the
+      // two other axes is computed and dropped: same values for the chosen one.)
+      const bool s0 = tdist[0] < tdist[1] && tdist[0] < tdist[2];
+      const bool s1 = !s0 && tdist[1] < tdist[2];
+      const bool s2 = !s0 && !s1;
+      const float n0 = tdist[0] + delta[0], n1 = tdist[1] + delta[1], n2 = tdist[2] + delta[2];
+      tdist[0] = s0 ? n0 : tdist[0];
+      tdist[1] = s1 ? n1 : tdist[1];
+      tdist[2] = s2 ? n2 : tdist[2];
+      cur[0] += s0 ? stepi[0] : 0;
+      cur[1] += s1 ? stepi[1] : 0;
+      cur[2] += s2 ? stepi[2] : 0;
+      cell += (uint32_t)(s0 ? dcell[0] : (s1 ? dcell[1] : dcell[2]));
+      const bool done = s0 ? (cur[0] == overflow[0]) : (s1 ? (cur[1] == overflow[1]) : (cur[2] == overflow[2]));
       if (done) break;
     }
     if (pend) catch_up(t_pend);
