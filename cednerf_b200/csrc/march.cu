@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(128, MARCH_MIN_BLOCKS) march_kernel(MarchArgs 
       cur[1] += s1 ? stepi[1] : 0;
       cur[2] += s2 ? stepi[2] : 0;
       cell += (uint32_t)(s0 ? dcell[0] : (s1 ? dcell[1] : dcell[2]));
-      const bool done = s0 ? (cur[0] == overflow[0]) : (s1 ? (cur[1] == overflow[1]) : (cur[2] == overflow[2]));
+      const bool done = (s0 & (cur[0] == overflow[0])) | (s1 & (cur[1] == overflow[1])) | (s2 & (cur[2] == overflow[2]));
       if (done) break;
     }
     if (pend) catch_up(t_pend);
