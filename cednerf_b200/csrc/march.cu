@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(128, MARCH_MIN_BLOCKS) march_kernel(MarchArgs 
   const int64_t sm_base = FILL && a.sm_starts ? a.sm_starts[oi] : 0;
   int n_iv = 0, n_sm = 0;
   float t_last = near;
-  bool continuous = false;
+  int continuous = 0;  // (int, not bool: the compiler packs bools into byte lanes and shuffles them with PRMT in the cell loop)
   int runs = 0, run_len = 0;  // run bookkeeping (count pass with run recording)
   const int limit = a.limit_dev ? *a.limit_dev : a.limit;
   const float step_size = a.step_size, cone = a.cone_angle;
@@ -286,13 +286,14 @@ __global__ void __launch_bounds__(128, MARCH_MIN_BLOCKS) march_kernel(MarchArgs 
     // t_last + dt/2 >= plane, and the planes increase along the ray, so catching up once to the last plane walks the same
     // recurrence to the same stop.  With the coarse bits, cells of a block known to be empty are not even looked up.
     float t_pend = 0.0f;
-    bool pend = false;
+    int pend = 0;
     int eb0 = -1, eb1 = -1, eb2 = -1;  // the 4^3 block known to be empty (-1: none)
     auto catch_up = [&](float t_target) { advance_to(t_last, t_target, cone, step_size); };
     // the cell's bit index, kept incrementally (one add per DDA step; 32 bits: the entry point checks L res^3 < 2^31)
     uint32_t cell = ((uint32_t)cur[0] * (uint32_t)res + (uint32_t)cur[1]) * (uint32_t)res + (uint32_t)cur[2] +
                     (uint32_t)level * (uint32_t)cells_per_level;
-    const int dcell[3] = {stepi[0] * res * res, stepi[1] * res, stepi[2]};
+    int dcell[3] = {stepi[0] * res * res, stepi[1] * res, stepi[2]};
+    asm volatile("" : "+r"(dcell[0]), "+r"(dcell[1]));  // keep the products in registers (ptxas re-formed them per step)
     while (limit <= 0 || n_sm < limit) {
       const float t_trav = fminf(fminf(tdist[0], fminf(tdist[1], tdist[2])), this_tmax);
       bool occupied = false;
@@ -310,12 +311,12 @@ __global__ void __launch_bounds__(128, MARCH_MIN_BLOCKS) march_kernel(MarchArgs 
       }
       if (!occupied) {
         t_pend = t_trav;
-        pend = true;
-        continuous = false;
+        pend = 1;
+        continuous = 0;
       } else {
         if (pend) {
           catch_up(t_pend);
-          pend = false;
+          pend = 0;
         }
         while (limit <= 0 || n_sm < limit) {
           float t_next;
@@ -366,7 +367,7 @@ __global__ void __launch_bounds__(128, MARCH_MIN_BLOCKS) march_kernel(MarchArgs 
           }
           n_iv += continuous ? 1 : 2;
           n_sm += 1;
-          continuous = true;
+          continuous = 1;
           t_last = t_next;
           if (t_next >= t_trav) break;
         }
