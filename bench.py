@@ -335,10 +335,17 @@ def peaks():
         return 6650.0, "fallback"
 
 
+# entry points that are several kernels behind one call (their time is a sum, not a kernel's duration)
+MULTI_KERNEL_ENTRIES = {"cednerf_field_train_bwd"}
+
+
 def roofline_of(agg, n_iter, total_ms):
     """Dominant kernel (by time, among those with algorithmic bytes) against the HBM copy peak; plus the whole step."""
     hbm_peak, src = peaks()
-    top = max((n for n in agg if agg[n]["has_bytes"]), key=lambda n: agg[n]["ms"])
+    # the dominant KERNEL: entry points that are one launch (cednerf_field_train_bwd is seven kernels behind one call, its
+    # sum is not a kernel's duration)
+    single = [n for n in agg if agg[n]["has_bytes"] and n not in MULTI_KERNEL_ENTRIES]
+    top = max(single or [n for n in agg if agg[n]["has_bytes"]], key=lambda n: agg[n]["ms"])
     d = agg[top]
     achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9
     traffic = None  # dram__bytes_read + dram__bytes_write per launch of that kernel, from the committed ncu capture
