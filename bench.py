@@ -622,7 +622,9 @@ def render_leg(D, cb, workload, cfg, args, poses, times, opengl, bkgd, profile: 
             copies.pop(0).synchronize()   # every frame has reached the host before the clock stops
         return n_samples_box[0]
 
-    render_all(list(range(min(2, len(frames)))))
+    # warm-up: one frame more than there are frames in flight, so that every stream of render_images_test has run a frame
+    # (each stream has its own allocator pool; a cold pool means cudaMallocs of ~1 GB of per-frame buffers inside the clock)
+    render_all(list(range(min(max(3, args.render_streams + 1), len(frames)))))
     D.barrier()
     r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = _lib.launch_count()

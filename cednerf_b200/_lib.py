@@ -75,6 +75,19 @@ class DpSmall(ctypes.Structure):
                 ("weight_decay", ctypes.c_float * 8), ("grad_div", ctypes.c_float), ("chunk_begin", ctypes.c_int64 * 9)]
 
 
+class RenderRound(ctypes.Structure):
+    _P, _I, _L, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+    _fields_ = [("rays_o", _P), ("rays_d", _P), ("n_rays", _L), ("occ_bits", _P), ("aabbs", _P), ("n_levels", _I),
+                ("resolution", _I), ("near_term", _P), ("far_const", _F), ("step_size", _F), ("cone_angle", _F),
+                ("early_stop_eps", _F), ("t_sorted", _P), ("t_indices", _P), ("hits", _P), ("state", _P), ("total", _P),
+                ("n_samples", _P), ("run_t", _P), ("run_n", _P), ("n_runs", _P), ("occ_coarse", _P), ("capacity", _L),
+                ("offsets", _P), ("totals", _P), ("scan_workspace", _P), ("t_starts", _P), ("t_ends", _P),
+                ("ray_indices", _P), ("overflow", _P), ("timestamps", _P), ("image_deform", _P), ("image_density", _P),
+                ("image_colour", _P), ("table_f16", _P), ("desc", ctypes.POINTER(FieldDesc)), ("sigma", _P), ("rgbs", _P),
+                ("colors", _P), ("opacity", _P), ("depth", _P), ("alive_flags", _P), ("positions", _P),
+                ("position_totals", _P), ("run_cap", _I), ("k_hint", _I), ("max_samples", _I), ("min_samples", _I)]
+
+
 # p = pointer, i = int, l = int64, f = float, A = AdamTensors*, G = GridLevels*, M = MlpDesc*, F = FieldDesc*
 _SIGNATURES = {
     "cednerf_ray_aabb_intersect": "pplpifffpppp",
@@ -121,6 +134,7 @@ _SIGNATURES = {
     "cednerf_march_fill_runs_round": "lpppppiffppppppp",
     "cednerf_render_round_composite": "pppppppplifppppp",
     "cednerf_render_round_compact":"ppplppliippp",
+    "cednerf_render_round": "Rlppp",
     "cednerf_generate_rays": "ppppiffffiilpppp",
     "cednerf_distortion_fwd": "pppplpppp",
     "cednerf_distortion_bwd": "pppplpppp",
@@ -144,7 +158,7 @@ _SIGNATURES = {
 _CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_int64, "f": ctypes.c_float,
        "G": ctypes.POINTER(GridLevels), "M": ctypes.POINTER(MlpDesc), "F": ctypes.POINTER(FieldDesc),
        "A": ctypes.POINTER(AdamTensors), "P": ctypes.POINTER(DpPeers), "D": ctypes.POINTER(DpAdam), "S": ctypes.POINTER(DpSmall),
-       "u": ctypes.c_uint32}
+       "u": ctypes.c_uint32, "R": ctypes.POINTER(RenderRound)}
 
 _lib = None
 
@@ -168,6 +182,10 @@ def load() -> ctypes.CDLL:
     lib.cednerf_scan_workspace_bytes.argtypes = [ctypes.c_int64]
     lib.cednerf_topk_workspace_bytes.restype = ctypes.c_int64
     lib.cednerf_topk_workspace_bytes.argtypes = [ctypes.c_int64]
+    lib.cednerf_render_round_bytes.restype = ctypes.c_int64
+    lib.cednerf_render_round_bytes.argtypes = []
+    if lib.cednerf_render_round_bytes() != ctypes.sizeof(RenderRound):
+        raise ImportError("cednerf_b200: CednerfRenderRound layout mismatch between the library and _lib.RenderRound")
     lib.cednerf_distortion_workspace_bytes.restype = ctypes.c_int64
     lib.cednerf_distortion_workspace_bytes.argtypes = []
     lib.cednerf_sample_order_workspace_bytes.restype = ctypes.c_int64
@@ -183,7 +201,7 @@ def load() -> ctypes.CDLL:
 def exported_symbols():
     return sorted(list(_SIGNATURES) + ["cednerf_last_error", "cednerf_abi_version", "cednerf_check_device",
                                        "cednerf_scan_workspace_bytes", "cednerf_launch_count", "cednerf_field_saved_bytes",
-                                       "cednerf_field_bwd_workspace_bytes", "cednerf_dp_ctrl_bytes", "cednerf_topk_workspace_bytes", "cednerf_sample_order_workspace_bytes", "cednerf_distortion_workspace_bytes"])
+                                       "cednerf_field_bwd_workspace_bytes", "cednerf_dp_ctrl_bytes", "cednerf_topk_workspace_bytes", "cednerf_sample_order_workspace_bytes", "cednerf_distortion_workspace_bytes", "cednerf_render_round_bytes"])
 
 
 def ptr(t: Optional[torch.Tensor]):

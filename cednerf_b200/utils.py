@@ -160,6 +160,7 @@ def render_image(radiance_field, estimator, rays, near_plane=0.0, far_plane=1e10
 
 _DEVICE_ROUNDS = True   # False: the host-driven rounds below (one host read per round, as the reference does)
 _ROUND_LAG = 4          # rounds the host may run ahead of the newest alive count it has seen
+_ROUND_BY_PARTS = bool(int(__import__("os").environ.get("CEDNERF_ROUND_BY_PARTS", "0")))  # diagnostic: eight calls per round
 
 
 def _render_rounds_gen(max_samples, field, rays, bits, aabbs, res, near, far_plane, step, cone, early_stop_eps,
@@ -211,31 +212,38 @@ def _render_rounds_gen(max_samples, field, rays, bits, aabbs, res, near, far_pla
     max_rounds = (max_samples + min_samples - 1) // min_samples + 1
     import ctypes as _ct
 
+    # everything that is the same for every round of the frame goes into one struct; a round is then ONE library call
+    # (eight launches: count pass, scan, fill from runs, fallback fill, field, compositing, scan, ordered compaction)
+    from . import _lib
+    from ._lib import RenderRound
+
+    rr = RenderRound()
+    for name, t in (("rays_o", o), ("rays_d", d), ("occ_bits", bits), ("aabbs", aabbs_c), ("near_term", near),
+                    ("t_sorted", t_sorted), ("t_indices", t_indices), ("hits", hits), ("state", state), ("total", total),
+                    ("n_samples", n_sm), ("run_t", run_t), ("run_n", run_n), ("n_runs", n_runs), ("occ_coarse", coarse),
+                    ("offsets", offsets), ("totals", totals), ("scan_workspace", ws), ("t_starts", t0), ("t_ends", t1),
+                    ("ray_indices", ridx), ("overflow", overflow), ("timestamps", ts), ("image_deform", images[0]),
+                    ("image_density", images[1]), ("image_colour", images[2]), ("table_f16", table), ("sigma", sigma),
+                    ("rgbs", rgbs), ("colors", rgb), ("opacity", opacity), ("depth", depth), ("alive_flags", flags),
+                    ("positions", pos), ("position_totals", pos_tot)):
+        setattr(rr, name, ptr(t))
+    rr.n_rays, rr.n_levels, rr.resolution, rr.capacity = n, n_levels, res, cap
+    rr.far_const, rr.step_size, rr.cone_angle, rr.early_stop_eps = far_plane, float(step), float(cone), float(early_stop_eps)
+    rr.desc = _ct.pointer(desc)
+    rr.run_cap, rr.k_hint, rr.max_samples, rr.min_samples = run_cap, int(k_hint), int(max_samples), int(min_samples)
+    rr_ref = _ct.byref(rr)
+    list_ptrs = (ptr(lists[0]), ptr(lists[1]))
     call("cednerf_render_round_begin", ptr(state), n, int(max_samples), int(min_samples), None, ptr(total), stream())
     for rnd in range(max_rounds):   # (every later round is begun by the compaction launch that ends its predecessor)
-        cur, nxt = lists[rnd & 1], lists[(rnd + 1) & 1]
         host = ring[rnd % len(ring)]
         host.copy_(state, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
         pending.append((ev, host))
-        call("cednerf_march_round", 0, ptr(o), ptr(d), bound, ptr(bits), ptr(aabbs_c), n_levels, res, ptr(near), far_plane,
-             float(step), float(cone), ptr(t_sorted), ptr(t_indices), ptr(hits), ptr(cur), ptr(state), None, None, None,
-             None, None, ptr(n_sm), ptr(run_t), ptr(run_n), ptr(n_runs), run_cap, ptr(coarse), stream())
-        call("cednerf_exclusive_scan_capped", ptr(n_sm), bound, cap, ptr(offsets), ptr(totals), ptr(ws), stream())
-        call("cednerf_march_fill_runs_round", bound, ptr(offsets), ptr(n_sm), ptr(run_t), ptr(run_n), ptr(n_runs), run_cap,
-             float(step), float(cone), ptr(cur), ptr(state), ptr(t0), ptr(t1), ptr(ridx), ptr(overflow), stream())
-        call("cednerf_march_round", 1, ptr(o), ptr(d), bound, ptr(bits), ptr(aabbs_c), n_levels, res, ptr(near), far_plane,
-             float(step), float(cone), ptr(t_sorted), ptr(t_indices), ptr(hits), ptr(cur), ptr(state), ptr(overflow),
-             ptr(offsets), ptr(t0), ptr(t1), ptr(ridx), None, None, None, None, run_cap, ptr(coarse), stream())
-        call("cednerf_field_fwd", ptr(ridx), ptr(t0), ptr(t1), ptr(o), ptr(d), None, None, ptr(ts), 0, cap, ptr(images[0]),
-             ptr(images[1]), ptr(images[2]), ptr(table), _ct.byref(desc), ptr(sigma), ptr(rgbs), ptr(totals), stream())
-        call("cednerf_render_round_composite", ptr(t0), ptr(t1), ptr(sigma), ptr(rgbs), ptr(offsets), ptr(cur), ptr(state),
-             ptr(n_sm), bound, int(k_hint), float(early_stop_eps), ptr(rgb), ptr(opacity), ptr(depth), ptr(flags), stream())
-        # ordered compaction of the surviving rays: the list stays in pixel order, so a warp's rays stay coherent
-        call("cednerf_exclusive_scan_capped", ptr(flags), bound, n, ptr(pos), ptr(pos_tot), ptr(ws), stream())
-        call("cednerf_render_round_compact", ptr(flags), ptr(pos), ptr(cur), bound, ptr(state), ptr(nxt), n,
-             int(max_samples), int(min_samples), ptr(totals), ptr(total), stream())
+        if _lib._timers is None and not _ROUND_BY_PARTS:
+            call("cednerf_render_round", rr_ref, bound, list_ptrs[rnd & 1], list_ptrs[(rnd + 1) & 1], stream())
+        else:   # bench.py's per-entry-point instrumentation: the same eight launches as separate calls
+            _round_by_parts(rr, bound, list_ptrs[rnd & 1], list_ptrs[(rnd + 1) & 1], desc)
         # look at the oldest state copies that have arrived; never run more than _ROUND_LAG rounds ahead of one
         stop = False
         while pending and (pending[0][0].query() or len(pending) > _ROUND_LAG):
@@ -260,6 +268,31 @@ def _render_rounds_gen(max_samples, field, rays, bits, aabbs, res, near, far_pla
     while not done_ev.query():
         yield
     return int(total_host[0])
+
+
+def _round_by_parts(r, bound, cur, nxt, desc):
+    """cednerf_render_round spelled out as its eight entry points (csrc/render_round.cu), for per-kernel timing."""
+    import ctypes as _ct
+
+    from ._lib import call, stream
+
+    st = stream()
+    call("cednerf_march_round", 0, r.rays_o, r.rays_d, bound, r.occ_bits, r.aabbs, r.n_levels, r.resolution, r.near_term,
+         r.far_const, r.step_size, r.cone_angle, r.t_sorted, r.t_indices, r.hits, cur, r.state, None, None, None, None, None,
+         r.n_samples, r.run_t, r.run_n, r.n_runs, r.run_cap, r.occ_coarse, st)
+    call("cednerf_exclusive_scan_capped", r.n_samples, bound, r.capacity, r.offsets, r.totals, r.scan_workspace, st)
+    call("cednerf_march_fill_runs_round", bound, r.offsets, r.n_samples, r.run_t, r.run_n, r.n_runs, r.run_cap, r.step_size,
+         r.cone_angle, cur, r.state, r.t_starts, r.t_ends, r.ray_indices, r.overflow, st)
+    call("cednerf_march_round", 1, r.rays_o, r.rays_d, bound, r.occ_bits, r.aabbs, r.n_levels, r.resolution, r.near_term,
+         r.far_const, r.step_size, r.cone_angle, r.t_sorted, r.t_indices, r.hits, cur, r.state, r.overflow, r.offsets,
+         r.t_starts, r.t_ends, r.ray_indices, None, None, None, None, r.run_cap, r.occ_coarse, st)
+    call("cednerf_field_fwd", r.ray_indices, r.t_starts, r.t_ends, r.rays_o, r.rays_d, None, None, r.timestamps, 0, r.capacity,
+         r.image_deform, r.image_density, r.image_colour, r.table_f16, _ct.byref(desc), r.sigma, r.rgbs, r.totals, st)
+    call("cednerf_render_round_composite", r.t_starts, r.t_ends, r.sigma, r.rgbs, r.offsets, cur, r.state, r.n_samples, bound,
+         r.k_hint, r.early_stop_eps, r.colors, r.opacity, r.depth, r.alive_flags, st)
+    call("cednerf_exclusive_scan_capped", r.alive_flags, bound, r.n_rays, r.positions, r.position_totals, r.scan_workspace, st)
+    call("cednerf_render_round_compact", r.alive_flags, r.positions, cur, bound, r.state, nxt, r.n_rays, r.max_samples,
+         r.min_samples, r.totals, r.total, st)
 
 
 def _lib_scan_ws(n):

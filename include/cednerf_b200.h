@@ -298,6 +298,56 @@ int cednerf_render_round_compact(const int32_t* alive_flags, const int64_t* posi
                                  int64_t n_bound, int32_t* round_state, int32_t* next_alive, int64_t n_rays,
                                  int max_samples /*> 0: also begin the next round, as cednerf_render_round_begin*/,
                                  int min_samples, const int64_t* round_totals, int64_t* total, void* stream);
+/* One marching round behind one call (the eight launches above, in the order render_image_test needs them): a frame is
+ * 40-220 rounds, and eight calls with ~25 arguments each per round made the host the bound of the interleaved rounds.
+ * Everything that stays the same over the rounds of a frame lives in the struct; `alive` / `next_alive` swap every
+ * round and n_bound (an upper bound of the live part of `alive`) only shrinks. */
+typedef struct CednerfRenderRound {
+  const float* rays_o;
+  const float* rays_d;
+  int64_t n_rays;
+  const uint32_t* occ_bits;
+  const float* aabbs;
+  int n_levels, resolution;
+  float* near_term;
+  float far_const, step_size, cone_angle, early_stop_eps;
+  const float* t_sorted;
+  const int64_t* t_indices;
+  const uint8_t* hits;
+  int32_t* state;
+  int64_t* total;
+  int32_t* n_samples;
+  float* run_t;
+  int32_t* run_n;
+  int32_t* n_runs;
+  const uint32_t* occ_coarse;
+  int64_t capacity;
+  int64_t* offsets;
+  int64_t* totals;
+  void* scan_workspace;
+  float* t_starts;
+  float* t_ends;
+  int64_t* ray_indices;
+  uint8_t* overflow;
+  const float* timestamps;
+  const void* image_deform;
+  const void* image_density;
+  const void* image_colour;
+  const void* table_f16;
+  const CednerfFieldDesc* desc;
+  float* sigma;
+  float* rgbs;
+  float* colors;
+  float* opacity;
+  float* depth;
+  int32_t* alive_flags;
+  int64_t* positions;
+  int64_t* position_totals;
+  int run_cap, k_hint, max_samples, min_samples;
+} CednerfRenderRound;
+int64_t cednerf_render_round_bytes(void);
+int cednerf_render_round(const CednerfRenderRound* round, int64_t n_bound, const int32_t* alive, int32_t* next_alive,
+                         void* stream);
 /* nerfacc.accumulate_along_rays / accumulate_along_rays_ — cednerf/render.py:158-169, cednerf/utils.py:282-299 */
 int cednerf_accumulate_fwd(const float* weights, const float* values /*nullable*/, int n_channels,
                            const int64_t* offsets, int64_t n_samples, int64_t n_rays, float* outputs, int inplace,

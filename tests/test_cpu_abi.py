@@ -51,6 +51,8 @@ def test_ctypes_signatures_match_header():
                 sig += "D"
             elif "CednerfDpSmall" in a:
                 sig += "S"
+            elif "CednerfRenderRound" in a:
+                sig += "R"
             elif a.startswith("uint32_t "):
                 sig += "u"
             elif "*" in a:
@@ -75,6 +77,7 @@ def test_descriptor_structs_match_header_layout():
     assert ctypes.sizeof(_lib.AdamTensors) == 8 + 5 * 8 * 8 + 8 * 8 + 2 * 4 * 8 + 9 * 8
     assert ctypes.sizeof(_lib.DpCtrl) == 8 * 4 + 4 + 4 == _lib.load().cednerf_dp_ctrl_bytes()
     assert ctypes.sizeof(_lib.DpPeers) == 8 + 8 * 8
+    assert ctypes.sizeof(_lib.RenderRound) == _lib.load().cednerf_render_round_bytes() == 344
     # world, rank, grad[8], n_out (+ padding), p32_out[8], p16_out[8], m, v, lo, hi, lr, weight_decay, grad_div (+ padding),
     # grad_mc, p16_mc
     assert ctypes.sizeof(_lib.DpAdam) == 8 + 64 + 8 + 64 + 64 + 16 + 16 + 16 + 16
