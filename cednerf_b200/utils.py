@@ -316,6 +316,19 @@ def render_image_test(max_samples, radiance_field, estimator, rays, near_plane=0
 
 
 @torch.no_grad()
+_FRAME_STREAMS = {}
+
+
+def _frame_streams(k: int):
+    """The side streams frames are interleaved on, kept for the life of the process: the caching allocator pools memory per
+    stream, so fresh streams on every call would re-allocate every per-frame buffer (and strand the old pools)."""
+    dev = torch.cuda.current_device()
+    pool = _FRAME_STREAMS.setdefault(dev, [])
+    while len(pool) < k:
+        pool.append(torch.cuda.Stream(device=dev))
+    return pool[:k]
+
+
 def render_images_test(max_samples, radiance_field, estimator, rays_list, timestamps_list, concurrency: int = 2,
                        on_frame=None, **kwargs):
     """render_image_test for several independent frames (a video: datasets/utils.py:67-112 poses, one timestamp each),
@@ -327,7 +340,7 @@ def render_images_test(max_samples, radiance_field, estimator, rays_list, timest
     n_frames = len(rays_list)
     results = [None] * n_frames
     main = torch.cuda.current_stream()
-    streams = [torch.cuda.Stream() for _ in range(max(1, min(int(concurrency), n_frames)))]
+    streams = _frame_streams(max(1, min(int(concurrency), n_frames)))
     free, active, nxt = list(streams), [], 0
     while active or nxt < n_frames:
         while free and nxt < n_frames:
