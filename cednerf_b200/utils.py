@@ -315,7 +315,6 @@ def render_image_test(max_samples, radiance_field, estimator, rays, near_plane=0
             return fin.value
 
 
-@torch.no_grad()
 _FRAME_STREAMS = {}
 
 
@@ -329,6 +328,7 @@ def _frame_streams(k: int):
     return pool[:k]
 
 
+@torch.no_grad()
 def render_images_test(max_samples, radiance_field, estimator, rays_list, timestamps_list, concurrency: int = 2,
                        on_frame=None, **kwargs):
     """render_image_test for several independent frames (a video: datasets/utils.py:67-112 poses, one timestamp each),
