@@ -23,11 +23,19 @@ Parity status
   algorithms (SURVEY.md Appendix A/B and the in-tree Taichi source) and are the
   only pin that exists.
 
+* ``torch.multinomial`` (the ISG / IST draw of ``datasets/dnerf_3d_video_IS.py:401-418``): PINNED to the real thing -
+  torch is installed here, and ``oracle.dataset_ref.multinomial_without_replacement`` (top-k of weights / Exp(1) draws)
+  equals ``torch.multinomial`` index for index under the same generator state
+  (``tests/test_oracle_golden.py::test_multinomial_restatement_is_torch_multinomial``).
+* ``torch_efficient_distloss`` (the ``-d`` regulariser, not vendored): its O(N) form is pinned to the O(N^2) definition it
+  implements (``test_distortion_restatement_against_its_definition``).
+
 Modules
 -------
 march_oracle.c   plain-C marcher (ray/aabb, boundary sort, traverse_grids), bit-exact contract
 nerfacc_ref.py   ctypes wrapper + OccGridEstimator + volrend (torch, CPU)
 tcnn_ref.py      hash grid, Frequency/SH encodings, fp16 fully-fused-MLP emulation
 taichi_ref.py    the in-tree Taichi HashEncoder variants (3-D f16, 4-D key-frame)
-cednerf_ref.py   DNGPradianceField, rendering, render_image, render_image_test
+cednerf_ref.py   DNGPradianceField, rendering, render_image, render_image_test, distortion
+dataset_ref.py   the training branch of SubjectLoader.fetch_data (importance-sampled batches)
 """
