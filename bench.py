@@ -796,6 +796,19 @@ def run_ours(args):
                                      "dp": s["dp_mode"]}
         line["configs"] = others
         line["config"]["others"] = others
+    try:   # the last ~400 characters of the line: what a truncated log keeps of every configuration
+        cfgs_ = line.get("configs") or {}
+        rnd = line.get("render") or {}
+        line["summary"] = {
+            "n_gpus": world, "metric": line.get("metric"), "value": line.get("value"), "ms_per_step": line.get("ms_per_step"),
+            "e2e": (line.get("e2e") or {}).get("value"), "roofline_frac": (line.get("roofline") or {}).get("frac"),
+            "video_rays_per_s": rnd.get("rays_per_s"), "video_ms_per_frame_per_gpu": rnd.get("ms_per_frame_per_gpu"),
+            "dnerf_ms_per_frame": (cfgs_.get("dnerf") or {}).get("ms_per_frame_per_gpu"),
+            "hypernerf_ms_per_step": (cfgs_.get("hypernerf") or {}).get("ms_per_step"),
+            "dynerf_2p20_rays_per_s": (cfgs_.get("dynerf_2p20") or {}).get("rays_per_s"),
+            "encoder4d_fwd_bwd_frac": [(cfgs_.get("encoder4d") or {}).get("fwd_frac"), (cfgs_.get("encoder4d") or {}).get("bwd_frac")]}
+    except Exception:  # noqa: BLE001 - a summary must never cost the line
+        pass
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
