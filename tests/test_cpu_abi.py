@@ -142,6 +142,17 @@ def test_no_cpu_fallback():
     est = cb.OccGridEstimator([-1, -1, -1, 1, 1, 1], resolution=16, levels=1)
     with pytest.raises(RuntimeError):
         est.mark_invisible_cells(torch.eye(3)[None], torch.eye(4)[None], 8, 8, 0.1)
+    # the importance-sampled batch of the DyNeRF loader and the 4-D encoder: same rule
+    with pytest.raises(RuntimeError):
+        cb.importance.weighted_sample(torch.rand(100), 10)
+    with pytest.raises(RuntimeError):   # host tensors are refused when the sampler is built
+        cb.importance.ImportanceSampler(torch.zeros(2, 8, 8, 3, dtype=torch.uint8), torch.eye(4)[None, :3].repeat(2, 1, 1),
+                                        torch.eye(3), torch.zeros(2, 1), torch.ones(2 * 4 * 4), 2, num_rays=16)
+    with pytest.raises(ValueError):   # argument checks come before any launch
+        cb.importance.ImportanceSampler(torch.zeros(2, 8, 8, 3), torch.eye(4)[None, :3], torch.eye(3), torch.zeros(2, 1),
+                                        torch.ones(32), 2)
+    with pytest.raises(RuntimeError):
+        cb.hash_encoder.HashEncoder4D(max_params=2 ** 8, levels=4, base_res=4.0, max_res=16.0)(torch.rand(5, 4))
 
 
 def test_product_never_imports_the_oracle():
